@@ -1,0 +1,177 @@
+/* turner_b200 -- C ABI of the B200-native path-tracing hot path.
+ *
+ * Drop-in boundary: the body of the reference's render loop, main.cpp:181-236
+ * (inputs: triangles, camera, lights, TracerConfig; output: the per-pixel RGBA
+ * image + Stats). The reference's own plug point is the link-time symbol
+ *   Color trace(const Ray&, KDTreeIntersection&, const std::vector<Light>&, int, const TracerConfig&)
+ * (trace.h:23-25, called from main.cpp:212-214 one ray at a time); a wavefront
+ * GPU renderer cannot live behind a per-ray call, so the boundary sits one level
+ * up. INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * All entry points: plain pointers and sizes, no C++/torch types, return 0 on
+ * success or a negative trn_status; trn_last_error() gives the message of the
+ * last failure on the calling thread. Nothing here aborts. There is NO CPU
+ * fallback: compute entry points fail with TRN_ERR_CUDA when no sm_100 device
+ * is usable.
+ *
+ * Citations are relative to the reference repository root.
+ */
+#ifndef TURNER_B200_H
+#define TURNER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRN_MISS_ID 0x40000000u /* OptionalId miss value, lib/kdtree.h:156-161 */
+
+typedef enum trn_status {
+    TRN_OK = 0,
+    TRN_ERR_INVALID = -1, /* bad argument (the reference would assert, config.h:29-33,119-126) */
+    TRN_ERR_CUDA = -2,    /* CUDA runtime / no usable device */
+    TRN_ERR_NCCL = -3,    /* NCCL failure or libnccl not loadable (multi-GPU only) */
+    TRN_ERR_IO = -4,      /* scene file unreadable / unsupported (.blend loader) */
+    TRN_ERR_LIMIT = -5    /* workload exceeds an implementation limit (stated in the message) */
+} trn_status;
+
+typedef struct trn_scene trn_scene; /* opaque: triangles + kd-tree, host copy + per-device copies */
+
+/* Camera as the render loop uses it: lib/types.h:92-123 (Camera ctor + raster2cam). */
+typedef struct trn_camera {
+    float pos[3];  /* mPosition after `trafo * mPosition` (types.h:101) */
+    float rot[9];  /* aiMatrix3x3 trafo_, row-major a1..c3 (types.h:141) */
+    float delta_x; /* tan(mHorizontalFOV) (types.h:103) */
+    float delta_y; /* delta_x / mAspect   (types.h:104) */
+} trn_camera;
+
+/* Light, lib/types.h:81-84. */
+typedef struct trn_light {
+    float pos[3];
+    float rgba[4];
+} trn_light;
+
+enum { TRN_PATHTRACER = 0 /* pathtracer.cpp:14-102 */, TRN_RAYCASTER = 1 /* raycaster.cpp:7-24 */ };
+
+/* TracerConfig (config.h:103-153) + image size + the sample split. */
+typedef struct trn_render_config {
+    int32_t width;         /* --width (config.h:16) */
+    int32_t height;        /* width / aspect (main.cpp:178-179) */
+    int32_t max_depth;     /* --max-depth > 0 (config.h:107,121) */
+    int32_t mc_samples;    /* --monte-carlo-samples >= 1 here (config.h:117; 0 divides by zero in the reference) */
+    int32_t pixel_samples; /* --pixel-samples >= 1 (config.h:116,124) */
+    int32_t integrator;    /* TRN_PATHTRACER | TRN_RAYCASTER */
+    float bg_rgba[4];      /* --background, alpha 1 (config.h:45-60) */
+    float max_visibility;  /* raycaster only (config.h:110) */
+    int32_t num_lights;    /* 0 or 1 (main.cpp:123) */
+    trn_light light;
+    uint64_t seed;         /* run seed of the counter-seeded hemisphere streams (DESIGN.md "RNG") */
+    /* Sample split (multi-GPU): this call renders pixel samples
+     * i = sample_begin, sample_begin + sample_stride, ... < pixel_samples. 0/1 = all. */
+    int32_t sample_begin;
+    int32_t sample_stride;
+} trn_render_config;
+
+typedef struct trn_stats {
+    uint64_t rays;        /* Stats::num_rays: trace() calls that pass the depth check (pathtracer.cpp:17-21) */
+    uint64_t prim_rays;   /* Stats::num_prim_rays (main.cpp:211) */
+    uint64_t shadow_rays; /* shadow queries (pathtracer.cpp:49-50), not counted by the reference */
+    uint64_t launches;    /* kernels launched by this call */
+    double ms_render;     /* device time of the call (CUDA events), ms; host-buffer variants include the D2H copy */
+    double ms_trace;      /* summed device time of the closest-hit traversal kernel (only when profiling is on) */
+    double ms_shadow;     /* ... of the any-hit traversal kernel */
+    double ms_shade;      /* ... of the shade/bounce kernel */
+    double ms_other;      /* ... raygen + bookkeeping */
+} trn_stats;
+
+typedef struct trn_scene_info {
+    uint64_t num_triangles; /* Stats::num_triangles */
+    uint64_t num_nodes;     /* KDTree::num_nodes(), lib/kdtree.h:219 */
+    uint64_t kdtree_height; /* KDTree::height(), lib/kdtree.h:197-218 */
+    uint64_t num_leaf_refs; /* triangle references in leaves */
+    float box[6];           /* KDTree::box(): min xyz, max xyz */
+    double build_ms;        /* host kd-tree build time */
+    double upload_ms;       /* layout + H2D */
+} trn_scene_info;
+
+const char* trn_last_error(void);
+/* number of usable CUDA devices (0 when there is none; never fails) */
+int32_t trn_device_count(void);
+
+/* ---- scene: replaces `KDTree tree(triangles_from_scene(scene))`, main.cpp:25-82,156-157.
+ * verts/normals: n*9 floats (v0 v1 v2 / n0 n1 n2, world space), diffuse: n*4 rgba. Copies its inputs.
+ * Builds the kd-tree on the host (same SAH build as lib/kdtree.cpp:124-467, node-for-node) and keeps a host
+ * copy; device copies are created lazily per device on first use. */
+int32_t trn_scene_create(const float* verts, const float* normals, const float* diffuse, uint32_t n, trn_scene** out);
+void trn_scene_destroy(trn_scene* scene);
+int32_t trn_scene_get_info(const trn_scene* scene, trn_scene_info* info);
+/* the flattened tree in the reference's FlatNode encoding (lib/kdtree.h:62-154), num_nodes uint64 values */
+int32_t trn_scene_get_nodes(const trn_scene* scene, uint64_t* out_nodes);
+
+/* ---- closest hit for arbitrary rays: replaces KDTreeIntersection::intersect(ray, r, a, b),
+ * lib/kdtree.cpp:515-578. Host buffers: origins/dirs n*3 floats in; ids n (TRN_MISS_ID on miss), rst n*3 out. */
+int32_t trn_intersect(trn_scene* scene, int32_t device, const float* origins, const float* dirs, uint64_t n,
+                      uint32_t* ids, float* rst);
+
+/* ---- primary-hit parity hook (BASELINE config 2): the closest hit of every primary ray the render loop would
+ * shoot (main.cpp:201-214), index (y*width + x)*pixel_samples + i. ids / rst (3 per ray) are host buffers. */
+int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
+                         uint32_t* ids, float* rst);
+
+/* ---- render: replaces the loop main.cpp:187-236 up to (not including) `/= pps`, exposure and gamma.
+ * out_rgba_sum: width*height*4 floats, HOST memory, per-pixel SUM over the rendered pixel samples of trace().
+ * Blocking; includes the device->host copy. */
+int32_t trn_render(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
+                   float* out_rgba_sum, trn_stats* stats);
+
+/* Same, but ADDS into a caller-owned DEVICE buffer (width*height*4 floats on `device`) on the given CUDA stream
+ * (cudaStream_t passed as void*; NULL = legacy default stream) and returns once the work is enqueued and the
+ * host-side bookkeeping is done; the caller synchronises. For callers that own device memory / streams / a
+ * process-per-GPU reduce (torch.distributed). stats->ms_render is then measured with events on that stream and
+ * the call blocks on the last event only if `stats` is non-NULL. */
+int32_t trn_render_device(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
+                          float* d_accum_rgba, void* cuda_stream, trn_stats* stats);
+
+/* Single-process multi-GPU render (sample split over `num_devices` GPUs, scene replicated, one ncclReduce(sum)
+ * of the float accumulation buffers onto devices[0]). libnccl is dlopen()ed on first use. */
+int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_devices, const trn_camera* cam,
+                         const trn_render_config* cfg, float* out_rgba_sum, trn_stats* stats);
+
+/* per-kernel timing inside trn_render* (adds an event pair per launch); off by default */
+void trn_set_profiling(int32_t enabled);
+
+/* ---- host-side pieces of the reference's main() that the CLI keeps (no GPU involved) ------------------- */
+
+/* Camera(trafo, aiCamera) + height, lib/types.h:92-105, main.cpp:109-119,178-179.
+ * trafo4x4: the camera node's transformation, row-major a1..d4. */
+int32_t trn_camera_setup(const float* trafo4x4, float hfov, float aspect, int32_t width, trn_camera* cam,
+                         int32_t* height);
+/* image(x,y) /= pps; exposure; gamma -- main.cpp:216-223, lib/effects.h:15-48. in/out: npix*4 floats. */
+int32_t trn_tonemap(const float* rgba_sum, uint64_t npix, int32_t pixel_samples, float exposure,
+                    int32_t gamma_enabled, float inverse_gamma, float* rgba_out);
+/* operator<<(ostream, Image) + std::endl, lib/raster.h:79-100, main.cpp:242. Returns the byte count needed;
+ * writes at most cap bytes. */
+uint64_t trn_write_p3(const float* rgba, int32_t width, int32_t height, char* buf, uint64_t cap);
+
+/* .blend scene file -> triangle arrays + camera + light (replaces Assimp::Importer::ReadFile + triangles_from_scene,
+ * main.cpp:25-82,96-136). Arrays are malloc()ed; release with trn_loaded_scene_free. */
+typedef struct trn_loaded_scene {
+    uint32_t num_triangles;
+    float* verts;   /* n*9 */
+    float* normals; /* n*9 */
+    float* diffuse; /* n*4 */
+    int32_t has_camera;
+    float cam_trafo4x4[16];
+    float cam_hfov;
+    float cam_aspect; /* 0 when the file does not fix one (Blender importer leaves mAspect = 0) */
+    int32_t num_lights;
+    trn_light light;
+} trn_loaded_scene;
+int32_t trn_load_blend(const char* path, trn_loaded_scene* out);
+void trn_loaded_scene_free(trn_loaded_scene* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TURNER_B200_H */

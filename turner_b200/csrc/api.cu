@@ -1,0 +1,784 @@
+// C ABI (include/turner_b200.h) + the host side of the wavefront: device scene
+// layout, wave buffers, the depth-by-depth launch schedule, sample-split
+// multi-GPU. No CPU compute path exists here: every compute entry point needs a
+// CUDA device and fails with TRN_ERR_CUDA otherwise.
+#include "../../include/turner_b200.h"
+
+#include "host_util.h"
+#include "kdtree_build.h"
+#include "kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace trn {
+
+thread_local std::string g_last_error;
+static int g_profiling = 0;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t e__ = (expr);                                                                               \
+        if (e__ != cudaSuccess)                                                                                 \
+            return fail(TRN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
+                                          std::to_string(__LINE__) + ")");                                      \
+    } while (0)
+
+// ------------------------------------------------------------ per-device state
+struct DeviceScene {
+    int device = -1;
+    DevScene dev{};
+    void* d_nodes = nullptr;
+    void* d_refs = nullptr;
+    void* d_isect = nullptr;
+    void* d_shade = nullptr;
+    // work buffers (sized lazily, reused across calls)
+    uint64_t wave_cap = 0;        // rays per wave buffer
+    std::vector<RayWave> waves;   // one per depth level in use
+    std::vector<void*> wave_mem;  // backing allocations of `waves`
+    ShadowWave shadow{};
+    void* shadow_mem = nullptr;
+    uint4* d_hits = nullptr;
+    WaveCounters* d_counters = nullptr;  // ring of counters, one per (launch) use
+    WaveCounters* h_counters = nullptr;  // pinned mirror
+    uint32_t counter_slots = 0;
+    unsigned long long* d_hitcount = nullptr;
+    float2* d_jitter = nullptr;
+    size_t jitter_elems = 0;
+    int jitter_w = 0, jitter_pps = 0;
+    float4* d_accum = nullptr; // internal accumulation buffer for host-buffer renders
+    size_t accum_pixels = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_sync = nullptr;
+    double upload_ms = 0;
+
+    void release() {
+        if (device < 0) return;
+        cudaSetDevice(device);
+        cudaFree(d_nodes);
+        cudaFree(d_refs);
+        cudaFree(d_isect);
+        cudaFree(d_shade);
+        for (void* p : wave_mem) cudaFree(p);
+        cudaFree(shadow_mem);
+        cudaFree(d_hits);
+        cudaFree(d_counters);
+        if (h_counters) cudaFreeHost(h_counters);
+        cudaFree(d_hitcount);
+        cudaFree(d_jitter);
+        cudaFree(d_accum);
+        if (ev_sync) cudaEventDestroy(ev_sync);
+        if (stream) cudaStreamDestroy(stream);
+        device = -1;
+    }
+};
+
+} // namespace trn
+
+struct trn_scene {
+    trn::HostTriangles tris;
+    trn::KdTree tree;
+    // device layout, built once on the host
+    std::vector<uint2> gpu_nodes;
+    std::vector<uint32_t> leaf_refs;
+    std::map<int, std::unique_ptr<trn::DeviceScene>> devices;
+    std::mutex mu;
+};
+
+namespace trn {
+
+// Rewrite the reference-format node array for the GPU: same indexing (so `right` links stay
+// valid), but the head of every leaf run becomes (first ref offset, count<<2 | 3) into a flat
+// triangle-reference list, so a leaf costs one 8-byte node load + `count` 4-byte id loads.
+static void make_gpu_layout(trn_scene& sc) {
+    const auto& nodes = sc.tree.nodes;
+    sc.gpu_nodes.resize(nodes.size());
+    for (size_t i = 0; i < nodes.size(); ++i)
+        sc.gpu_nodes[i] = make_uint2(static_cast<uint32_t>(nodes[i] >> 32), static_cast<uint32_t>(nodes[i]));
+    sc.leaf_refs.clear();
+    sc.leaf_refs.reserve(sc.tree.num_leaf_refs);
+    std::vector<uint32_t> stack;
+    stack.push_back(0);
+    while (!stack.empty()) {
+        uint32_t idx = stack.back();
+        stack.pop_back();
+        uint64_t n = nodes[idx];
+        if ((n & 3) != 3) {
+            stack.push_back(static_cast<uint32_t>(n) >> 2);
+            stack.push_back(idx + 1);
+            continue;
+        }
+        const uint32_t first = static_cast<uint32_t>(sc.leaf_refs.size());
+        uint32_t count = 0;
+        for (uint32_t k = idx; (nodes[k] & 3) == 3; ++k) { // lib/kdtree.cpp:599-605
+            sc.leaf_refs.push_back(static_cast<uint32_t>(nodes[k] >> 32));
+            ++count;
+            if (static_cast<uint32_t>(nodes[k]) == 0xFFFFFFFFu) break;
+            sc.leaf_refs.push_back(static_cast<uint32_t>(nodes[k] & 0xFFFFFFFFu) >> 2);
+            ++count;
+        }
+        sc.gpu_nodes[idx] = make_uint2(first, (count << 2) | 3u);
+    }
+}
+
+static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(TRN_ERR_CUDA, "no CUDA device available (turner_b200 has no CPU fallback)");
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= ndev) return fail(TRN_ERR_INVALID, "device ordinal out of range");
+    std::lock_guard<std::mutex> lock(sc->mu);
+    auto it = sc->devices.find(device);
+    if (it != sc->devices.end()) {
+        *out = it->second.get();
+        return TRN_OK;
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    CUDA_TRY(cudaSetDevice(device));
+    std::unique_ptr<DeviceScene> ds(new DeviceScene);
+    ds->device = device;
+    auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    };
+    CUDA_TRY(up(&ds->d_nodes, sc->gpu_nodes.data(), sc->gpu_nodes.size() * sizeof(uint2)));
+    CUDA_TRY(up(&ds->d_refs, sc->leaf_refs.data(), sc->leaf_refs.size() * sizeof(uint32_t)));
+    CUDA_TRY(up(&ds->d_isect, sc->tris.isect.data(), sc->tris.isect.size() * sizeof(float)));
+    CUDA_TRY(up(&ds->d_shade, sc->tris.shade.data(), sc->tris.shade.size() * sizeof(float)));
+    ds->dev.nodes = static_cast<const uint2*>(ds->d_nodes);
+    ds->dev.leaf_refs = static_cast<const uint32_t*>(ds->d_refs);
+    ds->dev.isect = static_cast<const float4*>(ds->d_isect);
+    ds->dev.shade = static_cast<const float4*>(ds->d_shade);
+    for (int c = 0; c < 3; ++c) {
+        ds->dev.lo[c] = sc->tree.box[c];
+        ds->dev.hi[c] = sc->tree.box[3 + c];
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_sync, cudaEventDisableTiming));
+    ds->counter_slots = 4096;
+    CUDA_TRY(cudaMalloc(&ds->d_counters, ds->counter_slots * sizeof(WaveCounters)));
+    CUDA_TRY(cudaMallocHost(&ds->h_counters, ds->counter_slots * sizeof(WaveCounters)));
+    CUDA_TRY(cudaMalloc(&ds->d_hitcount, sizeof(unsigned long long)));
+    ds->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    *out = ds.get();
+    sc->devices[device] = std::move(ds);
+    return TRN_OK;
+}
+
+static uint64_t env_u64(const char* name, uint64_t dflt) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return dflt;
+    return std::strtoull(v, nullptr, 10);
+}
+
+// wave buffers: `levels` ray waves of `cap` rays + one shadow wave + one hit buffer
+static int ensure_waves(DeviceScene* ds, uint64_t cap, int levels) {
+    if (ds->wave_cap != cap) {
+        for (void* p : ds->wave_mem) cudaFree(p);
+        ds->wave_mem.clear();
+        ds->waves.clear();
+        cudaFree(ds->shadow_mem);
+        ds->shadow_mem = nullptr;
+        cudaFree(ds->d_hits);
+        ds->d_hits = nullptr;
+        ds->wave_cap = cap;
+    }
+    if (!ds->d_hits) CUDA_TRY(cudaMalloc(&ds->d_hits, cap * sizeof(uint4)));
+    if (!ds->shadow_mem) {
+        CUDA_TRY(cudaMalloc(&ds->shadow_mem, cap * 3 * sizeof(float4)));
+        float4* p = static_cast<float4*>(ds->shadow_mem);
+        ds->shadow = ShadowWave{p, p + cap, p + 2 * cap};
+    }
+    while (static_cast<int>(ds->waves.size()) < levels) {
+        void* mem = nullptr;
+        CUDA_TRY(cudaMalloc(&mem, cap * 3 * sizeof(float4)));
+        float4* p = static_cast<float4*>(mem);
+        ds->wave_mem.push_back(mem);
+        ds->waves.push_back(RayWave{p, p + cap, p + 2 * cap});
+    }
+    return TRN_OK;
+}
+
+// the reference's per-row jitter stream (main.cpp:201-206): xorshift64star<float>(42), two draws per
+// pixel sample, restarted every row -> one [width][pps] table of (dx, dy)
+static int ensure_jitter(DeviceScene* ds, int width, int pps) {
+    if (ds->d_jitter && ds->jitter_w == width && ds->jitter_pps == pps) return TRN_OK;
+    cudaFree(ds->d_jitter);
+    ds->d_jitter = nullptr;
+    std::vector<float2> tab(static_cast<size_t>(width) * pps);
+    uint64_t s = 42;
+    auto next = [&]() {
+        s ^= s >> 12;
+        s ^= s << 25;
+        s ^= s >> 27;
+        uint64_t v = s * 2685821657736338717ULL;
+        return std::ldexp(static_cast<float>(v & 0xFFFFFFull), -24);
+    };
+    for (size_t k = 0; k < tab.size(); ++k) {
+        float dx = next();
+        float dy = next();
+        tab[k] = make_float2(dx, dy);
+    }
+    CUDA_TRY(cudaMalloc(&ds->d_jitter, tab.size() * sizeof(float2)));
+    CUDA_TRY(cudaMemcpy(ds->d_jitter, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    ds->jitter_w = width;
+    ds->jitter_pps = pps;
+    return TRN_OK;
+}
+
+static int validate(const trn_camera* cam, const trn_render_config* cfg) {
+    if (!cam || !cfg) return fail(TRN_ERR_INVALID, "null camera/config");
+    if (cfg->width < 1 || cfg->height < 1) return fail(TRN_ERR_INVALID, "width/height must be >= 1");
+    if (cfg->pixel_samples < 1) return fail(TRN_ERR_INVALID, "pixel_samples must be >= 1 (config.h:124)");
+    if (cfg->integrator != TRN_PATHTRACER && cfg->integrator != TRN_RAYCASTER)
+        return fail(TRN_ERR_INVALID, "unknown integrator");
+    if (cfg->integrator == TRN_PATHTRACER) {
+        if (cfg->max_depth < 1) return fail(TRN_ERR_INVALID, "max_depth must be > 0 (config.h:121)");
+        if (cfg->mc_samples < 1) return fail(TRN_ERR_INVALID, "mc_samples must be >= 1");
+        double nodes = 0, p = 1;
+        for (int d = 0; d <= cfg->max_depth; ++d) {
+            nodes += p;
+            p *= cfg->mc_samples;
+        }
+        if (nodes >= 4294967295.0)
+            return fail(TRN_ERR_LIMIT, "ray tree has >= 2^32 nodes per primary sample (sum of mc_samples^d, d<=max_depth)");
+    }
+    if (cfg->num_lights < 0 || cfg->num_lights > 1) return fail(TRN_ERR_INVALID, "0 or 1 lights (main.cpp:123)");
+    if (cfg->sample_stride < 0 || cfg->sample_begin < 0) return fail(TRN_ERR_INVALID, "bad sample split");
+    if (static_cast<double>(cfg->width) * cfg->height >= 4294967295.0) return fail(TRN_ERR_LIMIT, "more than 2^32 pixels");
+    return TRN_OK;
+}
+
+static FrameParams make_frame(const trn_camera* cam, const trn_render_config* cfg) {
+    FrameParams fp{};
+    std::memcpy(fp.cam.pos, cam->pos, sizeof fp.cam.pos);
+    std::memcpy(fp.cam.rot, cam->rot, sizeof fp.cam.rot);
+    fp.cam.delta_x = cam->delta_x;
+    fp.cam.delta_y = cam->delta_y;
+    fp.width = cfg->width;
+    fp.height = cfg->height;
+    fp.pps = cfg->pixel_samples;
+    fp.sample_stride = cfg->sample_stride > 0 ? cfg->sample_stride : 1;
+    fp.sample_begin = cfg->sample_begin;
+    fp.n_local = fp.sample_begin < fp.pps ? (fp.pps - fp.sample_begin + fp.sample_stride - 1) / fp.sample_stride : 0;
+    fp.mc_samples = cfg->mc_samples;
+    fp.max_depth = cfg->max_depth;
+    std::memcpy(fp.bg, cfg->bg_rgba, sizeof fp.bg);
+    fp.has_light = cfg->num_lights;
+    std::memcpy(fp.light_pos, cfg->light.pos, sizeof fp.light_pos);
+    std::memcpy(fp.light_rgba, cfg->light.rgba, sizeof fp.light_rgba);
+    fp.max_visibility = cfg->max_visibility;
+    fp.seed = cfg->seed;
+    return fp;
+}
+
+struct KernelTimer {
+    cudaStream_t stream;
+    bool on;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+    explicit KernelTimer(cudaStream_t s) : stream(s), on(g_profiling != 0) {}
+    void begin(int kind) {
+        if (!on) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, stream);
+        spans.push_back({kind, {a, b}});
+    }
+    void end() {
+        if (!on) return;
+        cudaEventRecord(spans.back().second.second, stream);
+    }
+    void collect(trn_stats* st) {
+        for (auto& s : spans) {
+            float ms = 0;
+            cudaEventSynchronize(s.second.second);
+            cudaEventElapsedTime(&ms, s.second.first, s.second.second);
+            if (st) {
+                if (s.first == 0) st->ms_trace += ms;
+                else if (s.first == 1) st->ms_shadow += ms;
+                else if (s.first == 2) st->ms_shade += ms;
+                else st->ms_other += ms;
+            }
+            cudaEventDestroy(s.second.first);
+            cudaEventDestroy(s.second.second);
+        }
+        spans.clear();
+    }
+};
+
+static inline unsigned blocks_for(uint64_t n, unsigned bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
+
+// The wavefront over one device: primaries in batches; per batch a depth-first walk over waves.
+// A wave at depth d is processed in chunks small enough that its children (<= m per ray) fit the next
+// wave buffer, so arbitrary (m, max_depth) work with fixed memory. After each shade launch the wave
+// counters come back to the host over a pinned buffer while the shadow kernel of the same chunk is
+// already running, so the GPU does not idle on the round trip.
+struct Renderer {
+    DeviceScene* ds;
+    FrameParams fp;
+    int integrator;
+    float4* acc;
+    cudaStream_t stream;
+    KernelTimer timer;
+    uint64_t rays = 0, prim = 0, shadow = 0, launches = 0;
+    uint32_t slot = 0;
+    uint64_t cap;
+
+    Renderer(DeviceScene* d, const FrameParams& f, int integ, float4* a, cudaStream_t s)
+        : ds(d), fp(f), integrator(integ), acc(a), stream(s), timer(s), cap(d->wave_cap) {}
+
+    int next_slot(uint32_t* out) {
+        if (slot >= ds->counter_slots) { // recycle the ring: everything before has been consumed (host synced on each)
+            slot = 0;
+        }
+        if (slot == 0) CUDA_TRY(cudaMemsetAsync(ds->d_counters, 0, ds->counter_slots * sizeof(WaveCounters), stream));
+        *out = slot++;
+        return TRN_OK;
+    }
+
+    int process(int depth, const RayWave& wave, uint32_t count, uint64_t first_local_index) {
+        const int m = fp.mc_samples;
+        const bool spawn = integrator == TRN_PATHTRACER && depth < fp.max_depth;
+        const uint64_t chunk_max = spawn ? std::max<uint64_t>(1, cap / static_cast<uint64_t>(m)) : cap;
+        for (uint64_t off = 0; off < count; off += chunk_max) {
+            const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(chunk_max, count - off));
+            RayWave w{wave.a + off, wave.b + off, wave.T + off};
+            timer.begin(0);
+            trace_closest_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits);
+            timer.end();
+            ++launches;
+            if (integrator == TRN_RAYCASTER) {
+                timer.begin(2);
+                shade_raycast_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(ds->dev, fp, first_local_index, w, ds->d_hits, n,
+                                                                            ds->d_hitcount, acc);
+                timer.end();
+                ++launches;
+                continue;
+            }
+            rays += n;
+            uint32_t cs;
+            int rc = next_slot(&cs);
+            if (rc) return rc;
+            RayWave next = spawn ? ds->waves[depth + 1] : RayWave{nullptr, nullptr, nullptr};
+            timer.begin(2);
+            shade_bounce_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(ds->dev, fp, first_local_index, w, ds->d_hits, n, depth, next,
+                                                                       ds->shadow, ds->d_counters + cs, acc);
+            timer.end();
+            ++launches;
+            CUDA_TRY(cudaMemcpyAsync(ds->h_counters + cs, ds->d_counters + cs, sizeof(WaveCounters), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaEventRecord(ds->ev_sync, stream));
+            if (fp.has_light) {
+                timer.begin(1);
+                trace_shadow_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_counters + cs, acc);
+                timer.end();
+                ++launches;
+            }
+            CUDA_TRY(cudaEventSynchronize(ds->ev_sync));
+            const WaveCounters wc = ds->h_counters[cs];
+            shadow += wc.shadow_count;
+            if (spawn && wc.next_count) {
+                rc = process(depth + 1, next, wc.next_count, first_local_index);
+                if (rc) return rc;
+            }
+        }
+        return TRN_OK;
+    }
+
+    int run() {
+        const uint64_t total = static_cast<uint64_t>(fp.width) * fp.height * static_cast<uint64_t>(fp.n_local);
+        if (integrator == TRN_RAYCASTER) CUDA_TRY(cudaMemsetAsync(ds->d_hitcount, 0, sizeof(unsigned long long), stream));
+        // primaries per batch: as many as fit one wave
+        const uint64_t batch = cap;
+        for (uint64_t first = 0; first < total; first += batch) {
+            const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(batch, total - first));
+            timer.begin(3);
+            raygen_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(fp, ds->d_jitter, first, n, ds->waves[0]);
+            timer.end();
+            ++launches;
+            prim += n;
+            int rc = process(0, ds->waves[0], n, first);
+            if (rc) return rc;
+        }
+        if (integrator == TRN_RAYCASTER) {
+            unsigned long long hc = 0;
+            CUDA_TRY(cudaMemcpyAsync(&hc, ds->d_hitcount, sizeof hc, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            rays = hc; // raycaster.cpp:17 counts a ray only when it hits
+        }
+        CUDA_TRY(cudaGetLastError());
+        return TRN_OK;
+    }
+};
+
+static int render_on_device(trn_scene* scene, int device, const trn_camera* cam, const trn_render_config* cfg,
+                            float4* d_accum, cudaStream_t user_stream, bool use_user_stream, trn_stats* stats,
+                            DeviceScene** ds_out) {
+    int rc = validate(cam, cfg);
+    if (rc) return rc;
+    DeviceScene* ds = nullptr;
+    rc = get_device_scene(scene, device, &ds);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ds->device));
+    if (ds_out) *ds_out = ds;
+    FrameParams fp = make_frame(cam, cfg);
+    const int levels = cfg->integrator == TRN_PATHTRACER ? cfg->max_depth + 1 : 1;
+    const uint64_t cap = env_u64("TRN_WAVE_CAP", 16ull << 20);
+    rc = ensure_waves(ds, cap, levels);
+    if (rc) return rc;
+    rc = ensure_jitter(ds, cfg->width, cfg->pixel_samples);
+    if (rc) return rc;
+    cudaStream_t stream = use_user_stream ? user_stream : ds->stream;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        CUDA_TRY(cudaEventRecord(e0, stream));
+    }
+    Renderer r(ds, fp, cfg->integrator, d_accum, stream);
+    rc = r.run();
+    if (stats) {
+        cudaEventRecord(e1, stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        stats->ms_render = ms;
+        stats->rays = r.rays;
+        stats->prim_rays = r.prim;
+        stats->shadow_rays = r.shadow;
+        stats->launches = r.launches;
+        r.timer.collect(stats);
+    } else {
+        r.timer.collect(nullptr);
+    }
+    return rc;
+}
+
+static int ensure_accum(DeviceScene* ds, size_t pixels) {
+    if (ds->accum_pixels < pixels) {
+        cudaFree(ds->d_accum);
+        ds->d_accum = nullptr;
+        CUDA_TRY(cudaMalloc(&ds->d_accum, pixels * sizeof(float4)));
+        ds->accum_pixels = pixels;
+    }
+    return TRN_OK;
+}
+
+// ------------------------------------------------------------------ NCCL (dlopen)
+struct NcclApi {
+    void* lib = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+static int load_nccl(NcclApi& api) {
+    const char* names[] = {std::getenv("TRN_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        if (!n || !*n) continue;
+        api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) return fail(TRN_ERR_NCCL, std::string("cannot dlopen libnccl: ") + dlerror());
+    api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(dlsym(api.lib, "ncclCommInitAll"));
+    api.Reduce = reinterpret_cast<decltype(api.Reduce)>(dlsym(api.lib, "ncclReduce"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.lib, "ncclCommDestroy"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(api.lib, "ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(api.lib, "ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
+    if (!api.CommInitAll || !api.Reduce || !api.CommDestroy || !api.GroupStart || !api.GroupEnd)
+        return fail(TRN_ERR_NCCL, "libnccl lacks a required symbol");
+    return TRN_OK;
+}
+
+} // namespace trn
+
+// =========================================================================== C ABI
+using namespace trn;
+
+extern "C" {
+
+const char* trn_last_error(void) { return g_last_error.c_str(); }
+
+int32_t trn_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void trn_set_profiling(int32_t enabled) { g_profiling = enabled; }
+
+int32_t trn_scene_create(const float* verts, const float* normals, const float* diffuse, uint32_t n, trn_scene** out) {
+    if (!verts || !normals || !diffuse || !out) return fail(TRN_ERR_INVALID, "null argument");
+    if (n == 0) return fail(TRN_ERR_INVALID, "scene needs at least one triangle (lib/kdtree.cpp:475)");
+    if (n >= TRN_MISS_ID) return fail(TRN_ERR_LIMIT, "triangle count must be < 2^30 (lib/kdtree.cpp:476)");
+    for (size_t i = 0; i < size_t(n) * 9; ++i)
+        if (!std::isfinite(verts[i])) return fail(TRN_ERR_INVALID, "non-finite vertex coordinate");
+    std::unique_ptr<trn_scene> sc(new trn_scene);
+    precompute_triangles(verts, normals, diffuse, n, sc->tris);
+    build_kdtree(sc->tris, sc->tree, static_cast<int>(env_u64("TRN_BUILD_THREADS", 0)));
+    if (sc->tree.height + 1 > static_cast<uint64_t>(kStackDepth))
+        return fail(TRN_ERR_LIMIT, "kd-tree height " + std::to_string(sc->tree.height) + " exceeds the traversal stack (" +
+                                       std::to_string(kStackDepth) + ")");
+    make_gpu_layout(*sc);
+    *out = sc.release();
+    return TRN_OK;
+}
+
+void trn_scene_destroy(trn_scene* scene) {
+    if (!scene) return;
+    for (auto& kv : scene->devices) kv.second->release();
+    delete scene;
+}
+
+int32_t trn_scene_get_info(const trn_scene* scene, trn_scene_info* info) {
+    if (!scene || !info) return fail(TRN_ERR_INVALID, "null argument");
+    info->num_triangles = scene->tris.count;
+    info->num_nodes = scene->tree.nodes.size();
+    info->kdtree_height = scene->tree.height;
+    info->num_leaf_refs = scene->tree.num_leaf_refs;
+    std::memcpy(info->box, scene->tree.box, sizeof info->box);
+    info->build_ms = scene->tree.build_ms;
+    info->upload_ms = 0;
+    for (auto& kv : scene->devices) info->upload_ms += kv.second->upload_ms;
+    return TRN_OK;
+}
+
+int32_t trn_scene_get_nodes(const trn_scene* scene, uint64_t* out_nodes) {
+    if (!scene || !out_nodes) return fail(TRN_ERR_INVALID, "null argument");
+    std::memcpy(out_nodes, scene->tree.nodes.data(), scene->tree.nodes.size() * sizeof(uint64_t));
+    return TRN_OK;
+}
+
+int32_t trn_intersect(trn_scene* scene, int32_t device, const float* origins, const float* dirs, uint64_t n,
+                      uint32_t* ids, float* rst) {
+    if (!scene || !origins || !dirs || !ids || !rst) return fail(TRN_ERR_INVALID, "null argument");
+    DeviceScene* ds = nullptr;
+    int rc = get_device_scene(scene, device, &ds);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ds->device));
+    const uint64_t chunk = 8ull << 20;
+    float *d_o = nullptr, *d_d = nullptr, *d_rst = nullptr;
+    uint4* d_h = nullptr;
+    uint32_t* d_ids = nullptr;
+    const uint64_t cn = std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1));
+    CUDA_TRY(cudaMalloc(&d_o, cn * 12));
+    CUDA_TRY(cudaMalloc(&d_d, cn * 12));
+    CUDA_TRY(cudaMalloc(&d_rst, cn * 12));
+    CUDA_TRY(cudaMalloc(&d_h, cn * 16));
+    CUDA_TRY(cudaMalloc(&d_ids, cn * 4));
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint32_t c = static_cast<uint32_t>(std::min<uint64_t>(chunk, n - off));
+        CUDA_TRY(cudaMemcpyAsync(d_o, origins + 3 * off, size_t(c) * 12, cudaMemcpyHostToDevice, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_d, dirs + 3 * off, size_t(c) * 12, cudaMemcpyHostToDevice, ds->stream));
+        trace_closest_plain_kernel<<<blocks_for(c, 128), 128, 0, ds->stream>>>(ds->dev, d_o, d_d, c, d_h);
+        unpack_hits_kernel<<<blocks_for(c, 256), 256, 0, ds->stream>>>(d_h, c, d_ids, d_rst);
+        CUDA_TRY(cudaMemcpyAsync(ids + off, d_ids, size_t(c) * 4, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(rst + 3 * off, d_rst, size_t(c) * 12, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaStreamSynchronize(ds->stream));
+    }
+    CUDA_TRY(cudaGetLastError());
+    cudaFree(d_o);
+    cudaFree(d_d);
+    cudaFree(d_rst);
+    cudaFree(d_h);
+    cudaFree(d_ids);
+    return TRN_OK;
+}
+
+int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
+                         uint32_t* ids, float* rst) {
+    if (!scene || !ids || !rst) return fail(TRN_ERR_INVALID, "null argument");
+    int rc = validate(cam, cfg);
+    if (rc) return rc;
+    DeviceScene* ds = nullptr;
+    rc = get_device_scene(scene, device, &ds);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ds->device));
+    trn_render_config c2 = *cfg;
+    c2.sample_begin = 0;
+    c2.sample_stride = 1;
+    FrameParams fp = make_frame(cam, &c2);
+    const uint64_t cap = env_u64("TRN_WAVE_CAP", 16ull << 20);
+    rc = ensure_waves(ds, cap, 1);
+    if (rc) return rc;
+    rc = ensure_jitter(ds, cfg->width, cfg->pixel_samples);
+    if (rc) return rc;
+    uint32_t* d_ids = nullptr;
+    float* d_rst = nullptr;
+    const uint64_t total = static_cast<uint64_t>(fp.width) * fp.height * static_cast<uint64_t>(fp.n_local);
+    const uint64_t cn = std::min<uint64_t>(cap, total);
+    CUDA_TRY(cudaMalloc(&d_ids, cn * 4));
+    CUDA_TRY(cudaMalloc(&d_rst, cn * 12));
+    for (uint64_t first = 0; first < total; first += cap) {
+        const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(cap, total - first));
+        raygen_kernel<<<blocks_for(n, 256), 256, 0, ds->stream>>>(fp, ds->d_jitter, first, n, ds->waves[0]);
+        trace_closest_kernel<<<blocks_for(n, 128), 128, 0, ds->stream>>>(ds->dev, ds->waves[0].a, ds->waves[0].b, n, ds->d_hits);
+        unpack_hits_kernel<<<blocks_for(n, 256), 256, 0, ds->stream>>>(ds->d_hits, n, d_ids, d_rst);
+        CUDA_TRY(cudaMemcpyAsync(ids + first, d_ids, size_t(n) * 4, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(rst + 3 * first, d_rst, size_t(n) * 12, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaStreamSynchronize(ds->stream));
+    }
+    CUDA_TRY(cudaGetLastError());
+    cudaFree(d_ids);
+    cudaFree(d_rst);
+    return TRN_OK;
+}
+
+int32_t trn_render_device(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
+                          float* d_accum_rgba, void* cuda_stream, trn_stats* stats) {
+    if (!scene || !d_accum_rgba) return fail(TRN_ERR_INVALID, "null argument");
+    return render_on_device(scene, device, cam, cfg, reinterpret_cast<float4*>(d_accum_rgba),
+                            static_cast<cudaStream_t>(cuda_stream), true, stats, nullptr);
+}
+
+int32_t trn_render(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
+                   float* out_rgba_sum, trn_stats* stats) {
+    if (!scene || !out_rgba_sum) return fail(TRN_ERR_INVALID, "null argument");
+    int rc = validate(cam, cfg);
+    if (rc) return rc;
+    DeviceScene* ds = nullptr;
+    rc = get_device_scene(scene, device, &ds);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(ds->device));
+    const size_t pixels = static_cast<size_t>(cfg->width) * cfg->height;
+    rc = ensure_accum(ds, pixels);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, ds->stream));
+    CUDA_TRY(cudaMemsetAsync(ds->d_accum, 0, pixels * sizeof(float4), ds->stream));
+    trn_stats local;
+    rc = render_on_device(scene, ds->device, cam, cfg, ds->d_accum, ds->stream, true, &local, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_rgba_sum, ds->d_accum, pixels * sizeof(float4), cudaMemcpyDeviceToHost, ds->stream));
+    CUDA_TRY(cudaEventRecord(e1, ds->stream));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    local.ms_render = ms;
+    if (stats) *stats = local;
+    return TRN_OK;
+}
+
+int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_devices, const trn_camera* cam,
+                         const trn_render_config* cfg, float* out_rgba_sum, trn_stats* stats) {
+    if (!scene || !devices || num_devices < 1 || !out_rgba_sum) return fail(TRN_ERR_INVALID, "null argument");
+    if (num_devices == 1) return trn_render(scene, devices[0], cam, cfg, out_rgba_sum, stats);
+    int rc = validate(cam, cfg);
+    if (rc) return rc;
+    static NcclApi nccl;
+    static std::mutex nccl_mu;
+    {
+        std::lock_guard<std::mutex> lock(nccl_mu);
+        if (!nccl.lib) {
+            rc = load_nccl(nccl);
+            if (rc) return rc;
+        }
+    }
+    const size_t pixels = static_cast<size_t>(cfg->width) * cfg->height;
+    std::vector<DeviceScene*> dss(num_devices, nullptr);
+    for (int g = 0; g < num_devices; ++g) {
+        rc = get_device_scene(scene, devices[g], &dss[g]);
+        if (rc) return rc;
+        CUDA_TRY(cudaSetDevice(dss[g]->device));
+        rc = ensure_accum(dss[g], pixels);
+        if (rc) return rc;
+    }
+    std::vector<void*> comms(num_devices, nullptr);
+    std::vector<int> devs(devices, devices + num_devices);
+    int nrc = nccl.CommInitAll(comms.data(), num_devices, devs.data());
+    if (nrc != 0) return fail(TRN_ERR_NCCL, std::string("ncclCommInitAll: ") + (nccl.GetErrorString ? nccl.GetErrorString(nrc) : "?"));
+
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<trn_stats> st(num_devices);
+    std::vector<int> rcs(num_devices, 0);
+    std::vector<std::string> errs(num_devices);
+    std::vector<std::thread> workers;
+    const int base_begin = cfg->sample_begin;
+    const int base_stride = cfg->sample_stride > 0 ? cfg->sample_stride : 1;
+    for (int g = 0; g < num_devices; ++g) {
+        workers.emplace_back([&, g]() {
+            cudaSetDevice(dss[g]->device);
+            trn_render_config c = *cfg;
+            c.sample_begin = base_begin + g * base_stride; // sample split: i = begin + stride*(g + G*k)
+            c.sample_stride = base_stride * num_devices;
+            cudaMemsetAsync(dss[g]->d_accum, 0, pixels * sizeof(float4), dss[g]->stream);
+            rcs[g] = render_on_device(scene, dss[g]->device, cam, &c, dss[g]->d_accum, dss[g]->stream, true, &st[g], nullptr);
+            if (rcs[g]) errs[g] = g_last_error;
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (int g = 0; g < num_devices; ++g)
+        if (rcs[g]) {
+            for (void* c : comms) nccl.CommDestroy(c);
+            return fail(rcs[g], errs[g]);
+        }
+    // one ncclReduce(sum) of the float accumulation buffers onto devices[0]
+    nccl.GroupStart();
+    for (int g = 0; g < num_devices; ++g) {
+        cudaSetDevice(dss[g]->device);
+        nrc = nccl.Reduce(dss[g]->d_accum, dss[g]->d_accum, pixels * 4, /*ncclFloat32*/ 7, /*ncclSum*/ 0, 0, comms[g], dss[g]->stream);
+        if (nrc != 0) break;
+    }
+    int erc = nccl.GroupEnd();
+    if (nrc != 0 || erc != 0) {
+        for (void* c : comms) nccl.CommDestroy(c);
+        return fail(TRN_ERR_NCCL, "ncclReduce failed");
+    }
+    for (int g = 0; g < num_devices; ++g) {
+        cudaSetDevice(dss[g]->device);
+        CUDA_TRY(cudaStreamSynchronize(dss[g]->stream));
+    }
+    CUDA_TRY(cudaSetDevice(dss[0]->device));
+    CUDA_TRY(cudaMemcpy(out_rgba_sum, dss[0]->d_accum, pixels * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (void* c : comms) nccl.CommDestroy(c);
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        for (auto& s : st) {
+            stats->rays += s.rays;
+            stats->prim_rays += s.prim_rays;
+            stats->shadow_rays += s.shadow_rays;
+            stats->launches += s.launches;
+            stats->ms_trace = std::max(stats->ms_trace, s.ms_trace);
+            stats->ms_shadow = std::max(stats->ms_shadow, s.ms_shadow);
+            stats->ms_shade = std::max(stats->ms_shade, s.ms_shade);
+            stats->ms_other = std::max(stats->ms_other, s.ms_other);
+        }
+        stats->ms_render = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return TRN_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,73 @@
+// Host-side pieces of the reference's main() that stay on the CPU: camera set-up,
+// tone mapping and the P3 writer. libm's expf/powf are used on purpose so that, given the
+// same linear buffer, the 8-bit output equals the reference's (lib/effects.h:15-48).
+#include "../../include/turner_b200.h"
+#include "host_util.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+extern "C" {
+
+// Camera(trafo, aiCamera), lib/types.h:92-105: position = trafo * (0,0,0), rotation = upper 3x3,
+// delta_x = tan(hfov) evaluated in double (the unqualified tan() there binds to ::tan(double)),
+// delta_y = delta_x / aspect; image height = int(width / aspect), main.cpp:178-179.
+int32_t trn_camera_setup(const float* trafo4x4, float hfov, float aspect, int32_t width, trn_camera* cam, int32_t* height) {
+    if (!trafo4x4 || !cam) return trn::fail(TRN_ERR_INVALID, "null argument");
+    if (!(aspect > 0)) return trn::fail(TRN_ERR_INVALID, "aspect must be > 0 (config.h:30)");
+    const float* m = trafo4x4;
+    for (int r = 0; r < 3; ++r) {
+        cam->pos[r] = m[4 * r] * 0.f + m[4 * r + 1] * 0.f + m[4 * r + 2] * 0.f + m[4 * r + 3];
+        for (int c = 0; c < 3; ++c) cam->rot[3 * r + c] = m[4 * r + c];
+    }
+    cam->delta_x = static_cast<float>(std::tan(static_cast<double>(hfov)));
+    cam->delta_y = cam->delta_x / aspect;
+    if (height) *height = static_cast<int32_t>(width / aspect);
+    return TRN_OK;
+}
+
+int32_t trn_tonemap(const float* rgba_sum, uint64_t npix, int32_t pixel_samples, float exposure, int32_t gamma_enabled,
+                    float inverse_gamma, float* rgba_out) {
+    if (!rgba_sum || !rgba_out || pixel_samples < 1) return trn::fail(TRN_ERR_INVALID, "bad argument");
+    const float n = static_cast<float>(pixel_samples);
+    for (uint64_t i = 0; i < npix; ++i) {
+        float c[4];
+        for (int k = 0; k < 4; ++k) c[k] = rgba_sum[4 * i + k] / n;           // main.cpp:216
+        for (int k = 0; k < 3; ++k) c[k] = 1 - expf(-c[k] * exposure);        // effects.h:15-17
+        if (gamma_enabled)
+            for (int k = 0; k < 3; ++k) c[k] = powf(c[k], inverse_gamma);     // effects.h:36-38
+        std::memcpy(rgba_out + 4 * i, c, sizeof c);
+    }
+    return TRN_OK;
+}
+
+uint64_t trn_write_p3(const float* rgba, int32_t width, int32_t height, char* buf, uint64_t cap) {
+    // lib/raster.h:79-100: header, then per pixel "\n" at row starts else " ", three setw(3) ints of
+    // int(clamp(255*c*a, 0, 255)); main.cpp:242 appends std::endl.
+    std::string head = "P3\n" + std::to_string(width) + " " + std::to_string(height) + "\n255";
+    const uint64_t npix = static_cast<uint64_t>(width) * height;
+    const uint64_t need = head.size() + npix * 12 + 1;
+    if (!buf || cap == 0) return need;
+    uint64_t pos = 0;
+    auto put = [&](const char* s, size_t n) {
+        for (size_t i = 0; i < n && pos < cap; ++i) buf[pos++] = s[i];
+    };
+    put(head.data(), head.size());
+    char tmp[16];
+    auto q = [](float v) {
+        float c = v < 0.f ? 0.f : (255.f < v ? 255.f : v);
+        return static_cast<int>(c);
+    };
+    for (uint64_t i = 0; i < npix; ++i) {
+        const float* p = rgba + 4 * i;
+        tmp[0] = (i % static_cast<uint64_t>(width) == 0) ? '\n' : ' ';
+        int n = std::snprintf(tmp + 1, sizeof tmp - 1, "%3d %3d %3d", q(255 * p[0] * p[3]), q(255 * p[1] * p[3]), q(255 * p[2] * p[3]));
+        put(tmp, static_cast<size_t>(n) + 1);
+    }
+    put("\n", 1);
+    return need;
+}
+
+} // extern "C"

@@ -1,0 +1,40 @@
+// Host-side kd-tree construction for the B200 path tracer.
+//
+// Produces, node for node, the tree the reference's KDTree(Triangles) constructor
+// builds (lib/kdtree.cpp:124-490: SAH sweep of Wald-Havran Alg. 4 with clipped
+// triangle boxes, then the DFS flatten), so that Stats' "Kd-Tree Height", the
+// leaf visiting order and therefore exact-tie resolution are identical -- but as
+// a task-parallel build over allocation-free clipping instead of the reference's
+// single-threaded recursion over std::vector<Point3f>.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace trn {
+
+struct HostTriangles {
+    // 64-byte intersection record per triangle, the reference's precomputed quantities
+    // (lib/triangle.h:33-39): v0.xyz n.xyz u.xyz v.xyz uv vv uu denom
+    std::vector<float> isect; // n*16
+    // shading record: n0.xyz n1.xyz n2.xyz pad*3 rgba (lib/triangle.h:95-98)
+    std::vector<float> shade; // n*16
+    std::vector<float> verts; // n*9, as given
+    uint32_t count = 0;
+};
+
+// fills isect/shade from raw arrays (verts n*9, normals n*9, diffuse n*4)
+void precompute_triangles(const float* verts, const float* normals, const float* diffuse, uint32_t n, HostTriangles& out);
+
+struct KdTree {
+    float box[6]; // min xyz, max xyz (KDTree::box())
+    // the reference's FlatNode encoding (lib/kdtree.h:62-154), DFS order, left child = next node
+    std::vector<uint64_t> nodes;
+    uint64_t height = 0;
+    uint64_t num_leaf_refs = 0;
+    double build_ms = 0;
+};
+
+// num_threads <= 0: hardware concurrency
+void build_kdtree(const HostTriangles& tris, KdTree& out, int num_threads = 0);
+
+} // namespace trn

@@ -1,0 +1,492 @@
+// sm_100a wavefront kernel set of the path tracer: raygen, closest-hit kd traversal,
+// shade/bounce (+ warp-ballot compaction of the next wave), any-hit shadow traversal.
+//
+// Arithmetic contract (tests/test_gpu_parity.py): everything that decides WHICH
+// triangle is hit -- primary ray setup, slab test, split-plane distances, the
+// ray/triangle test -- is the reference's fp32 operation sequence
+// (lib/types.h:119-123, lib/intersection.h:40-128, lib/kdtree.cpp:515-607) with
+// IEEE division and no FMA contraction: this file is compiled with -fmad=false
+// (-prec-div/-prec-sqrt default to true). Hit triangle ids and (r,s,t) are
+// therefore bit-identical to the reference's.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace trn {
+
+constexpr float kEpsDir = 0.00001f;            // EPS, lib/types.h:13 (fix_direction, lib/kdtree.cpp:503-511)
+constexpr uint32_t kMiss = 0x40000000u;         // OptionalId miss, lib/kdtree.h:156-161
+constexpr int kStackDepth = 64;                 // >= tree height + 1 (checked at scene creation)
+constexpr float kFltMax = 3.402823466e+38f;
+
+// ------------------------------------------------------------------ device scene
+struct DevScene {
+    const uint2* nodes;        // inner: (split bits, right<<2 | axis)   leaf-run head: (first ref, count<<2 | 3)
+    const uint32_t* leaf_refs; // triangle ids of all leaf runs, in the reference's visiting order
+    const float4* isect;       // 4 x float4 per triangle: v0.xyz n.x | n.yz u.xy | u.z v.xyz | uv vv uu denom
+    const float4* shade;       // 4 x float4 per triangle: n0.xyz n1.x | n1.yz n2.xy | n2.z - - - | rgba
+    float lo[3], hi[3];        // KDTree::box()
+};
+
+// ray wave, SoA of float4 (fully coalesced 16-byte lanes)
+struct RayWave {
+    float4* a; // o.x o.y o.z d.x
+    float4* b; // d.y d.z  rel(u32: primary-sample index relative to the batch)  node(u32: index in the m-ary ray tree)
+    float4* T; // rgba throughput
+};
+struct ShadowWave {
+    float4* a; // o.x o.y o.z d.x
+    float4* b; // d.y d.z tmax pixel(u32)
+    float4* c; // rgba contribution to add when unoccluded
+};
+
+struct CameraDev {
+    float pos[3];
+    float rot[9];
+    float delta_x, delta_y;
+};
+
+struct FrameParams {
+    CameraDev cam;
+    int32_t width, height;
+    int32_t pps;           // --pixel-samples of the whole job (RNG key + jitter table stride)
+    int32_t n_local;       // pixel samples this call renders per pixel
+    int32_t sample_begin, sample_stride;
+    int32_t mc_samples, max_depth;
+    float bg[4];
+    int32_t has_light;
+    float light_pos[3];
+    float light_rgba[4];
+    float max_visibility;
+    uint64_t seed;
+};
+
+// -------------------------------------------------------------------------- RNG
+// xorshift64* (lib/xorshift.h:36-41) and its float conversion (lib/xorshift.h:57-59)
+__device__ __forceinline__ uint64_t xs64star_next(uint64_t& s) {
+    s ^= s >> 12;
+    s ^= s << 25;
+    s ^= s >> 27;
+    return s * 2685821657736338717ULL;
+}
+__device__ __forceinline__ float xs64star_float(uint64_t& s) {
+    return static_cast<float>(xs64star_next(s) & 0xFFFFFFull) * 5.9604644775390625e-8f; // ldexp(x, -24), exact
+}
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// counter-seeded stream of one ray-tree node (DESIGN.md "RNG"); replaces sampling.h:12's sequential stream
+__host__ __device__ __forceinline__ uint64_t node_state(uint64_t seed_mix, uint64_t sample_index, uint64_t node) {
+    uint64_t s = splitmix64(splitmix64(seed_mix ^ splitmix64(sample_index)) + node);
+    return s ? s : 0x9E3779B97F4A7C15ull;
+}
+
+// ------------------------------------------------------------------- traversal
+struct HitRec {
+    uint32_t id;
+    float r, s, t;
+};
+
+__device__ __forceinline__ float sel3(int ax, float x, float y, float z) { return ax == 0 ? x : (ax == 1 ? y : z); }
+
+// Front-to-back kd traversal (Hapala-Havran Alg. 2 as in lib/kdtree.cpp:515-578) with the
+// stack in local memory. Differences from the reference, none of which can change the
+// result (pinned in tests): tenter is clamped to 0 and the walk stops once the
+// best hit lies inside the current cell instead of draining the stack.
+// ANY_HIT: stop at the first accepted triangle with r <= tmax (shadow predicate,
+// pathtracer.cpp:53: lit <=> !hit || r_closest > dist_to_light).
+template <bool ANY_HIT>
+__device__ __forceinline__ bool traverse(const DevScene& sc, float ox, float oy, float oz, float dx, float dy, float dz,
+                                         float tmax_any, HitRec& out) {
+    const float fdx = dx == 0.f ? kEpsDir : dx;
+    const float fdy = dy == 0.f ? kEpsDir : dy;
+    const float fdz = dz == 0.f ? kEpsDir : dz;
+    const float ix = 1 / fdx, iy = 1 / fdy, iz = 1 / fdz;
+
+    // intersect_ray_box, lib/intersection.h:105-128
+    float tx1 = (sc.lo[0] - ox) * ix, tx2 = (sc.hi[0] - ox) * ix;
+    float tenter = fminf(tx1, tx2), texit = fmaxf(tx1, tx2);
+    float ty1 = (sc.lo[1] - oy) * iy, ty2 = (sc.hi[1] - oy) * iy;
+    tenter = fmaxf(tenter, fminf(ty1, ty2));
+    texit = fminf(texit, fmaxf(ty1, ty2));
+    float tz1 = (sc.lo[2] - oz) * iz, tz2 = (sc.hi[2] - oz) * iz;
+    tenter = fmaxf(tenter, fminf(tz1, tz2));
+    texit = fminf(texit, fmaxf(tz1, tz2));
+
+    out.id = kMiss;
+    out.r = kFltMax;
+    out.s = 0.f;
+    out.t = 0.f;
+    if (texit < tenter) return false;
+    if (tenter < 0.f) tenter = 0.f;
+
+    uint32_t stk_node[kStackDepth];
+    float stk_tmin[kStackDepth];
+    float stk_tmax[kStackDepth];
+    int sp = 0;
+    uint32_t node = 0;
+
+    for (;;) {
+        uint2 n = __ldg(&sc.nodes[node]);
+        while ((n.y & 3u) != 3u) {
+            const int ax = static_cast<int>(n.y & 3u);
+            const float split = __uint_as_float(n.x);
+            const float o_ax = sel3(ax, ox, oy, oz);
+            const float i_ax = sel3(ax, ix, iy, iz);
+            const float d_ax = sel3(ax, fdx, fdy, fdz);
+            const float t = (split - o_ax) * i_ax;
+            uint32_t near = node + 1, far = n.y >> 2;
+            if (d_ax <= 0.f) {
+                const uint32_t tmp = near;
+                near = far;
+                far = tmp;
+            }
+            if (texit < t) {
+                node = near;
+            } else if (t < tenter) {
+                node = far;
+            } else {
+                stk_node[sp] = far;
+                stk_tmin[sp] = t;
+                stk_tmax[sp] = texit;
+                ++sp;
+                node = near;
+                texit = t;
+            }
+            n = __ldg(&sc.nodes[node]);
+        }
+
+        // leaf run (lib/kdtree.cpp:580-607): strict '<' keeps the first-visited triangle on ties
+        const uint32_t first = n.x, count = n.y >> 2;
+        for (uint32_t i = 0; i < count; ++i) {
+            const uint32_t id = __ldg(&sc.leaf_refs[first + i]);
+            const float4* rec = sc.isect + 4 * static_cast<size_t>(id);
+            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
+            // intersect_ray_plane, lib/intersection.h:40-49
+            const float nx = q0.w, ny = q1.x, nz = q1.y;
+            const float denom = nx * dx + ny * dy + nz * dz;
+            if (denom == 0.f) continue;
+            const float nom = nx * (q0.x - ox) + ny * (q0.y - oy) + nz * (q0.z - oz);
+            const float r = nom / denom;
+            // r < 0 rejects (intersection.h:66); a hit only matters if it beats the running
+            // minimum (kdtree.cpp:591,569), resp. lies within tmax for the shadow predicate
+            if (!(r >= 0.f)) continue;
+            if (ANY_HIT ? !(r <= tmax_any) : !(r < out.r)) continue;
+            const float4 q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
+            // lib/intersection.h:70-86
+            const float wx = (ox + r * dx) - q0.x, wy = (oy + r * dy) - q0.y, wz = (oz + r * dz) - q0.z;
+            const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
+            const float wv = wx * vx + wy * vy + wz * vz;
+            const float wu = wx * ux + wy * uy + wz * uz;
+            const float s = (q3.x * wv - q3.y * wu) / q3.w;
+            if (s < 0.f) continue;
+            const float t = (q3.x * wu - q3.z * wv) / q3.w;
+            if (t < 0.f || 1.f < s + t) continue;
+            out.id = id;
+            out.r = r;
+            out.s = s;
+            out.t = t;
+            if (ANY_HIT) return true;
+        }
+
+        if (out.id != kMiss && out.r <= texit) break;
+        if (sp == 0) break;
+        --sp;
+        node = stk_node[sp];
+        tenter = stk_tmin[sp];
+        texit = stk_tmax[sp];
+        // the stack is ordered front to back: once the nearest pending cell starts beyond the
+        // light, nothing behind it can hold an occluder with r <= tmax
+        if (ANY_HIT && tenter > tmax_any) break;
+    }
+    return out.id != kMiss;
+}
+
+// ---------------------------------------------------------------------- kernels
+
+// raygen: one thread per primary sample of the batch. Batch-relative index rel -> (pixel, local sample j) ->
+// jittered raster position -> Camera::raster2cam (lib/types.h:119-123). Jitter = the reference's per-row
+// xorshift64star<float>(42) stream (main.cpp:201-206), precomputed on the host as a [width][pps][2] table
+// because every row restarts it.
+__global__ void __launch_bounds__(256) raygen_kernel(FrameParams fp, const float2* __restrict__ jitter,
+                                                     uint64_t first_local_index, uint32_t count, RayWave out) {
+    const uint32_t rel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rel >= count) return;
+    const uint64_t gl = first_local_index + rel;
+    const uint32_t pixel = static_cast<uint32_t>(gl / static_cast<uint32_t>(fp.n_local));
+    const uint32_t j = static_cast<uint32_t>(gl % static_cast<uint32_t>(fp.n_local));
+    const uint32_t i = fp.sample_begin + j * fp.sample_stride;
+    const int x = static_cast<int>(pixel % static_cast<uint32_t>(fp.width));
+    const int y = static_cast<int>(pixel / static_cast<uint32_t>(fp.width));
+    const float2 jit = __ldg(&jitter[static_cast<size_t>(x) * fp.pps + i]);
+    const float px = x + jit.x, py = y + jit.y;
+    const float w = static_cast<float>(fp.width), h = static_cast<float>(fp.height);
+    const float vx = -fp.cam.delta_x * (1 - 2 * px / w);
+    const float vy = fp.cam.delta_y * (1 - 2 * py / h);
+    const float vz = -1.f;
+    const float* m = fp.cam.rot;
+    const float dx = m[0] * vx + m[1] * vy + m[2] * vz;
+    const float dy = m[3] * vx + m[4] * vy + m[5] * vz;
+    const float dz = m[6] * vx + m[7] * vy + m[8] * vz;
+    out.a[rel] = make_float4(fp.cam.pos[0], fp.cam.pos[1], fp.cam.pos[2], dx);
+    out.b[rel] = make_float4(dy, dz, __uint_as_float(rel), __uint_as_float(0u));
+    out.T[rel] = make_float4(1.f, 1.f, 1.f, 1.f);
+}
+
+// closest hit for a wave of rays; one thread per ray
+__global__ void __launch_bounds__(128) trace_closest_kernel(DevScene sc, const float4* __restrict__ ra,
+                                                            const float4* __restrict__ rb, uint32_t count,
+                                                            uint4* __restrict__ hits) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const float4 a = ra[idx];
+    const float4 b = rb[idx];
+    HitRec h;
+    traverse<false>(sc, a.x, a.y, a.z, a.w, b.x, b.y, 0.f, h);
+    hits[idx] = make_uint4(h.id, __float_as_uint(h.r), __float_as_uint(h.s), __float_as_uint(h.t));
+}
+
+// plain (o, d) arrays in, for trn_intersect
+__global__ void __launch_bounds__(128) trace_closest_plain_kernel(DevScene sc, const float* __restrict__ o,
+                                                                  const float* __restrict__ d, uint32_t count,
+                                                                  uint4* __restrict__ hits) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    HitRec h;
+    traverse<false>(sc, o[3 * idx], o[3 * idx + 1], o[3 * idx + 2], d[3 * idx], d[3 * idx + 1], d[3 * idx + 2], 0.f, h);
+    hits[idx] = make_uint4(h.id, __float_as_uint(h.r), __float_as_uint(h.s), __float_as_uint(h.t));
+}
+
+struct WaveCounters {
+    uint32_t next_count;   // rays appended to the next wave
+    uint32_t shadow_count; // shadow rays appended
+    uint32_t pad0, pad1;
+};
+
+__device__ __forceinline__ void accumulate(float4* acc, uint32_t pixel, float4 v) {
+    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) return;
+    atomicAdd(acc + pixel, v); // red.global.add.v4.f32 (sm_90+)
+}
+
+__device__ __forceinline__ uint32_t pixel_of(const FrameParams& fp, uint64_t first_local_index, uint32_t rel,
+                                             uint32_t& sample_i) {
+    const uint64_t gl = first_local_index + rel;
+    const uint32_t pixel = static_cast<uint32_t>(gl / static_cast<uint32_t>(fp.n_local));
+    const uint32_t j = static_cast<uint32_t>(gl % static_cast<uint32_t>(fp.n_local));
+    sample_i = fp.sample_begin + j * fp.sample_stride;
+    return pixel;
+}
+
+// shade/bounce (pathtracer.cpp:26-101 in throughput form): per ray of the wave
+//   miss            -> acc[pixel] += T * bg
+//   hit             -> shadow ray with pre-weighted contribution T * rho * max(0, n.l) * light / pi
+//                      and, below max depth, m uniform-hemisphere children with T' = T * rho * (2 cos / m)
+// The next wave is built compacted: per warp one ballot/popc and one atomicAdd reserve the slots
+// (children laid out k-major inside the warp's block so that every store is a coalesced run).
+__global__ void __launch_bounds__(256) shade_bounce_kernel(DevScene sc, FrameParams fp, uint64_t first_local_index,
+                                                           RayWave cur, const uint4* __restrict__ hits, uint32_t count,
+                                                           int depth, RayWave next, ShadowWave shadow,
+                                                           WaveCounters* __restrict__ counters,
+                                                           float4* __restrict__ acc) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const bool valid = idx < count;
+    bool is_hit = false;
+    float4 a, b, T;
+    uint4 h;
+    uint32_t rel = 0, node = 0, pixel = 0, sample_i = 0;
+    if (valid) {
+        a = cur.a[idx];
+        b = cur.b[idx];
+        T = cur.T[idx];
+        h = hits[idx];
+        rel = __float_as_uint(b.z);
+        node = __float_as_uint(b.w);
+        pixel = pixel_of(fp, first_local_index, rel, sample_i);
+        is_hit = h.x != kMiss;
+        if (!is_hit) accumulate(acc, pixel, make_float4(T.x * fp.bg[0], T.y * fp.bg[1], T.z * fp.bg[2], T.w * fp.bg[3]));
+    }
+
+    float nx = 0, ny = 0, nz = 0, p2x = 0, p2y = 0, p2z = 0;
+    float4 rho = make_float4(0, 0, 0, 0);
+    bool want_shadow = false;
+    float ldx = 0, ldy = 0, ldz = 0, ldist = 0;
+    float4 contrib = make_float4(0, 0, 0, 0);
+    if (is_hit) {
+        const float r = __uint_as_float(h.y), s = __uint_as_float(h.z), t = __uint_as_float(h.w);
+        const float dx = a.w, dy = b.x, dz = b.y;
+        const float px = a.x + r * dx, py = a.y + r * dy, pz = a.z + r * dz; // pathtracer.cpp:30
+        const float4* srec = sc.shade + 4 * static_cast<size_t>(h.x);
+        const float4 s0 = __ldg(srec), s1 = __ldg(srec + 1), s2 = __ldg(srec + 2);
+        rho = __ldg(srec + 3);
+        // Triangle::interpolate_normal(1-s-t, s, t), lib/triangle.h:54-56
+        const float br = 1.f - s - t;
+        float mx = (br * s0.x + s * s0.w) + t * s1.z;
+        float my = (br * s0.y + s * s1.x) + t * s1.w;
+        float mz = (br * s0.z + s * s1.y) + t * s2.x;
+        const float inv = 1 / sqrtf(mx * mx + my * my + mz * mz);
+        nx = inv * mx;
+        ny = inv * my;
+        nz = inv * mz;
+        p2x = px + 0.0001f * nx; // pathtracer.cpp:36
+        p2y = py + 0.0001f * ny;
+        p2z = pz + 0.0001f * nz;
+        if (fp.has_light) { // pathtracer.cpp:44-58
+            float lx = fp.light_pos[0] - px, ly = fp.light_pos[1] - py, lz = fp.light_pos[2] - pz;
+            const float linv = 1 / sqrtf(lx * lx + ly * ly + lz * lz);
+            ldx = linv * lx;
+            ldy = linv * ly;
+            ldz = linv * lz;
+            const float qx = fp.light_pos[0] - p2x, qy = fp.light_pos[1] - p2y, qz = fp.light_pos[2] - p2z;
+            ldist = sqrtf(qx * qx + qy * qy + qz * qz);
+            const float wgt = fmaxf(0.f, ldx * nx + ldy * ny + ldz * nz);
+            const float k = 0.318309886183790671538f; // M_1_PI as float
+            contrib = make_float4(T.x * (rho.x * (k * (wgt * fp.light_rgba[0]))), T.y * (rho.y * (k * (wgt * fp.light_rgba[1]))),
+                                  T.z * (rho.z * (k * (wgt * fp.light_rgba[2]))), T.w * (rho.w * (k * (wgt * fp.light_rgba[3]))));
+            want_shadow = !(contrib.x == 0.f && contrib.y == 0.f && contrib.z == 0.f && contrib.w == 0.f);
+        }
+    }
+
+    // ---- compaction: shadow rays
+    const unsigned smask = __ballot_sync(0xffffffffu, want_shadow);
+    if (smask) {
+        uint32_t sbase = 0;
+        if (lane == 0) sbase = atomicAdd(&counters->shadow_count, __popc(smask));
+        sbase = __shfl_sync(0xffffffffu, sbase, 0);
+        if (want_shadow) {
+            const uint32_t slot = sbase + __popc(smask & ((1u << lane) - 1u));
+            shadow.a[slot] = make_float4(p2x, p2y, p2z, ldx);
+            shadow.b[slot] = make_float4(ldy, ldz, ldist, __uint_as_float(pixel));
+            shadow.c[slot] = contrib;
+        }
+    }
+
+    // ---- compaction: children
+    const bool spawn = is_hit && depth < fp.max_depth;
+    const unsigned hmask = __ballot_sync(0xffffffffu, spawn);
+    if (hmask == 0) return;
+    const int m = fp.mc_samples;
+    const uint32_t nh = __popc(hmask);
+    uint32_t cbase = 0;
+    if (lane == 0) cbase = atomicAdd(&counters->next_count, nh * static_cast<uint32_t>(m));
+    cbase = __shfl_sync(0xffffffffu, cbase, 0);
+    if (!spawn) return;
+    const uint32_t rank = __popc(hmask & ((1u << lane) - 1u));
+
+    // aiMatrix3x3::FromToMatrix((0,0,1) -> normal), assimp matrix3x3.inl (Moeller-Hughes), pathtracer.cpp:68-70
+    float m00, m01, m02, m10, m11, m12, m20, m21, m22;
+    {
+        const float fx = 0.f, fy = 0.f, fz = 1.f;
+        const float e = fx * nx + fy * ny + fz * nz;
+        const float f = e < 0.f ? -e : e;
+        if (f > 1.0f - 0.00001f) {
+            // x = axis "most nearly orthogonal" to from=(0,0,1) by assimp's tie rules -> (0,1,0)
+            const float xx = 0.f, xy = 1.f, xz = 0.f;
+            const float ux = xx - fx, uy = xy - fy, uz = xz - fz;
+            const float vx = xx - nx, vy = xy - ny, vz = xz - nz;
+            const float c1 = 2.0f / (ux * ux + uy * uy + uz * uz);
+            const float c2 = 2.0f / (vx * vx + vy * vy + vz * vz);
+            const float c3 = c1 * c2 * (ux * vx + uy * vy + uz * vz);
+            const float u[3] = {ux, uy, uz}, v[3] = {vx, vy, vz};
+            float mt[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+#pragma unroll
+                for (int j = 0; j < 3; j++) mt[i][j] = -c1 * u[i] * u[j] - c2 * v[i] * v[j] + c3 * v[i] * u[j];
+                mt[i][i] += 1.0f;
+            }
+            m00 = mt[0][0]; m01 = mt[0][1]; m02 = mt[0][2];
+            m10 = mt[1][0]; m11 = mt[1][1]; m12 = mt[1][2];
+            m20 = mt[2][0]; m21 = mt[2][1]; m22 = mt[2][2];
+        } else {
+            const float vx = fy * nz - fz * ny, vy = fz * nx - fx * nz, vz = fx * ny - fy * nx;
+            const float hh = 1.0f / (1.0f + e);
+            const float hvx = hh * vx, hvz = hh * vz;
+            const float hvxy = hvx * vy, hvxz = hvx * vz, hvyz = hvz * vy;
+            m00 = e + hvx * vx; m01 = hvxy - vz;        m02 = hvxz + vy;
+            m10 = hvxy + vz;    m11 = e + hh * vy * vy; m12 = hvyz - vx;
+            m20 = hvxz - vy;    m21 = hvyz + vx;        m22 = e + hvz * vz;
+        }
+    }
+
+    const uint64_t sample_index = static_cast<uint64_t>(pixel) * static_cast<uint64_t>(fp.pps) + sample_i;
+    const float fm = static_cast<float>(m);
+    for (int k = 0; k < m; ++k) {
+        const uint32_t child = node * static_cast<uint32_t>(m) + static_cast<uint32_t>(k) + 1u;
+        uint64_t st = node_state(fp.seed, sample_index, child);
+        const float u1 = xs64star_float(st);
+        const float u2 = xs64star_float(st);
+        // sampling::hemisphere, lib/sampling.h:20-32
+        const float z = u1;
+        const float rr = sqrtf(fmaxf(0.f, 1.f - z * z));
+        const float phi = 6.28318530717958647692f * u2;
+        const float lx = rr * cosf(phi), ly = rr * sinf(phi), lz = z;
+        const float dx = m00 * lx + m01 * ly + m02 * lz;
+        const float dy = m10 * lx + m11 * ly + m12 * lz;
+        const float dz = m20 * lx + m21 * ly + m22 * lz;
+        const float wgt = (2.f * u1) / fm; // pathtracer.cpp:84,88,100-101: rho * 2 * (cos / m)
+        const uint32_t slot = cbase + static_cast<uint32_t>(k) * nh + rank;
+        next.a[slot] = make_float4(p2x, p2y, p2z, dx);
+        next.b[slot] = make_float4(dy, dz, __uint_as_float(rel), __uint_as_float(child));
+        next.T[slot] = make_float4(T.x * (rho.x * wgt), T.y * (rho.y * wgt), T.z * (rho.z * wgt), T.w * (rho.w * wgt));
+    }
+}
+
+// raycaster.cpp:7-24: colour = diffuse rgb, alpha = clamp(1 - r / max_visibility); bg on a miss
+__global__ void __launch_bounds__(256) shade_raycast_kernel(DevScene sc, FrameParams fp, uint64_t first_local_index,
+                                                            RayWave cur, const uint4* __restrict__ hits, uint32_t count,
+                                                            unsigned long long* __restrict__ hit_counter,
+                                                            float4* __restrict__ acc) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < count;
+    bool is_hit = false;
+    if (valid) {
+        const uint4 h = hits[idx];
+        const float4 b = cur.b[idx];
+        uint32_t sample_i;
+        const uint32_t pixel = pixel_of(fp, first_local_index, __float_as_uint(b.z), sample_i);
+        is_hit = h.x != kMiss;
+        float4 c;
+        if (is_hit) {
+            c = __ldg(sc.shade + 4 * static_cast<size_t>(h.x) + 3);
+            const float al = 1.f - (__uint_as_float(h.y) / fp.max_visibility);
+            c.w = al < 0.f ? 0.f : (1.f < al ? 1.f : al);
+        } else {
+            c = make_float4(fp.bg[0], fp.bg[1], fp.bg[2], fp.bg[3]);
+        }
+        accumulate(acc, pixel, c);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, is_hit);
+    if ((threadIdx.x & 31u) == 0 && mask) atomicAdd(hit_counter, static_cast<unsigned long long>(__popc(mask)));
+}
+
+// any-hit shadow traversal; count is read from device memory (the wave was built by shade_bounce_kernel in the
+// same stream), the grid covers the upper bound
+__global__ void __launch_bounds__(128) trace_shadow_kernel(DevScene sc, ShadowWave sw,
+                                                           const WaveCounters* __restrict__ counters,
+                                                           float4* __restrict__ acc) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= counters->shadow_count) return;
+    const float4 a = sw.a[idx];
+    const float4 b = sw.b[idx];
+    HitRec h;
+    const bool occluded = traverse<true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, b.z, h);
+    if (!occluded) accumulate(acc, __float_as_uint(b.w), sw.c[idx]);
+}
+
+__global__ void unpack_hits_kernel(const uint4* __restrict__ hits, uint32_t count, uint32_t* __restrict__ ids,
+                                   float* __restrict__ rst) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const uint4 h = hits[idx];
+    ids[idx] = h.x;
+    const bool miss = h.x == kMiss;
+    rst[3 * idx] = miss ? 0.f : __uint_as_float(h.y);
+    rst[3 * idx + 1] = miss ? 0.f : __uint_as_float(h.z);
+    rst[3 * idx + 2] = miss ? 0.f : __uint_as_float(h.w);
+}
+
+} // namespace trn
