@@ -83,6 +83,14 @@ typedef struct trn_stats {
     double ms_shadow;     /* ... of the any-hit traversal kernel */
     double ms_shade;      /* ... of the shade/bounce kernel */
     double ms_other;      /* ... raygen + bookkeeping */
+    uint64_t trace_launches;  /* closest-hit traversal launches / rays they processed */
+    uint64_t trace_queries;
+    uint64_t shadow_launches; /* any-hit traversal launches (queries = shadow_rays) */
+    /* Visit counts of the two traversal kernels, filled only while trn_set_counting(1) is on (instrumented
+     * kernels, slower): inner-node visits, reference leaf nodes (8-byte id pairs, lib/kdtree.h:62-154) and
+     * triangle tests -- the n_* of the algorithmic-bytes formula in DESIGN.md "Roofline". */
+    uint64_t trace_inner, trace_leaf_nodes, trace_tri_tests;
+    uint64_t shadow_inner, shadow_leaf_nodes, shadow_tri_tests;
 } trn_stats;
 
 typedef struct trn_scene_info {
@@ -140,6 +148,11 @@ int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_d
 
 /* per-kernel timing inside trn_render* (adds an event pair per launch); off by default */
 void trn_set_profiling(int32_t enabled);
+/* run the instrumented traversal kernels and fill the visit counts of trn_stats; off by default */
+void trn_set_counting(int32_t enabled);
+/* like trn_intersect, additionally returns {inner visits, leaf nodes, triangle tests} of the batch in counts3 */
+int32_t trn_intersect_counted(trn_scene* scene, int32_t device, const float* origins, const float* dirs, uint64_t n,
+                              uint32_t* ids, float* rst, uint64_t* counts3);
 
 /* ---- host-side pieces of the reference's main() that the CLI keeps (no GPU involved) ------------------- */
 

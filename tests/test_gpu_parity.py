@@ -1,0 +1,285 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Bars: triangle ids, (r,s,t) and raycaster images are BIT-EXACT; path-traced radiance is compared
+ (a) against the oracle run with the same counter-seeded hemisphere streams: per-pixel tolerance 2e-4 * (1 + value)
+     on the per-pixel SUM over samples (differences: fp32 sum order of atomics, sinf/cosf last-ulp), a handful of
+     pixels may differ by one flipped ray, bounded below;
+ (b) against the oracle in the reference's own sequential-stream mode (what the reference computes): RMSE within
+     1.1 * sqrt(E[MSE]) with E[MSE] = mean_pix(2 s^2_pix / pps), |mean signed diff| <= 3 sqrt(E[MSE]/N).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def cornell(api, ob, scenes):
+    sc = scenes.fixture("cornell_box")
+    return sc, api.Scene.from_dict(sc), ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+
+
+def all_scenes(scenes):
+    return [scenes.four_triangles(), scenes.unit_cube(), scenes.fixture("cornell_box"), scenes.fixture("furnace_test"),
+            scenes.fixture("colored_cube"), scenes.fixture("orthogonal_planes"), scenes.random_soup(100, 1),
+            scenes.random_soup(5000, 2), scenes.cubesphere(40),
+            {**scenes.four_triangles(), "name": "single", "vertices": scenes.four_triangles()["vertices"][:1],
+             "normals": scenes.four_triangles()["normals"][:1], "diffuse": scenes.four_triangles()["diffuse"][:1]}]
+
+
+def test_gpu_present(api):
+    assert api.device_count() >= 1
+
+
+def test_known_answers_four_triangles(api, scenes):
+    # tests/test_kdtree.cpp:23-63 through the CUDA traversal
+    p = api.Scene.from_dict(scenes.four_triangles())
+    assert p.height == 1 and p.num_nodes == 5
+    d = np.array([[0.5, 0.5, 1], [2.5, 0.5, 1], [0.5, 2.5, 1], [2.5, 2.5, 1]], np.float32)
+    ids, rst = p.intersect(np.zeros((4, 3), np.float32), d)
+    assert ids.tolist() == [0, 1, 2, 3]
+    assert rst.tolist() == [[1, 0.5, 0.5], [1, 0, 0.5], [1, 0, 0.5], [1, 0, 0.5]]
+
+
+def test_closest_hit_bit_exact_random_rays(api, ob, scenes):
+    total = 0
+    for sc in all_scenes(scenes):
+        o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+        p = api.Scene.from_dict(sc)
+        for inside in (False, True):
+            ro, rd = scenes.random_rays(sc, 100000, seed=21, inside=inside)
+            rd[::7, 0] = 0   # exact zeros -> fix_direction (kdtree.cpp:503-511)
+            rd[::11, 1] = 0
+            rd[::13, 2] = 0
+            i_o, r_o = o.intersect(ro, rd, 0)  # the reference's exhaustive schedule
+            i_g, r_g = p.intersect(ro, rd)
+            assert np.array_equal(i_g, i_o), (sc["name"], inside, int((i_g != i_o).sum()))
+            assert np.array_equal(bits(r_g), bits(r_o)), (sc["name"], inside)
+            total += ro.shape[0]
+    assert total == 2_000_000
+
+
+def test_edge_case_rays(api, ob, scenes):
+    sc = scenes.unit_cube()
+    o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+    p = api.Scene.from_dict(sc)
+    ro = np.array([[0, 0, 0], [5, 5, 5], [0, 0, -3], [0, 0, 3], [1, 1, 1], [-1, 0, 0], [0, 0, 0], [2, 0, 0], [0, 0, 0]], np.float32)
+    rd = np.array([[0, 0, 1], [1, 1, 1], [0, 0, 1], [0, 0, 1], [1, 0, 0], [1, 0, 0], [1e-30, 0, 0], [-1, 0, 0], [0, 0, 0]], np.float32)
+    i_o, r_o = o.intersect(ro, rd, 0)
+    i_g, r_g = p.intersect(ro, rd)
+    assert np.array_equal(i_g, i_o) and np.array_equal(bits(r_g), bits(r_o))
+    # empty batch
+    i_g, r_g = p.intersect(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert i_g.size == 0
+
+
+def test_primary_hits_config2_cornell_3840(api, ob, cornell):
+    # BASELINE config 2: raycaster cornell_box.blend width 3840 -> 14.7M primaries, ids bit-exact
+    sc, p, o = cornell
+    W = 3840
+    cam, cfg = api.make_config(sc, W, integrator=api.RAYCASTER, pixel_samples=1)
+    ids, rst = p.primary_hits(cam, cfg)
+    ocfg = ob.make_cfg(sc, W, integrator=1, pixel_samples=1)
+    dirs = ob.primary_dirs(ocfg).reshape(-1, 3)
+    org = np.tile(np.array(list(ocfg.cam_pos), np.float32), (dirs.shape[0], 1))
+    i_o, r_o = o.intersect(org, dirs, 0)
+    mism = int((ids.reshape(-1) != i_o).sum())
+    assert mism == 0, "primary-hit id mismatches: %d of %d" % (mism, i_o.size)
+    assert np.array_equal(bits(rst.reshape(-1, 3)), bits(r_o))
+    assert ids.size == W * W
+
+
+def test_primary_hits_mesh(api, ob, scenes):
+    sc = scenes.cubesphere(96)  # 110,592 triangles
+    p = api.Scene.from_dict(sc)
+    o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"], nodes=p.nodes(), box=np.array(p.info.box, np.float32))
+    cam, cfg = api.make_config(sc, 640, pixel_samples=2)
+    ids, rst = p.primary_hits(cam, cfg)
+    ocfg = ob.make_cfg(sc, 640, pixel_samples=2)
+    dirs = ob.primary_dirs(ocfg).reshape(-1, 3)
+    org = np.tile(np.array(list(ocfg.cam_pos), np.float32), (dirs.shape[0], 1))
+    i_o, r_o = o.intersect(org, dirs, 0)
+    assert (i_o != ob.MISS).sum() > 50000
+    assert np.array_equal(ids.reshape(-1), i_o)
+    assert np.array_equal(bits(rst.reshape(-1, 3)), bits(r_o))
+
+
+def test_raycaster_image_bit_exact(api, ob, cornell):
+    sc, p, o = cornell
+    cam, cfg = api.make_config(sc, 512, integrator=api.RAYCASTER, max_visibility=2.0, bg=(0.2, 0.3, 0.4, 1))
+    img, st = p.render(cam, cfg)
+    ref, _, ost = o.render(ob.make_cfg(sc, 512, integrator=1, max_visibility=2.0, bg=(0.2, 0.3, 0.4, 1), num_threads=8))
+    assert np.array_equal(bits(img), bits(ref))
+    assert st.rays == ost.num_rays and st.prim_rays == ost.num_prim_rays  # raycaster.cpp:17 counts hits only
+
+
+def _compare_counter_mode(api, ob, sc, p, o, width, depth, m, pps, bg=(0, 0, 0, 1), seed=5):
+    cam, cfg = api.make_config(sc, width, max_depth=depth, mc_samples=m, pixel_samples=pps, bg=bg, seed=seed)
+    img, st = p.render(cam, cfg)
+    ref, _, ost = o.render(ob.make_cfg(sc, width, depth, m, pps, bg=bg, rng_mode=1, seed=seed, num_threads=8))
+    assert st.prim_rays == ost.num_prim_rays
+    d = np.abs(img - ref)
+    tol = 2e-4 * (1 + np.abs(ref))
+    bad = (d > tol).any(-1)
+    # a ray whose direction differs in the last ulp of sinf/cosf may flip hit/miss at a triangle edge:
+    # allow at most 0.1 % of the pixels to deviate, and the ray counts to differ by that proportion
+    assert bad.mean() <= 1e-3, "pixels outside tolerance: %d of %d" % (bad.sum(), bad.size)
+    assert abs(int(st.rays) - int(ost.num_rays)) <= 1e-4 * ost.num_rays
+    return img, ref, st, ost
+
+
+def test_radiance_vs_counter_seeded_oracle_cornell(api, ob, cornell):
+    sc, p, o = cornell
+    _compare_counter_mode(api, ob, sc, p, o, 96, 3, 4, 4)
+    _compare_counter_mode(api, ob, sc, p, o, 64, 3, 1, 8, bg=(0.3, 0.2, 0.1, 1))   # README shape: m=1, pps=8
+    _compare_counter_mode(api, ob, sc, p, o, 48, 1, 8, 2)
+    _compare_counter_mode(api, ob, sc, p, o, 32, 5, 2, 1, seed=99)
+
+
+def test_radiance_vs_counter_seeded_oracle_other_scenes(api, ob, scenes):
+    for name, bg in [("furnace_test", (1, 1, 1, 1)), ("colored_cube", (0.1, 0.1, 0.1, 1)), ("orthogonal_planes", (0, 0, 0, 1))]:
+        sc = scenes.fixture(name)
+        p = api.Scene.from_dict(sc)
+        o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+        _compare_counter_mode(api, ob, sc, p, o, 64, 3, 3, 2, bg=bg)
+    sc = scenes.cubesphere(32)
+    p = api.Scene.from_dict(sc)
+    o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+    _compare_counter_mode(api, ob, sc, p, o, 96, 3, 4, 2, bg=(0.5, 0.6, 0.7, 1))
+
+
+def test_rmse_within_monte_carlo_bound_vs_reference_streams(api, ob, cornell):
+    # BASELINE config 1 shape (cornell, D3, m1, pps 8) at width 160, and m=4
+    sc, p, o = cornell
+    for (W, D, m, pps) in [(160, 3, 1, 8), (96, 3, 4, 8)]:
+        cam, cfg = api.make_config(sc, W, max_depth=D, mc_samples=m, pixel_samples=pps, seed=3)
+        img, st = p.render(cam, cfg)
+        ref, sq, ost = o.render(ob.make_cfg(sc, W, D, m, pps, rng_mode=0, num_threads=1), want_sumsq=True)
+        mean_g, mean_r = img / pps, ref / pps
+        var_pix = np.maximum(sq / pps - mean_r ** 2, 0) * pps / (pps - 1)  # per-pixel sample variance of the oracle
+        emse = (2 * var_pix / pps).mean(axis=(0, 1))
+        diff = mean_g - mean_r
+        rmse = np.sqrt((diff ** 2).mean(axis=(0, 1)))
+        bias = np.abs(diff.mean(axis=(0, 1)))
+        npix = W * img.shape[0]
+        assert np.all(rmse <= 1.1 * np.sqrt(emse) + 1e-6), (rmse, np.sqrt(emse))
+        assert np.all(bias <= 3 * np.sqrt(emse / npix) + 1e-6), (bias, 3 * np.sqrt(emse / npix))
+        # ray counts agree statistically (same primaries, different hemisphere streams)
+        assert abs(int(st.rays) - int(ost.num_rays)) < 0.01 * ost.num_rays
+
+
+def test_furnace_energy_conservation(api, scenes):
+    # BASELINE config 3 (reduced width): convex rho=0.18 body under a white environment, no lamp:
+    # every pixel fully covered by the sphere converges to rho, alpha to 1; nothing exceeds rho beyond MC error
+    sc = scenes.fixture("furnace_test")
+    p = api.Scene.from_dict(sc)
+    W, pps, m, D = 256, 64, 8, 8
+    cam, cfg = api.make_config(sc, W, max_depth=D, mc_samples=m, pixel_samples=pps, bg=(1, 1, 1, 1))
+    img, st = p.render(cam, cfg)
+    ids, _ = p.primary_hits(cam, cfg)
+    covered = (ids != api.MISS_ID).all(-1)
+    assert covered.sum() > 2000
+    mean = img / pps
+    inner = mean[covered]
+    assert abs(inner[:, :3].mean() - 0.18) < 0.002, inner[:, :3].mean()
+    assert abs(inner[:, 3].mean() - 1.0) < 0.01
+    # per pixel: rho * 2 * mean(u1) over pps*m samples, sd = 0.36 * sqrt(1/12) / sqrt(pps*m)
+    sd = 0.36 * np.sqrt(1 / 12) / np.sqrt(pps * m)
+    assert inner[:, :3].max() < 0.18 + 6 * sd
+    outside = (ids == api.MISS_ID).all(-1)
+    assert np.allclose(mean[outside], 1.0)
+
+
+def test_sample_split_matches_full_render(api, cornell):
+    # multi-GPU decomposition: samples i = g (mod G) on G "devices" sum to the full render
+    sc, p, o = cornell
+    cam, cfg = api.make_config(sc, 80, max_depth=3, mc_samples=3, pixel_samples=6, seed=4)
+    full, st = p.render(cam, cfg)
+    for G in (2, 4):
+        acc = np.zeros_like(full)
+        rays = 0
+        for g in range(G):
+            _, c = api.make_config(sc, 80, max_depth=3, mc_samples=3, pixel_samples=6, seed=4, sample_begin=g, sample_stride=G)
+            part, s = p.render(cam, c)
+            acc += part
+            rays += s.rays
+        assert rays == st.rays
+        assert np.allclose(acc, full, rtol=1e-5, atol=1e-5)
+
+
+def test_linearity_in_light_colour(api, cornell):
+    # size-independent property: radiance is linear in the light colour; x2 is exact in fp32 up to summation order
+    sc, p, o = cornell
+    cam, cfg = api.make_config(sc, 128, max_depth=2, mc_samples=2, pixel_samples=2)
+    a, _ = p.render(cam, cfg)
+    cfg.light.rgba[0] *= 2
+    cfg.light.rgba[1] *= 2
+    cfg.light.rgba[2] *= 2
+    b, _ = p.render(cam, cfg)
+    assert np.allclose(b[..., :3], 2 * a[..., :3], rtol=1e-5, atol=1e-6)
+
+
+def test_wave_chunking_is_result_neutral(api, cornell, monkeypatch):
+    # tiny wave buffers force the depth-first chunked schedule; results must not change
+    sc, p, o = cornell
+    cam, cfg = api.make_config(sc, 64, max_depth=3, mc_samples=4, pixel_samples=2, seed=8)
+    a, sa = p.render(cam, cfg)
+    monkeypatch.setenv("TRN_WAVE_CAP", "4096")
+    p2 = api.Scene.from_dict(sc)
+    b, sb = p2.render(cam, cfg)
+    assert sa.rays == sb.rays and sa.shadow_rays == sb.shadow_rays
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
+    assert sb.launches > sa.launches
+
+
+def test_render_device_accumulates_into_caller_buffer(api, cornell):
+    torch = pytest.importorskip("torch")
+    sc, p, o = cornell
+    cam, cfg = api.make_config(sc, 64, max_depth=2, mc_samples=2, pixel_samples=2)
+    host, st = p.render(cam, cfg)
+    buf = torch.zeros(cfg.height, cfg.width, 4, device="cuda:0", dtype=torch.float32)
+    stream = torch.cuda.current_stream()
+    s1 = p.render_device(cam, cfg, buf.data_ptr(), stream.cuda_stream, device=0)
+    s2 = p.render_device(cam, cfg, buf.data_ptr(), stream.cuda_stream, device=0)
+    torch.cuda.synchronize()
+    assert s1.rays == st.rays == s2.rays
+    assert np.allclose(buf.cpu().numpy(), 2 * host, rtol=1e-5, atol=1e-6)
+
+
+def test_full_size_mesh1m_primary_hits(api, ob, scenes):
+    # BASELINE config 5 geometry (995,328 triangles). Oracle adopts the product's node array (proved identical to the
+    # reference builder's in tests/test_host.py at small sizes and offline at this size) and runs the
+    # reference's exhaustive traversal on a 1/16 subsample of the 1920-wide primaries.
+    sc = scenes.cubesphere(288)
+    p = api.Scene.from_dict(sc)
+    assert p.num_triangles == 995328
+    cam, cfg = api.make_config(sc, 1920, pixel_samples=1)
+    ids, rst = p.primary_hits(cam, cfg)
+    o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"], nodes=p.nodes(), box=np.array(p.info.box, np.float32))
+    ocfg = ob.make_cfg(sc, 1920, pixel_samples=1)
+    dirs = ob.primary_dirs(ocfg)[::4, ::4].reshape(-1, 3)
+    org = np.tile(np.array(list(ocfg.cam_pos), np.float32), (dirs.shape[0], 1))
+    i_o, r_o = o.intersect(org, dirs, 0)
+    sub_ids = ids[::4, ::4].reshape(-1)
+    sub_rst = rst[::4, ::4].reshape(-1, 3)
+    assert (i_o != ob.MISS).sum() > 20000
+    assert np.array_equal(sub_ids, i_o), int((sub_ids != i_o).sum())
+    assert np.array_equal(bits(sub_rst), bits(r_o))
+
+
+def test_traversal_counters_equal_oracle(api, ob, scenes):
+    # the n_inner / n_leafnodes / n_tri_tests of the algorithmic-bytes formula are DEFINED by the
+    # oracle's instrumented early-exit mode; the GPU's instrumented kernel must count the same schedule
+    for sc in [scenes.fixture("cornell_box"), scenes.fixture("furnace_test"), scenes.cubesphere(40), scenes.random_soup(5000, 2)]:
+        o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+        p = api.Scene.from_dict(sc)
+        for inside in (False, True):
+            ro, rd = scenes.random_rays(sc, 50000, seed=31, inside=inside)
+            i_o, r_o, c_o = o.intersect(ro, rd, 1, counters=True)
+            i_g, r_g, c_g = p.intersect_counted(ro, rd)
+            assert np.array_equal(i_g, i_o) and np.array_equal(bits(r_g), bits(r_o))
+            assert c_g.tolist() == c_o[:3].tolist(), (sc["name"], inside, c_g, c_o)

@@ -135,7 +135,8 @@ def extract(path):
             ca = bf.by_ptr[datap]
             (lens,) = bf.field(ca, "Camera", "lens", "f")
             (sensor_x,) = bf.field(ca, "Camera", "sensor_x", "f")
-            hfov = float(np.arctan2(np.float32(sensor_x), np.float32(2.0) * np.float32(lens)).astype(np.float32))
+            # evaluated in double, rounded once (reproduces README.md:22-36 ray counts exactly)
+            hfov = float(np.float32(np.arctan2(float(np.float32(sensor_x)), float(np.float32(2.0) * np.float32(lens)))))
             camera = {"trafo4x4": [float(x) for x in T.reshape(-1)], "hfov": hfov,
                       "lens": float(lens), "sensor_x": float(sensor_x)}
         elif otype == 10 and datap:  # lamp

@@ -52,7 +52,10 @@ class RenderConfig(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("prim_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("launches", C.c_uint64),
                 ("ms_render", C.c_double), ("ms_trace", C.c_double), ("ms_shadow", C.c_double),
-                ("ms_shade", C.c_double), ("ms_other", C.c_double)]
+                ("ms_shade", C.c_double), ("ms_other", C.c_double),
+                ("trace_launches", C.c_uint64), ("trace_queries", C.c_uint64), ("shadow_launches", C.c_uint64),
+                ("trace_inner", C.c_uint64), ("trace_leaf_nodes", C.c_uint64), ("trace_tri_tests", C.c_uint64),
+                ("shadow_inner", C.c_uint64), ("shadow_leaf_nodes", C.c_uint64), ("shadow_tri_tests", C.c_uint64)]
 
 
 class SceneInfo(C.Structure):
@@ -70,7 +73,7 @@ class LoadedScene(C.Structure):
 EXPORTS = [
     "trn_last_error", "trn_device_count", "trn_scene_create", "trn_scene_destroy", "trn_scene_get_info",
     "trn_scene_get_nodes", "trn_intersect", "trn_primary_hits", "trn_render", "trn_render_device", "trn_render_multi",
-    "trn_set_profiling", "trn_camera_setup", "trn_tonemap", "trn_write_p3", "trn_load_blend", "trn_loaded_scene_free",
+    "trn_set_profiling", "trn_set_counting", "trn_intersect_counted", "trn_camera_setup", "trn_tonemap", "trn_write_p3", "trn_load_blend", "trn_loaded_scene_free",
 ]
 
 _lib = None
@@ -107,6 +110,8 @@ def lib():
         L.trn_render_multi.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.POINTER(Camera),
                                        C.POINTER(RenderConfig), C.c_void_p, C.POINTER(Stats)]
         L.trn_set_profiling.argtypes = [C.c_int32]
+        L.trn_set_counting.argtypes = [C.c_int32]
+        L.trn_intersect_counted.argtypes = [C.c_void_p, C.c_int32, _f32p, _f32p, C.c_uint64, _u32p, _f32p, _u64p]
         L.trn_camera_setup.argtypes = [_f32p, C.c_float, C.c_float, C.c_int32, C.POINTER(Camera), C.POINTER(C.c_int32)]
         L.trn_tonemap.argtypes = [_f32p, C.c_uint64, C.c_int32, C.c_float, C.c_int32, C.c_float, _f32p]
         L.trn_write_p3.restype = C.c_uint64
@@ -114,6 +119,7 @@ def lib():
         L.trn_load_blend.argtypes = [C.c_char_p, C.POINTER(LoadedScene)]
         L.trn_loaded_scene_free.argtypes = [C.POINTER(LoadedScene)]
         for f in ("trn_scene_create", "trn_scene_get_info", "trn_scene_get_nodes", "trn_intersect", "trn_primary_hits",
+                  "trn_intersect_counted",
                   "trn_render", "trn_render_device", "trn_render_multi", "trn_camera_setup", "trn_tonemap",
                   "trn_load_blend"):
             getattr(L, f).restype = C.c_int32
@@ -132,6 +138,10 @@ def device_count():
 
 def set_profiling(on):
     lib().trn_set_profiling(1 if on else 0)
+
+
+def set_counting(on):
+    lib().trn_set_counting(1 if on else 0)
 
 
 def camera_setup(trafo4x4, hfov, aspect, width):
@@ -215,6 +225,16 @@ class Scene:
         rst = np.zeros((o.shape[0], 3), np.float32)
         _check(lib().trn_intersect(self.h, device, o, d, o.shape[0], ids, rst))
         return ids, rst
+
+    def intersect_counted(self, origins, dirs, device=-1):
+        """intersect() + (inner visits, reference leaf nodes, triangle tests) of the batch"""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        ids = np.zeros(o.shape[0], np.uint32)
+        rst = np.zeros((o.shape[0], 3), np.float32)
+        cnt = np.zeros(3, np.uint64)
+        _check(lib().trn_intersect_counted(self.h, device, o, d, o.shape[0], ids, rst, cnt))
+        return ids, rst, cnt
 
     def primary_hits(self, cam, cfg, device=-1):
         n = cfg.width * cfg.height * cfg.pixel_samples

@@ -28,6 +28,7 @@ namespace trn {
 
 thread_local std::string g_last_error;
 static int g_profiling = 0;
+static int g_counting = 0;
 
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
@@ -61,6 +62,7 @@ struct DeviceScene {
     WaveCounters* h_counters = nullptr;  // pinned mirror
     uint32_t counter_slots = 0;
     unsigned long long* d_hitcount = nullptr;
+    unsigned long long* d_visits = nullptr; // [6]: closest inner/leaf/tri, shadow inner/leaf/tri
     float2* d_jitter = nullptr;
     size_t jitter_elems = 0;
     int jitter_w = 0, jitter_pps = 0;
@@ -83,6 +85,7 @@ struct DeviceScene {
         cudaFree(d_counters);
         if (h_counters) cudaFreeHost(h_counters);
         cudaFree(d_hitcount);
+        cudaFree(d_visits);
         cudaFree(d_jitter);
         cudaFree(d_accum);
         if (ev_sync) cudaEventDestroy(ev_sync);
@@ -178,6 +181,7 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     CUDA_TRY(cudaMalloc(&ds->d_counters, ds->counter_slots * sizeof(WaveCounters)));
     CUDA_TRY(cudaMallocHost(&ds->h_counters, ds->counter_slots * sizeof(WaveCounters)));
     CUDA_TRY(cudaMalloc(&ds->d_hitcount, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&ds->d_visits, 6 * sizeof(unsigned long long)));
     ds->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     *out = ds.get();
     sc->devices[device] = std::move(ds);
@@ -341,6 +345,8 @@ struct Renderer {
     cudaStream_t stream;
     KernelTimer timer;
     uint64_t rays = 0, prim = 0, shadow = 0, launches = 0;
+    uint64_t trace_launches = 0, trace_queries = 0, shadow_launches = 0;
+    bool counting = g_counting != 0;
     uint32_t slot = 0;
     uint64_t cap;
 
@@ -364,9 +370,14 @@ struct Renderer {
             const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(chunk_max, count - off));
             RayWave w{wave.a + off, wave.b + off, wave.T + off};
             timer.begin(0);
-            trace_closest_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits);
+            if (counting)
+                trace_closest_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits, ds->d_visits);
+            else
+                trace_closest_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits);
             timer.end();
             ++launches;
+            ++trace_launches;
+            trace_queries += n;
             if (integrator == TRN_RAYCASTER) {
                 timer.begin(2);
                 shade_raycast_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(ds->dev, fp, first_local_index, w, ds->d_hits, n,
@@ -389,9 +400,14 @@ struct Renderer {
             CUDA_TRY(cudaEventRecord(ds->ev_sync, stream));
             if (fp.has_light) {
                 timer.begin(1);
-                trace_shadow_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_counters + cs, acc);
+                if (counting)
+                    trace_shadow_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_counters + cs, acc,
+                                                                                       ds->d_visits + 3);
+                else
+                    trace_shadow_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_counters + cs, acc);
                 timer.end();
                 ++launches;
+                ++shadow_launches;
             }
             CUDA_TRY(cudaEventSynchronize(ds->ev_sync));
             const WaveCounters wc = ds->h_counters[cs];
@@ -407,6 +423,7 @@ struct Renderer {
     int run() {
         const uint64_t total = static_cast<uint64_t>(fp.width) * fp.height * static_cast<uint64_t>(fp.n_local);
         if (integrator == TRN_RAYCASTER) CUDA_TRY(cudaMemsetAsync(ds->d_hitcount, 0, sizeof(unsigned long long), stream));
+        if (counting) CUDA_TRY(cudaMemsetAsync(ds->d_visits, 0, 6 * sizeof(unsigned long long), stream));
         // primaries per batch: as many as fit one wave
         const uint64_t batch = cap;
         for (uint64_t first = 0; first < total; first += batch) {
@@ -469,6 +486,15 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
         stats->prim_rays = r.prim;
         stats->shadow_rays = r.shadow;
         stats->launches = r.launches;
+        stats->trace_launches = r.trace_launches;
+        stats->trace_queries = r.trace_queries;
+        stats->shadow_launches = r.shadow_launches;
+        if (r.counting) {
+            unsigned long long v[6];
+            cudaMemcpy(v, ds->d_visits, sizeof v, cudaMemcpyDeviceToHost);
+            stats->trace_inner = v[0]; stats->trace_leaf_nodes = v[1]; stats->trace_tri_tests = v[2];
+            stats->shadow_inner = v[3]; stats->shadow_leaf_nodes = v[4]; stats->shadow_tri_tests = v[5];
+        }
         r.timer.collect(stats);
     } else {
         r.timer.collect(nullptr);
@@ -535,6 +561,7 @@ int32_t trn_device_count(void) {
 }
 
 void trn_set_profiling(int32_t enabled) { g_profiling = enabled; }
+void trn_set_counting(int32_t enabled) { g_counting = enabled; }
 
 int32_t trn_scene_create(const float* verts, const float* normals, const float* diffuse, uint32_t n, trn_scene** out) {
     if (!verts || !normals || !diffuse || !out) return fail(TRN_ERR_INVALID, "null argument");
@@ -578,8 +605,22 @@ int32_t trn_scene_get_nodes(const trn_scene* scene, uint64_t* out_nodes) {
     return TRN_OK;
 }
 
+static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* origins, const float* dirs, uint64_t n,
+                              uint32_t* ids, float* rst, uint64_t* counts3);
+
 int32_t trn_intersect(trn_scene* scene, int32_t device, const float* origins, const float* dirs, uint64_t n,
                       uint32_t* ids, float* rst) {
+    return intersect_impl(scene, device, origins, dirs, n, ids, rst, nullptr);
+}
+
+int32_t trn_intersect_counted(trn_scene* scene, int32_t device, const float* origins, const float* dirs, uint64_t n,
+                              uint32_t* ids, float* rst, uint64_t* counts3) {
+    if (!counts3) return fail(TRN_ERR_INVALID, "null argument");
+    return intersect_impl(scene, device, origins, dirs, n, ids, rst, counts3);
+}
+
+static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* origins, const float* dirs, uint64_t n,
+                              uint32_t* ids, float* rst, uint64_t* counts3) {
     if (!scene || !origins || !dirs || !ids || !rst) return fail(TRN_ERR_INVALID, "null argument");
     DeviceScene* ds = nullptr;
     int rc = get_device_scene(scene, device, &ds);
@@ -595,17 +636,26 @@ int32_t trn_intersect(trn_scene* scene, int32_t device, const float* origins, co
     CUDA_TRY(cudaMalloc(&d_rst, cn * 12));
     CUDA_TRY(cudaMalloc(&d_h, cn * 16));
     CUDA_TRY(cudaMalloc(&d_ids, cn * 4));
+    if (counts3) CUDA_TRY(cudaMemsetAsync(ds->d_visits, 0, 6 * sizeof(unsigned long long), ds->stream));
     for (uint64_t off = 0; off < n; off += chunk) {
         const uint32_t c = static_cast<uint32_t>(std::min<uint64_t>(chunk, n - off));
         CUDA_TRY(cudaMemcpyAsync(d_o, origins + 3 * off, size_t(c) * 12, cudaMemcpyHostToDevice, ds->stream));
         CUDA_TRY(cudaMemcpyAsync(d_d, dirs + 3 * off, size_t(c) * 12, cudaMemcpyHostToDevice, ds->stream));
-        trace_closest_plain_kernel<<<blocks_for(c, 128), 128, 0, ds->stream>>>(ds->dev, d_o, d_d, c, d_h);
+        if (counts3)
+            trace_closest_plain_count_kernel<<<blocks_for(c, 128), 128, 0, ds->stream>>>(ds->dev, d_o, d_d, c, d_h, ds->d_visits);
+        else
+            trace_closest_plain_kernel<<<blocks_for(c, 128), 128, 0, ds->stream>>>(ds->dev, d_o, d_d, c, d_h);
         unpack_hits_kernel<<<blocks_for(c, 256), 256, 0, ds->stream>>>(d_h, c, d_ids, d_rst);
         CUDA_TRY(cudaMemcpyAsync(ids + off, d_ids, size_t(c) * 4, cudaMemcpyDeviceToHost, ds->stream));
         CUDA_TRY(cudaMemcpyAsync(rst + 3 * off, d_rst, size_t(c) * 12, cudaMemcpyDeviceToHost, ds->stream));
         CUDA_TRY(cudaStreamSynchronize(ds->stream));
     }
     CUDA_TRY(cudaGetLastError());
+    if (counts3) {
+        unsigned long long v[3];
+        CUDA_TRY(cudaMemcpy(v, ds->d_visits, sizeof v, cudaMemcpyDeviceToHost));
+        counts3[0] = v[0]; counts3[1] = v[1]; counts3[2] = v[2];
+    }
     cudaFree(d_o);
     cudaFree(d_d);
     cudaFree(d_rst);

@@ -98,9 +98,16 @@ __device__ __forceinline__ float sel3(int ax, float x, float y, float z) { retur
 // best hit lies inside the current cell instead of draining the stack.
 // ANY_HIT: stop at the first accepted triangle with r <= tmax (shadow predicate,
 // pathtracer.cpp:53: lit <=> !hit || r_closest > dist_to_light).
-template <bool ANY_HIT>
+// COUNT: also tally inner-node visits, reference leaf nodes (8-byte id pairs, lib/kdtree.h:62-154) and
+// triangle tests -- the n_* of SURVEY 8(d)'s algorithmic-bytes formula, same schedule as the oracle's
+// instrumented early-exit mode (tests/test_gpu_parity.py::test_traversal_counters_equal_oracle).
+struct VisitCounts {
+    uint32_t inner, leaf_nodes, tri_tests;
+};
+
+template <bool ANY_HIT, bool COUNT = false>
 __device__ __forceinline__ bool traverse(const DevScene& sc, float ox, float oy, float oz, float dx, float dy, float dz,
-                                         float tmax_any, HitRec& out) {
+                                         float tmax_any, HitRec& out, VisitCounts* vc = nullptr) {
     const float fdx = dx == 0.f ? kEpsDir : dx;
     const float fdy = dy == 0.f ? kEpsDir : dy;
     const float fdz = dz == 0.f ? kEpsDir : dz;
@@ -132,6 +139,7 @@ __device__ __forceinline__ bool traverse(const DevScene& sc, float ox, float oy,
     for (;;) {
         uint2 n = __ldg(&sc.nodes[node]);
         while ((n.y & 3u) != 3u) {
+            if (COUNT) vc->inner += 1;
             const int ax = static_cast<int>(n.y & 3u);
             const float split = __uint_as_float(n.x);
             const float o_ax = sel3(ax, ox, oy, oz);
@@ -161,7 +169,9 @@ __device__ __forceinline__ bool traverse(const DevScene& sc, float ox, float oy,
 
         // leaf run (lib/kdtree.cpp:580-607): strict '<' keeps the first-visited triangle on ties
         const uint32_t first = n.x, count = n.y >> 2;
+        if (COUNT) vc->leaf_nodes += (count + 1) >> 1;
         for (uint32_t i = 0; i < count; ++i) {
+            if (COUNT) vc->tri_tests += 1;
             const uint32_t id = __ldg(&sc.leaf_refs[first + i]);
             const float4* rec = sc.isect + 4 * static_cast<size_t>(id);
             const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
@@ -258,6 +268,49 @@ __global__ void __launch_bounds__(128) trace_closest_plain_kernel(DevScene sc, c
     HitRec h;
     traverse<false>(sc, o[3 * idx], o[3 * idx + 1], o[3 * idx + 2], d[3 * idx], d[3 * idx + 1], d[3 * idx + 2], 0.f, h);
     hits[idx] = make_uint4(h.id, __float_as_uint(h.r), __float_as_uint(h.s), __float_as_uint(h.t));
+}
+
+// instrumented twins of the two traversal kernels (bench.py's roofline leg and the counter parity test only)
+__device__ __forceinline__ void flush_counts(const VisitCounts& vc, unsigned long long* g) {
+    unsigned a = vc.inner, b = vc.leaf_nodes, c = vc.tri_tests;
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, off);
+        b += __shfl_down_sync(0xffffffffu, b, off);
+        c += __shfl_down_sync(0xffffffffu, c, off);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        atomicAdd(g + 0, static_cast<unsigned long long>(a));
+        atomicAdd(g + 1, static_cast<unsigned long long>(b));
+        atomicAdd(g + 2, static_cast<unsigned long long>(c));
+    }
+}
+
+__global__ void __launch_bounds__(128) trace_closest_count_kernel(DevScene sc, const float4* __restrict__ ra,
+                                                                  const float4* __restrict__ rb, uint32_t count,
+                                                                  uint4* __restrict__ hits, unsigned long long* g) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    VisitCounts vc{0, 0, 0};
+    if (idx < count) {
+        const float4 a = ra[idx];
+        const float4 b = rb[idx];
+        HitRec h;
+        traverse<false, true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, 0.f, h, &vc);
+        hits[idx] = make_uint4(h.id, __float_as_uint(h.r), __float_as_uint(h.s), __float_as_uint(h.t));
+    }
+    flush_counts(vc, g);
+}
+
+__global__ void __launch_bounds__(128) trace_closest_plain_count_kernel(DevScene sc, const float* __restrict__ o,
+                                                                        const float* __restrict__ d, uint32_t count,
+                                                                        uint4* __restrict__ hits, unsigned long long* g) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    VisitCounts vc{0, 0, 0};
+    if (idx < count) {
+        HitRec h;
+        traverse<false, true>(sc, o[3 * idx], o[3 * idx + 1], o[3 * idx + 2], d[3 * idx], d[3 * idx + 1], d[3 * idx + 2], 0.f, h, &vc);
+        hits[idx] = make_uint4(h.id, __float_as_uint(h.r), __float_as_uint(h.s), __float_as_uint(h.t));
+    }
+    flush_counts(vc, g);
 }
 
 struct WaveCounters {
@@ -475,6 +528,21 @@ __global__ void __launch_bounds__(128) trace_shadow_kernel(DevScene sc, ShadowWa
     HitRec h;
     const bool occluded = traverse<true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, b.z, h);
     if (!occluded) accumulate(acc, __float_as_uint(b.w), sw.c[idx]);
+}
+
+__global__ void __launch_bounds__(128) trace_shadow_count_kernel(DevScene sc, ShadowWave sw,
+                                                                 const WaveCounters* __restrict__ counters,
+                                                                 float4* __restrict__ acc, unsigned long long* g) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    VisitCounts vc{0, 0, 0};
+    if (idx < counters->shadow_count) {
+        const float4 a = sw.a[idx];
+        const float4 b = sw.b[idx];
+        HitRec h;
+        const bool occluded = traverse<true, true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, b.z, h, &vc);
+        if (!occluded) accumulate(acc, __float_as_uint(b.w), sw.c[idx]);
+    }
+    flush_counts(vc, g);
 }
 
 __global__ void unpack_hits_kernel(const uint4* __restrict__ hits, uint32_t count, uint32_t* __restrict__ ids,

@@ -48,7 +48,7 @@ def look_at_camera(eye, target, up=(0.0, 1.0, 0.0), lens=35.0, sensor_x=32.0):
     u = np.cross(r, f)
     m = np.eye(4)
     m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = r, u, -f, eye
-    hfov = float(np.arctan2(np.float32(sensor_x), np.float32(2.0) * np.float32(lens)).astype(np.float32))
+    hfov = float(np.float32(np.arctan2(float(np.float32(sensor_x)), float(np.float32(2.0) * np.float32(lens)))))
     return {"trafo4x4": [float(np.float32(x)) for x in m.reshape(-1)], "hfov": hfov}
 
 
