@@ -281,7 +281,8 @@ def main():
     # ---- roofline of the dominant kernel (closest-hit kd traversal): algorithmic bytes per launch from the
     # instrumented twin run once on the same steps' rays (untimed), duration from the event pairs above
     api.set_counting(True)
-    cnt = dict(inner=0, leaf=0, tri=0, q=0, s_inner=0, s_leaf=0, s_tri=0, s_q=0)
+    cnt = dict(inner=0, leaf=0, tri=0, q=0, s_inner=0, s_leaf=0, s_tri=0, s_q=0, a_inner=0, a_leaf=0, a_tri=0, sa_inner=0,
+               sa_leaf=0, sa_tri=0)
     probe_steps = min(args.steps, 2)
     for i in range(probe_steps):
         st = step(args.warmup + i)
@@ -293,6 +294,12 @@ def main():
         cnt["s_leaf"] += st.shadow_leaf_nodes
         cnt["s_tri"] += st.shadow_tri_tests
         cnt["s_q"] += st.shadow_rays
+        cnt["a_inner"] += st.trace_actual_inner
+        cnt["a_leaf"] += st.trace_actual_leaf_nodes
+        cnt["a_tri"] += st.trace_actual_tri_tests
+        cnt["sa_inner"] += st.shadow_actual_inner
+        cnt["sa_leaf"] += st.shadow_actual_leaf_nodes
+        cnt["sa_tri"] += st.shadow_actual_tri_tests
     api.set_counting(False)
     torch.cuda.synchronize()
     peak, peak_src = measured_peaks()
@@ -312,9 +319,14 @@ def main():
         "alg_bytes_per_query": bytes_per_query,
         "per_query": {"inner": cnt["inner"] / max(cnt["q"], 1), "leaf_nodes": cnt["leaf"] / max(cnt["q"], 1),
                       "tri_tests": cnt["tri"] / max(cnt["q"], 1)},
+        "per_query_actual": {"inner": cnt["a_inner"] / max(cnt["q"], 1), "leaf_nodes": cnt["a_leaf"] / max(cnt["q"], 1),
+                             "tri_tests": cnt["a_tri"] / max(cnt["q"], 1),
+                             "note": "visits of the production kernel on the device layout (empty-space cuts kept)"},
         "launches": tot["trace_launches"], "avg_launch_ms": tot["ms_trace"] / max(tot["trace_launches"], 1),
         "share_of_step": tot["ms_trace"] / ms,
         "kernel_ms": {k: tot[k] for k in ("ms_trace", "ms_shadow", "ms_shade", "ms_other")},
+        "shadow_per_query": {"ref": [cnt["s_inner"] / max(cnt["s_q"], 1), cnt["s_leaf"] / max(cnt["s_q"], 1), cnt["s_tri"] / max(cnt["s_q"], 1)],
+                             "actual": [cnt["sa_inner"] / max(cnt["s_q"], 1), cnt["sa_leaf"] / max(cnt["s_q"], 1), cnt["sa_tri"] / max(cnt["s_q"], 1)]},
         "shadow_kernel": {"alg_bytes_per_query": alg_bytes(cnt["s_inner"], cnt["s_leaf"], cnt["s_tri"], cnt["s_q"]) / max(cnt["s_q"], 1),
                           "achieved": alg_bytes(cnt["s_inner"], cnt["s_leaf"], cnt["s_tri"], cnt["s_q"]) / max(cnt["s_q"], 1)
                           * tot["shadow"] / max(tot["ms_shadow"], 1e-9) / 1e6},

@@ -91,6 +91,9 @@ typedef struct trn_stats {
      * triangle tests -- the n_* of the algorithmic-bytes formula in DESIGN.md "Roofline". */
     uint64_t trace_inner, trace_leaf_nodes, trace_tri_tests;
     uint64_t shadow_inner, shadow_leaf_nodes, shadow_tri_tests;
+    /* ... and what the production kernels really visit on the device layout (sibling pairs + empty-space cuts) */
+    uint64_t trace_actual_inner, trace_actual_leaf_nodes, trace_actual_tri_tests;
+    uint64_t shadow_actual_inner, shadow_actual_leaf_nodes, shadow_actual_tri_tests;
 } trn_stats;
 
 typedef struct trn_scene_info {
@@ -98,6 +101,7 @@ typedef struct trn_scene_info {
     uint64_t num_nodes;     /* KDTree::num_nodes(), lib/kdtree.h:219 */
     uint64_t kdtree_height; /* KDTree::height(), lib/kdtree.h:197-218 */
     uint64_t num_leaf_refs; /* triangle references in leaves */
+    uint64_t num_cut_nodes; /* empty-space cuts kept in the device layout (dropped by lib/kdtree.cpp:168-172) */
     float box[6];           /* KDTree::box(): min xyz, max xyz */
     double build_ms;        /* host kd-tree build time */
     double upload_ms;       /* layout + H2D */
@@ -150,9 +154,10 @@ int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_d
 void trn_set_profiling(int32_t enabled);
 /* run the instrumented traversal kernels and fill the visit counts of trn_stats; off by default */
 void trn_set_counting(int32_t enabled);
-/* like trn_intersect, additionally returns {inner visits, leaf nodes, triangle tests} of the batch in counts3 */
+/* like trn_intersect, additionally returns in counts6 the batch's {inner visits, reference leaf nodes, triangle
+ * tests} of the reference-shaped schedule (the B_alg definition) followed by the same three for the device layout */
 int32_t trn_intersect_counted(trn_scene* scene, int32_t device, const float* origins, const float* dirs, uint64_t n,
-                              uint32_t* ids, float* rst, uint64_t* counts3);
+                              uint32_t* ids, float* rst, uint64_t* counts6);
 
 /* ---- host-side pieces of the reference's main() that the CLI keeps (no GPU involved) ------------------- */
 

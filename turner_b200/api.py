@@ -55,12 +55,15 @@ class Stats(C.Structure):
                 ("ms_shade", C.c_double), ("ms_other", C.c_double),
                 ("trace_launches", C.c_uint64), ("trace_queries", C.c_uint64), ("shadow_launches", C.c_uint64),
                 ("trace_inner", C.c_uint64), ("trace_leaf_nodes", C.c_uint64), ("trace_tri_tests", C.c_uint64),
-                ("shadow_inner", C.c_uint64), ("shadow_leaf_nodes", C.c_uint64), ("shadow_tri_tests", C.c_uint64)]
+                ("shadow_inner", C.c_uint64), ("shadow_leaf_nodes", C.c_uint64), ("shadow_tri_tests", C.c_uint64),
+                ("trace_actual_inner", C.c_uint64), ("trace_actual_leaf_nodes", C.c_uint64),
+                ("trace_actual_tri_tests", C.c_uint64), ("shadow_actual_inner", C.c_uint64),
+                ("shadow_actual_leaf_nodes", C.c_uint64), ("shadow_actual_tri_tests", C.c_uint64)]
 
 
 class SceneInfo(C.Structure):
     _fields_ = [("num_triangles", C.c_uint64), ("num_nodes", C.c_uint64), ("kdtree_height", C.c_uint64),
-                ("num_leaf_refs", C.c_uint64), ("box", C.c_float * 6), ("build_ms", C.c_double),
+                ("num_leaf_refs", C.c_uint64), ("num_cut_nodes", C.c_uint64), ("box", C.c_float * 6), ("build_ms", C.c_double),
                 ("upload_ms", C.c_double)]
 
 
@@ -232,7 +235,7 @@ class Scene:
         d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
         ids = np.zeros(o.shape[0], np.uint32)
         rst = np.zeros((o.shape[0], 3), np.float32)
-        cnt = np.zeros(3, np.uint64)
+        cnt = np.zeros(6, np.uint64)
         _check(lib().trn_intersect_counted(self.h, device, o, d, o.shape[0], ids, rst, cnt))
         return ids, rst, cnt
 

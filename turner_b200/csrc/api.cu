@@ -7,6 +7,7 @@
 #include "host_util.h"
 #include "kdtree_build.h"
 #include "kernels.cuh"
+#include "traverse_persistent.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -49,6 +50,8 @@ struct DeviceScene {
     DevScene dev{};
     void* d_nodes = nullptr;
     void* d_refs = nullptr;
+    void* d_pnodes = nullptr;
+    void* d_prefs = nullptr;
     void* d_isect = nullptr;
     void* d_shade = nullptr;
     // work buffers (sized lazily, reused across calls)
@@ -61,6 +64,8 @@ struct DeviceScene {
     WaveCounters* d_counters = nullptr;  // ring of counters, one per (launch) use
     WaveCounters* h_counters = nullptr;  // pinned mirror
     uint32_t counter_slots = 0;
+    uint32_t ring_pos = 0;
+    int grid_closest = 0, grid_shadow = 0, grid_plain = 0; // persistent grids: resident CTAs per SM x SMs
     unsigned long long* d_hitcount = nullptr;
     unsigned long long* d_visits = nullptr; // [6]: closest inner/leaf/tri, shadow inner/leaf/tri
     float2* d_jitter = nullptr;
@@ -77,6 +82,8 @@ struct DeviceScene {
         cudaSetDevice(device);
         cudaFree(d_nodes);
         cudaFree(d_refs);
+        cudaFree(d_pnodes);
+        cudaFree(d_prefs);
         cudaFree(d_isect);
         cudaFree(d_shade);
         for (void* p : wave_mem) cudaFree(p);
@@ -165,10 +172,14 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     };
     CUDA_TRY(up(&ds->d_nodes, sc->gpu_nodes.data(), sc->gpu_nodes.size() * sizeof(uint2)));
     CUDA_TRY(up(&ds->d_refs, sc->leaf_refs.data(), sc->leaf_refs.size() * sizeof(uint32_t)));
+    CUDA_TRY(up(&ds->d_pnodes, sc->tree.pair_nodes.data(), sc->tree.pair_nodes.size() * sizeof(uint64_t)));
+    CUDA_TRY(up(&ds->d_prefs, sc->tree.pair_leaf_refs.data(), sc->tree.pair_leaf_refs.size() * sizeof(uint32_t)));
     CUDA_TRY(up(&ds->d_isect, sc->tris.isect.data(), sc->tris.isect.size() * sizeof(float)));
     CUDA_TRY(up(&ds->d_shade, sc->tris.shade.data(), sc->tris.shade.size() * sizeof(float)));
     ds->dev.nodes = static_cast<const uint2*>(ds->d_nodes);
     ds->dev.leaf_refs = static_cast<const uint32_t*>(ds->d_refs);
+    ds->dev.pnodes = static_cast<const uint2*>(ds->d_pnodes);
+    ds->dev.prefs = static_cast<const uint32_t*>(ds->d_prefs);
     ds->dev.isect = static_cast<const float4*>(ds->d_isect);
     ds->dev.shade = static_cast<const float4*>(ds->d_shade);
     for (int c = 0; c < 3; ++c) {
@@ -181,11 +192,38 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     CUDA_TRY(cudaMalloc(&ds->d_counters, ds->counter_slots * sizeof(WaveCounters)));
     CUDA_TRY(cudaMallocHost(&ds->h_counters, ds->counter_slots * sizeof(WaveCounters)));
     CUDA_TRY(cudaMalloc(&ds->d_hitcount, sizeof(unsigned long long)));
-    CUDA_TRY(cudaMalloc(&ds->d_visits, 6 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&ds->d_visits, 12 * sizeof(unsigned long long)));
+    {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        int b0 = 0, b1 = 0, b2 = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, trace_persistent_kernel<0>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, trace_persistent_kernel<1>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, trace_persistent_kernel<2>, 128, 0));
+        ds->grid_closest = std::max(1, b0) * prop.multiProcessorCount;
+        ds->grid_shadow = std::max(1, b1) * prop.multiProcessorCount;
+        ds->grid_plain = std::max(1, b2) * prop.multiProcessorCount;
+    }
     ds->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     *out = ds.get();
     sc->devices[device] = std::move(ds);
     return TRN_OK;
+}
+
+// one WaveCounters slot (wave counts + work cursors) from the ring; the ring is zeroed in bulk when it wraps
+static int alloc_slot(DeviceScene* ds, cudaStream_t stream, uint32_t* out) {
+    if (ds->ring_pos >= ds->counter_slots) {
+        CUDA_TRY(cudaDeviceSynchronize()); // every slot handed out so far has been consumed
+        ds->ring_pos = 0;
+    }
+    if (ds->ring_pos == 0) CUDA_TRY(cudaMemsetAsync(ds->d_counters, 0, ds->counter_slots * sizeof(WaveCounters), stream));
+    *out = ds->ring_pos++;
+    return TRN_OK;
+}
+
+static inline unsigned persistent_grid(int full, uint64_t n) {
+    const uint64_t need = (n + 127) / 128;
+    return static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(full), need)));
 }
 
 static uint64_t env_u64(const char* name, uint64_t dflt) {
@@ -347,20 +385,13 @@ struct Renderer {
     uint64_t rays = 0, prim = 0, shadow = 0, launches = 0;
     uint64_t trace_launches = 0, trace_queries = 0, shadow_launches = 0;
     bool counting = g_counting != 0;
-    uint32_t slot = 0;
+    bool persistent = std::getenv("TRN_PERSISTENT") != nullptr;
     uint64_t cap;
 
     Renderer(DeviceScene* d, const FrameParams& f, int integ, float4* a, cudaStream_t s)
         : ds(d), fp(f), integrator(integ), acc(a), stream(s), timer(s), cap(d->wave_cap) {}
 
-    int next_slot(uint32_t* out) {
-        if (slot >= ds->counter_slots) { // recycle the ring: everything before has been consumed (host synced on each)
-            slot = 0;
-        }
-        if (slot == 0) CUDA_TRY(cudaMemsetAsync(ds->d_counters, 0, ds->counter_slots * sizeof(WaveCounters), stream));
-        *out = slot++;
-        return TRN_OK;
-    }
+    int next_slot(uint32_t* out) { return alloc_slot(ds, stream, out); }
 
     int process(int depth, const RayWave& wave, uint32_t count, uint64_t first_local_index) {
         const int m = fp.mc_samples;
@@ -369,9 +400,15 @@ struct Renderer {
         for (uint64_t off = 0; off < count; off += chunk_max) {
             const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(chunk_max, count - off));
             RayWave w{wave.a + off, wave.b + off, wave.T + off};
+            uint32_t cs;
+            int rc = next_slot(&cs);
+            if (rc) return rc;
             timer.begin(0);
             if (counting)
                 trace_closest_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits, ds->d_visits);
+            else if (persistent)
+                trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, stream>>>(
+                    ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr);
             else
                 trace_closest_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits);
             timer.end();
@@ -387,9 +424,6 @@ struct Renderer {
                 continue;
             }
             rays += n;
-            uint32_t cs;
-            int rc = next_slot(&cs);
-            if (rc) return rc;
             RayWave next = spawn ? ds->waves[depth + 1] : RayWave{nullptr, nullptr, nullptr};
             timer.begin(2);
             shade_bounce_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(ds->dev, fp, first_local_index, w, ds->d_hits, n, depth, next,
@@ -403,6 +437,10 @@ struct Renderer {
                 if (counting)
                     trace_shadow_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_counters + cs, acc,
                                                                                        ds->d_visits + 3);
+                else if (persistent)
+                    trace_persistent_kernel<1><<<persistent_grid(ds->grid_shadow, n), 128, 0, stream>>>(
+                        ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
+                        &ds->d_counters[cs].shadow_cursor, nullptr, acc);
                 else
                     trace_shadow_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_counters + cs, acc);
                 timer.end();
@@ -423,7 +461,7 @@ struct Renderer {
     int run() {
         const uint64_t total = static_cast<uint64_t>(fp.width) * fp.height * static_cast<uint64_t>(fp.n_local);
         if (integrator == TRN_RAYCASTER) CUDA_TRY(cudaMemsetAsync(ds->d_hitcount, 0, sizeof(unsigned long long), stream));
-        if (counting) CUDA_TRY(cudaMemsetAsync(ds->d_visits, 0, 6 * sizeof(unsigned long long), stream));
+        if (counting) CUDA_TRY(cudaMemsetAsync(ds->d_visits, 0, 12 * sizeof(unsigned long long), stream));
         // primaries per batch: as many as fit one wave
         const uint64_t batch = cap;
         for (uint64_t first = 0; first < total; first += batch) {
@@ -490,10 +528,12 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
         stats->trace_queries = r.trace_queries;
         stats->shadow_launches = r.shadow_launches;
         if (r.counting) {
-            unsigned long long v[6];
+            unsigned long long v[12];
             cudaMemcpy(v, ds->d_visits, sizeof v, cudaMemcpyDeviceToHost);
             stats->trace_inner = v[0]; stats->trace_leaf_nodes = v[1]; stats->trace_tri_tests = v[2];
             stats->shadow_inner = v[3]; stats->shadow_leaf_nodes = v[4]; stats->shadow_tri_tests = v[5];
+            stats->trace_actual_inner = v[6]; stats->trace_actual_leaf_nodes = v[7]; stats->trace_actual_tri_tests = v[8];
+            stats->shadow_actual_inner = v[9]; stats->shadow_actual_leaf_nodes = v[10]; stats->shadow_actual_tri_tests = v[11];
         }
         r.timer.collect(stats);
     } else {
@@ -592,6 +632,7 @@ int32_t trn_scene_get_info(const trn_scene* scene, trn_scene_info* info) {
     info->num_nodes = scene->tree.nodes.size();
     info->kdtree_height = scene->tree.height;
     info->num_leaf_refs = scene->tree.num_leaf_refs;
+    info->num_cut_nodes = scene->tree.num_cut_nodes;
     std::memcpy(info->box, scene->tree.box, sizeof info->box);
     info->build_ms = scene->tree.build_ms;
     info->upload_ms = 0;
@@ -636,7 +677,7 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
     CUDA_TRY(cudaMalloc(&d_rst, cn * 12));
     CUDA_TRY(cudaMalloc(&d_h, cn * 16));
     CUDA_TRY(cudaMalloc(&d_ids, cn * 4));
-    if (counts3) CUDA_TRY(cudaMemsetAsync(ds->d_visits, 0, 6 * sizeof(unsigned long long), ds->stream));
+    if (counts3) CUDA_TRY(cudaMemsetAsync(ds->d_visits, 0, 12 * sizeof(unsigned long long), ds->stream));
     for (uint64_t off = 0; off < n; off += chunk) {
         const uint32_t c = static_cast<uint32_t>(std::min<uint64_t>(chunk, n - off));
         CUDA_TRY(cudaMemcpyAsync(d_o, origins + 3 * off, size_t(c) * 12, cudaMemcpyHostToDevice, ds->stream));
@@ -652,9 +693,10 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
     }
     CUDA_TRY(cudaGetLastError());
     if (counts3) {
-        unsigned long long v[3];
+        unsigned long long v[9];
         CUDA_TRY(cudaMemcpy(v, ds->d_visits, sizeof v, cudaMemcpyDeviceToHost));
         counts3[0] = v[0]; counts3[1] = v[1]; counts3[2] = v[2];
+        counts3[3] = v[6]; counts3[4] = v[7]; counts3[5] = v[8];
     }
     cudaFree(d_o);
     cudaFree(d_d);

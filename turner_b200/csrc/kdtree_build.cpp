@@ -112,9 +112,16 @@ struct Event {
     int type; // 0 end, 1 planar, 2 start -- sort order at equal position (lib/kdtree.cpp:254-256,311-316)
 };
 
+inline uint32_t float_bits(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+
 struct BuildNode {
     int axis = -1;
     float split = 0;
+    bool cut = false; // plane with nothing on one side: dropped by the reference layout, kept by the device layout
     BuildNode* left = nullptr;
     BuildNode* right = nullptr;
     std::vector<uint32_t> ids;
@@ -260,24 +267,61 @@ BuildNode* build_rec(Context& ctx, std::vector<uint32_t> ids, const Aabb& box) {
         l = build_rec(ctx, std::move(lt), lb);
         r = build_rec(ctx, std::move(rt), rb);
     }
-    if (!l) return r;
-    if (!r) return l;
+    if (!l && !r) return nullptr;
     BuildNode* n = new BuildNode;
     n->axis = best.axis;
     n->split = best.pos;
     n->left = l;
     n->right = r;
+    n->cut = !l || !r; // lib/kdtree.cpp:168-172 would return the surviving child here
     return n;
 }
 
-inline uint32_t float_bits(float f) {
-    uint32_t u;
-    std::memcpy(&u, &f, 4);
-    return u;
+inline BuildNode* skip_cuts(BuildNode* n) {
+    while (n && n->cut) n = n->left ? n->left : n->right;
+    return n;
+}
+
+// Sibling-pair device layout, cuts included (see kdtree_build.h).
+void flatten_pairs(BuildNode* root, KdTree& out) {
+    auto& nodes = out.pair_nodes;
+    auto& refs = out.pair_leaf_refs;
+    nodes.assign(2, 0);
+    nodes[1] = 3; // padding sibling of the root: an empty leaf
+    struct Item {
+        BuildNode* node;
+        uint32_t slot;
+    };
+    std::vector<Item> stack;
+    stack.push_back({root, 0});
+    out.num_cut_nodes = 0;
+    while (!stack.empty()) {
+        Item it = stack.back();
+        stack.pop_back();
+        BuildNode* n = it.node;
+        if (!n) {
+            nodes[it.slot] = static_cast<uint64_t>(3u) << 32; // empty leaf: count 0
+            continue;
+        }
+        if (n->axis >= 0) {
+            if (n->cut) ++out.num_cut_nodes;
+            const uint32_t pair = static_cast<uint32_t>(nodes.size());
+            nodes.push_back(0);
+            nodes.push_back(0);
+            nodes[it.slot] = (static_cast<uint64_t>((pair << 2) | static_cast<uint32_t>(n->axis)) << 32) | float_bits(n->split);
+            stack.push_back({n->right, pair + 1});
+            stack.push_back({n->left, pair});
+        } else {
+            const uint32_t first = static_cast<uint32_t>(refs.size());
+            refs.insert(refs.end(), n->ids.begin(), n->ids.end());
+            nodes[it.slot] = (static_cast<uint64_t>((static_cast<uint32_t>(n->ids.size()) << 2) | 3u) << 32) | first;
+        }
+    }
 }
 
 // DFS layout of lib/kdtree.cpp:420-467 in the FlatNode encoding of lib/kdtree.h:62-154.
-void flatten_tree(BuildNode* root, KdTree& out) {
+void flatten_tree(BuildNode* root_with_cuts, KdTree& out) {
+    BuildNode* root = skip_cuts(root_with_cuts);
     struct Item {
         BuildNode* node;
         uint32_t parent;
@@ -301,8 +345,8 @@ void flatten_tree(BuildNode* root, KdTree& out) {
         if (n->axis >= 0) {
             nodes.push_back((static_cast<uint64_t>(float_bits(n->split)) << 32) |
                             static_cast<uint32_t>((kInvalid << 2) | static_cast<uint32_t>(n->axis)));
-            stack.push_back({n->right, idx, it.level + 1});
-            stack.push_back({n->left, kInvalid, it.level + 1});
+            stack.push_back({skip_cuts(n->right), idx, it.level + 1});
+            stack.push_back({skip_cuts(n->left), kInvalid, it.level + 1});
         } else {
             const auto& ids = n->ids;
             out.num_leaf_refs += ids.size();
@@ -314,6 +358,17 @@ void flatten_tree(BuildNode* root, KdTree& out) {
             else
                 nodes.push_back(0); // all-zero inner node terminates the leaf run
         }
+    }
+}
+
+void free_tree(BuildNode* root) {
+    std::vector<BuildNode*> stack{root};
+    while (!stack.empty()) {
+        BuildNode* n = stack.back();
+        stack.pop_back();
+        if (!n) continue;
+        stack.push_back(n->left);
+        stack.push_back(n->right);
         delete n;
     }
 }
@@ -388,6 +443,8 @@ void build_kdtree(const HostTriangles& tris, KdTree& out, int num_threads) {
         out.box[3 + c] = box.hi[c];
     }
     flatten_tree(root, out);
+    flatten_pairs(root, out);
+    free_tree(root);
     out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 

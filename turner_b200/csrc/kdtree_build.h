@@ -32,6 +32,17 @@ struct KdTree {
     uint64_t height = 0;
     uint64_t num_leaf_refs = 0;
     double build_ms = 0;
+
+    // Device layout of the SAME tree plus the empty-space cuts the reference throws away
+    // (lib/kdtree.cpp:168-172 returns the non-empty child when the other side of the chosen plane holds no
+    // triangle, so its traversal walks the surviving subtree even where the ray only crosses the cut-off
+    // void). Nodes are 8 bytes, siblings adjacent and 16-byte aligned so one 16-byte load fetches both
+    // children:   inner: x = split bits,       y = (index of the child pair << 2) | axis
+    //             leaf:  x = first reference,  y = (count << 2) | 3        (count 0 = cut-off void)
+    // Node 0 is the root (node 1 pads the pair). Leaves are visited in the reference's order.
+    std::vector<uint64_t> pair_nodes;      // low 32 bits = x, high 32 bits = y
+    std::vector<uint32_t> pair_leaf_refs;  // triangle ids, leaf after leaf
+    uint64_t num_cut_nodes = 0;
 };
 
 // num_threads <= 0: hardware concurrency

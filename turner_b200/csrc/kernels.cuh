@@ -26,6 +26,10 @@ struct DevScene {
     const float4* isect;       // 4 x float4 per triangle: v0.xyz n.x | n.yz u.xy | u.z v.xyz | uv vv uu denom
     const float4* shade;       // 4 x float4 per triangle: n0.xyz n1.x | n1.yz n2.xy | n2.z - - - | rgba
     float lo[3], hi[3];        // KDTree::box()
+    // production layout: sibling pairs + empty-space cuts (kdtree_build.h); `nodes`/`leaf_refs` above hold the
+    // reference-shaped tree and are uploaded only for the instrumented reference-schedule twin
+    const uint2* pnodes;
+    const uint32_t* prefs;
 };
 
 // ray wave, SoA of float4 (fully coalesced 16-byte lanes)
@@ -215,6 +219,110 @@ __device__ __forceinline__ bool traverse(const DevScene& sc, float ox, float oy,
     return out.id != kMiss;
 }
 
+// Production traversal: same visiting order and per-triangle arithmetic as traverse<> above, on the
+// sibling-pair layout with the empty-space cuts kept (kdtree_build.h). One 16-byte load brings both children;
+// the far child's node word travels on the stack, so a pop needs no node load; cut-off voids are never pushed.
+// A void only removes leaves the ray segment does not pass through, which cannot hold the closest hit
+// (tests/test_gpu_parity.py compares against the reference's exhaustive schedule).
+template <bool ANY_HIT, bool COUNT = false>
+__device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, float oy, float oz, float dx, float dy, float dz,
+                                               float tmax_any, HitRec& out, VisitCounts* vc = nullptr) {
+    const float fdx = dx == 0.f ? kEpsDir : dx;
+    const float fdy = dy == 0.f ? kEpsDir : dy;
+    const float fdz = dz == 0.f ? kEpsDir : dz;
+    const float ix = 1 / fdx, iy = 1 / fdy, iz = 1 / fdz;
+
+    float tx1 = (sc.lo[0] - ox) * ix, tx2 = (sc.hi[0] - ox) * ix;
+    float tenter = fminf(tx1, tx2), texit = fmaxf(tx1, tx2);
+    float ty1 = (sc.lo[1] - oy) * iy, ty2 = (sc.hi[1] - oy) * iy;
+    tenter = fmaxf(tenter, fminf(ty1, ty2));
+    texit = fminf(texit, fmaxf(ty1, ty2));
+    float tz1 = (sc.lo[2] - oz) * iz, tz2 = (sc.hi[2] - oz) * iz;
+    tenter = fmaxf(tenter, fminf(tz1, tz2));
+    texit = fminf(texit, fmaxf(tz1, tz2));
+
+    out.id = kMiss;
+    out.r = kFltMax;
+    out.s = 0.f;
+    out.t = 0.f;
+    if (texit < tenter) return false;
+    if (tenter < 0.f) tenter = 0.f;
+
+    uint4 stack[kStackDepth]; // (node.x, node.y, tmin, tmax)
+    int sp = 0;
+    uint2 n = __ldg(&sc.pnodes[0]);
+
+    for (;;) {
+        while ((n.y & 3u) != 3u) {
+            if (COUNT) vc->inner += 1;
+            const int ax = static_cast<int>(n.y & 3u);
+            const float split = __uint_as_float(n.x);
+            const uint4 pair = __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
+            const float o_ax = sel3(ax, ox, oy, oz);
+            const float i_ax = sel3(ax, ix, iy, iz);
+            const float t = (split - o_ax) * i_ax;
+            // left is near unless fixed_ray.d[ax] <= 0 (lib/kdtree.cpp:549-553); sign(d) == sign(1/d), d != 0
+            const bool flip = (__float_as_uint(i_ax) >> 31) != 0u;
+            const uint2 near = flip ? make_uint2(pair.z, pair.w) : make_uint2(pair.x, pair.y);
+            const uint2 far = flip ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
+            if (texit < t) {
+                n = near;
+            } else if (t < tenter) {
+                n = far;
+            } else if (far.y == 3u) { // far side is a cut-off void: nothing to come back for
+                n = near;
+                texit = t;
+            } else if (near.y == 3u) { // near side is a void: go straight to the far side
+                n = far;
+                tenter = t;
+            } else {
+                stack[sp++] = make_uint4(far.x, far.y, __float_as_uint(t), __float_as_uint(texit));
+                n = near;
+                texit = t;
+            }
+        }
+
+        const uint32_t first = n.x, count = n.y >> 2;
+        if (COUNT) vc->leaf_nodes += (count + 1) >> 1;
+        for (uint32_t i = 0; i < count; ++i) {
+            if (COUNT) vc->tri_tests += 1;
+            const uint32_t id = __ldg(&sc.prefs[first + i]);
+            const float4* rec = sc.isect + 4 * static_cast<size_t>(id);
+            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
+            const float nx = q0.w, ny = q1.x, nz = q1.y;
+            const float denom = nx * dx + ny * dy + nz * dz; // lib/intersection.h:40-49
+            if (denom == 0.f) continue;
+            const float nom = nx * (q0.x - ox) + ny * (q0.y - oy) + nz * (q0.z - oz);
+            const float r = nom / denom;
+            if (!(r >= 0.f)) continue;
+            if (ANY_HIT ? !(r <= tmax_any) : !(r < out.r)) continue;
+            const float4 q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
+            const float wx = (ox + r * dx) - q0.x, wy = (oy + r * dy) - q0.y, wz = (oz + r * dz) - q0.z; // :70-71
+            const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
+            const float wv = wx * vx + wy * vy + wz * vz;
+            const float wu = wx * ux + wy * uy + wz * uz;
+            const float s = (q3.x * wv - q3.y * wu) / q3.w; // :78-86
+            if (s < 0.f) continue;
+            const float t = (q3.x * wu - q3.z * wv) / q3.w;
+            if (t < 0.f || 1.f < s + t) continue;
+            out.id = id;
+            out.r = r;
+            out.s = s;
+            out.t = t;
+            if (ANY_HIT) return true;
+        }
+
+        if (out.id != kMiss && out.r <= texit) break;
+        if (sp == 0) break;
+        const uint4 e = stack[--sp];
+        n = make_uint2(e.x, e.y);
+        tenter = __uint_as_float(e.z);
+        texit = __uint_as_float(e.w);
+        if (ANY_HIT && tenter > tmax_any) break;
+    }
+    return out.id != kMiss;
+}
+
 // ---------------------------------------------------------------------- kernels
 
 // raygen: one thread per primary sample of the batch. Batch-relative index rel -> (pixel, local sample j) ->
@@ -255,7 +363,7 @@ __global__ void __launch_bounds__(128) trace_closest_kernel(DevScene sc, const f
     const float4 a = ra[idx];
     const float4 b = rb[idx];
     HitRec h;
-    traverse<false>(sc, a.x, a.y, a.z, a.w, b.x, b.y, 0.f, h);
+    traverse_pairs<false>(sc, a.x, a.y, a.z, a.w, b.x, b.y, 0.f, h);
     hits[idx] = make_uint4(h.id, __float_as_uint(h.r), __float_as_uint(h.s), __float_as_uint(h.t));
 }
 
@@ -266,7 +374,7 @@ __global__ void __launch_bounds__(128) trace_closest_plain_kernel(DevScene sc, c
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= count) return;
     HitRec h;
-    traverse<false>(sc, o[3 * idx], o[3 * idx + 1], o[3 * idx + 2], d[3 * idx], d[3 * idx + 1], d[3 * idx + 2], 0.f, h);
+    traverse_pairs<false>(sc, o[3 * idx], o[3 * idx + 1], o[3 * idx + 2], d[3 * idx], d[3 * idx + 1], d[3 * idx + 2], 0.f, h);
     hits[idx] = make_uint4(h.id, __float_as_uint(h.r), __float_as_uint(h.s), __float_as_uint(h.t));
 }
 
@@ -289,34 +397,39 @@ __global__ void __launch_bounds__(128) trace_closest_count_kernel(DevScene sc, c
                                                                   const float4* __restrict__ rb, uint32_t count,
                                                                   uint4* __restrict__ hits, unsigned long long* g) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    VisitCounts vc{0, 0, 0};
+    VisitCounts vc{0, 0, 0}, vp{0, 0, 0};
     if (idx < count) {
         const float4 a = ra[idx];
         const float4 b = rb[idx];
         HitRec h;
-        traverse<false, true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, 0.f, h, &vc);
+        traverse<false, true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, 0.f, h, &vc);       // reference-shaped schedule: defines B_alg
+        traverse_pairs<false, true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, 0.f, h, &vp); // what the production kernel really visits
         hits[idx] = make_uint4(h.id, __float_as_uint(h.r), __float_as_uint(h.s), __float_as_uint(h.t));
     }
     flush_counts(vc, g);
+    flush_counts(vp, g + 6);
 }
 
 __global__ void __launch_bounds__(128) trace_closest_plain_count_kernel(DevScene sc, const float* __restrict__ o,
                                                                         const float* __restrict__ d, uint32_t count,
                                                                         uint4* __restrict__ hits, unsigned long long* g) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    VisitCounts vc{0, 0, 0};
+    VisitCounts vc{0, 0, 0}, vp{0, 0, 0};
     if (idx < count) {
         HitRec h;
         traverse<false, true>(sc, o[3 * idx], o[3 * idx + 1], o[3 * idx + 2], d[3 * idx], d[3 * idx + 1], d[3 * idx + 2], 0.f, h, &vc);
+        traverse_pairs<false, true>(sc, o[3 * idx], o[3 * idx + 1], o[3 * idx + 2], d[3 * idx], d[3 * idx + 1], d[3 * idx + 2], 0.f, h, &vp);
         hits[idx] = make_uint4(h.id, __float_as_uint(h.r), __float_as_uint(h.s), __float_as_uint(h.t));
     }
     flush_counts(vc, g);
+    flush_counts(vp, g + 6);
 }
 
 struct WaveCounters {
     uint32_t next_count;   // rays appended to the next wave
     uint32_t shadow_count; // shadow rays appended
-    uint32_t pad0, pad1;
+    uint32_t trace_cursor;  // work cursors of the persistent traversal kernels working on this chunk
+    uint32_t shadow_cursor;
 };
 
 __device__ __forceinline__ void accumulate(float4* acc, uint32_t pixel, float4 v) {
@@ -526,7 +639,7 @@ __global__ void __launch_bounds__(128) trace_shadow_kernel(DevScene sc, ShadowWa
     const float4 a = sw.a[idx];
     const float4 b = sw.b[idx];
     HitRec h;
-    const bool occluded = traverse<true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, b.z, h);
+    const bool occluded = traverse_pairs<true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, b.z, h);
     if (!occluded) accumulate(acc, __float_as_uint(b.w), sw.c[idx]);
 }
 
@@ -534,15 +647,17 @@ __global__ void __launch_bounds__(128) trace_shadow_count_kernel(DevScene sc, Sh
                                                                  const WaveCounters* __restrict__ counters,
                                                                  float4* __restrict__ acc, unsigned long long* g) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    VisitCounts vc{0, 0, 0};
+    VisitCounts vc{0, 0, 0}, vp{0, 0, 0};
     if (idx < counters->shadow_count) {
         const float4 a = sw.a[idx];
         const float4 b = sw.b[idx];
         HitRec h;
-        const bool occluded = traverse<true, true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, b.z, h, &vc);
+        traverse<true, true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, b.z, h, &vc);
+        const bool occluded = traverse_pairs<true, true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, b.z, h, &vp);
         if (!occluded) accumulate(acc, __float_as_uint(b.w), sw.c[idx]);
     }
     flush_counts(vc, g);
+    flush_counts(vp, g + 6);
 }
 
 __global__ void unpack_hits_kernel(const uint4* __restrict__ hits, uint32_t count, uint32_t* __restrict__ ids,
