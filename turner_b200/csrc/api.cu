@@ -52,7 +52,8 @@ struct DeviceScene {
     void* d_refs = nullptr;
     void* d_pnodes = nullptr;
     void* d_prefs = nullptr;
-    void* d_isect = nullptr;
+    void* d_isect_hot = nullptr;
+    void* d_isect_cold = nullptr;
     void* d_shade = nullptr;
     // work buffers (sized lazily, reused across calls)
     uint64_t wave_cap = 0;        // rays per wave buffer
@@ -84,7 +85,8 @@ struct DeviceScene {
         cudaFree(d_refs);
         cudaFree(d_pnodes);
         cudaFree(d_prefs);
-        cudaFree(d_isect);
+        cudaFree(d_isect_hot);
+        cudaFree(d_isect_cold);
         cudaFree(d_shade);
         for (void* p : wave_mem) cudaFree(p);
         cudaFree(shadow_mem);
@@ -174,13 +176,23 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     CUDA_TRY(up(&ds->d_refs, sc->leaf_refs.data(), sc->leaf_refs.size() * sizeof(uint32_t)));
     CUDA_TRY(up(&ds->d_pnodes, sc->tree.pair_nodes.data(), sc->tree.pair_nodes.size() * sizeof(uint64_t)));
     CUDA_TRY(up(&ds->d_prefs, sc->tree.pair_leaf_refs.data(), sc->tree.pair_leaf_refs.size() * sizeof(uint32_t)));
-    CUDA_TRY(up(&ds->d_isect, sc->tris.isect.data(), sc->tris.isect.size() * sizeof(float)));
+    {
+        const size_t nt = sc->tris.count;
+        std::vector<float> hot(nt * 8), cold(nt * 8);
+        for (size_t i = 0; i < nt; ++i) {
+            std::memcpy(&hot[i * 8], &sc->tris.isect[i * 16], 8 * sizeof(float));
+            std::memcpy(&cold[i * 8], &sc->tris.isect[i * 16 + 8], 8 * sizeof(float));
+        }
+        CUDA_TRY(up(&ds->d_isect_hot, hot.data(), hot.size() * sizeof(float)));
+        CUDA_TRY(up(&ds->d_isect_cold, cold.data(), cold.size() * sizeof(float)));
+    }
     CUDA_TRY(up(&ds->d_shade, sc->tris.shade.data(), sc->tris.shade.size() * sizeof(float)));
     ds->dev.nodes = static_cast<const uint2*>(ds->d_nodes);
     ds->dev.leaf_refs = static_cast<const uint32_t*>(ds->d_refs);
     ds->dev.pnodes = static_cast<const uint2*>(ds->d_pnodes);
     ds->dev.prefs = static_cast<const uint32_t*>(ds->d_prefs);
-    ds->dev.isect = static_cast<const float4*>(ds->d_isect);
+    ds->dev.isect_hot = static_cast<const float4*>(ds->d_isect_hot);
+    ds->dev.isect_cold = static_cast<const float4*>(ds->d_isect_cold);
     ds->dev.shade = static_cast<const float4*>(ds->d_shade);
     for (int c = 0; c < 3; ++c) {
         ds->dev.lo[c] = sc->tree.box[c];
@@ -225,6 +237,10 @@ static inline unsigned persistent_grid(int full, uint64_t n) {
     const uint64_t need = (n + 127) / 128;
     return static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(full), need)));
 }
+
+// production = one-thread-per-ray traversal kernels; TRN_PERSISTENT=1 selects the persistent-warp variant with lane
+// refill (traverse_persistent.cuh; same results, measured slower on both bench workloads -- profiles/README.md)
+static bool use_persistent() { return std::getenv("TRN_PERSISTENT") != nullptr; }
 
 static uint64_t env_u64(const char* name, uint64_t dflt) {
     const char* v = std::getenv(name);
@@ -385,7 +401,7 @@ struct Renderer {
     uint64_t rays = 0, prim = 0, shadow = 0, launches = 0;
     uint64_t trace_launches = 0, trace_queries = 0, shadow_launches = 0;
     bool counting = g_counting != 0;
-    bool persistent = std::getenv("TRN_PERSISTENT") != nullptr;
+    bool persistent = use_persistent();
     uint64_t cap;
 
     Renderer(DeviceScene* d, const FrameParams& f, int integ, float4* a, cudaStream_t s)
@@ -684,7 +700,13 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
         CUDA_TRY(cudaMemcpyAsync(d_d, dirs + 3 * off, size_t(c) * 12, cudaMemcpyHostToDevice, ds->stream));
         if (counts3)
             trace_closest_plain_count_kernel<<<blocks_for(c, 128), 128, 0, ds->stream>>>(ds->dev, d_o, d_d, c, d_h, ds->d_visits);
-        else
+        else if (use_persistent()) {
+            uint32_t cs;
+            int rc2 = alloc_slot(ds, ds->stream, &cs);
+            if (rc2) return rc2;
+            trace_persistent_kernel<2><<<persistent_grid(ds->grid_plain, c), 128, 0, ds->stream>>>(
+                ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr);
+        } else
             trace_closest_plain_kernel<<<blocks_for(c, 128), 128, 0, ds->stream>>>(ds->dev, d_o, d_d, c, d_h);
         unpack_hits_kernel<<<blocks_for(c, 256), 256, 0, ds->stream>>>(d_h, c, d_ids, d_rst);
         CUDA_TRY(cudaMemcpyAsync(ids + off, d_ids, size_t(c) * 4, cudaMemcpyDeviceToHost, ds->stream));
@@ -733,7 +755,16 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
     for (uint64_t first = 0; first < total; first += cap) {
         const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(cap, total - first));
         raygen_kernel<<<blocks_for(n, 256), 256, 0, ds->stream>>>(fp, ds->d_jitter, first, n, ds->waves[0]);
-        trace_closest_kernel<<<blocks_for(n, 128), 128, 0, ds->stream>>>(ds->dev, ds->waves[0].a, ds->waves[0].b, n, ds->d_hits);
+        if (use_persistent()) {
+            uint32_t cs;
+            rc = alloc_slot(ds, ds->stream, &cs);
+            if (rc) return rc;
+            trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, ds->stream>>>(
+                ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor,
+                ds->d_hits, nullptr);
+        } else {
+            trace_closest_kernel<<<blocks_for(n, 128), 128, 0, ds->stream>>>(ds->dev, ds->waves[0].a, ds->waves[0].b, n, ds->d_hits);
+        }
         unpack_hits_kernel<<<blocks_for(n, 256), 256, 0, ds->stream>>>(ds->d_hits, n, d_ids, d_rst);
         CUDA_TRY(cudaMemcpyAsync(ids + first, d_ids, size_t(n) * 4, cudaMemcpyDeviceToHost, ds->stream));
         CUDA_TRY(cudaMemcpyAsync(rst + 3 * first, d_rst, size_t(n) * 12, cudaMemcpyDeviceToHost, ds->stream));

@@ -23,7 +23,11 @@ constexpr float kFltMax = 3.402823466e+38f;
 struct DevScene {
     const uint2* nodes;        // inner: (split bits, right<<2 | axis)   leaf-run head: (first ref, count<<2 | 3)
     const uint32_t* leaf_refs; // triangle ids of all leaf runs, in the reference's visiting order
-    const float4* isect;       // 4 x float4 per triangle: v0.xyz n.x | n.yz u.xy | u.z v.xyz | uv vv uu denom
+    // intersection records (the reference's precomputed quantities, lib/triangle.h:33-39), split so that the part
+    // every test reads stays L2-resident: hot = 2 x float4 per triangle: v0.xyz n.x | n.yz u.xy  (plane test + first
+    // edge words), cold = 2 x float4: u.z v.xyz | uv vv uu denom (only for candidates that pass 0 <= r < best)
+    const float4* isect_hot;
+    const float4* isect_cold;
     const float4* shade;       // 4 x float4 per triangle: n0.xyz n1.x | n1.yz n2.xy | n2.z - - - | rgba
     float lo[3], hi[3];        // KDTree::box()
     // production layout: sibling pairs + empty-space cuts (kdtree_build.h); `nodes`/`leaf_refs` above hold the
@@ -177,7 +181,7 @@ __device__ __forceinline__ bool traverse(const DevScene& sc, float ox, float oy,
         for (uint32_t i = 0; i < count; ++i) {
             if (COUNT) vc->tri_tests += 1;
             const uint32_t id = __ldg(&sc.leaf_refs[first + i]);
-            const float4* rec = sc.isect + 4 * static_cast<size_t>(id);
+            const float4* rec = sc.isect_hot + 2 * static_cast<size_t>(id);
             const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
             // intersect_ray_plane, lib/intersection.h:40-49
             const float nx = q0.w, ny = q1.x, nz = q1.y;
@@ -189,7 +193,8 @@ __device__ __forceinline__ bool traverse(const DevScene& sc, float ox, float oy,
             // minimum (kdtree.cpp:591,569), resp. lies within tmax for the shadow predicate
             if (!(r >= 0.f)) continue;
             if (ANY_HIT ? !(r <= tmax_any) : !(r < out.r)) continue;
-            const float4 q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
+            const float4* rec2 = sc.isect_cold + 2 * static_cast<size_t>(id);
+            const float4 q2 = __ldg(rec2), q3 = __ldg(rec2 + 1);
             // lib/intersection.h:70-86
             const float wx = (ox + r * dx) - q0.x, wy = (oy + r * dy) - q0.y, wz = (oz + r * dz) - q0.z;
             const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
@@ -287,7 +292,7 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
         for (uint32_t i = 0; i < count; ++i) {
             if (COUNT) vc->tri_tests += 1;
             const uint32_t id = __ldg(&sc.prefs[first + i]);
-            const float4* rec = sc.isect + 4 * static_cast<size_t>(id);
+            const float4* rec = sc.isect_hot + 2 * static_cast<size_t>(id);
             const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
             const float nx = q0.w, ny = q1.x, nz = q1.y;
             const float denom = nx * dx + ny * dy + nz * dz; // lib/intersection.h:40-49
@@ -296,7 +301,8 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
             const float r = nom / denom;
             if (!(r >= 0.f)) continue;
             if (ANY_HIT ? !(r <= tmax_any) : !(r < out.r)) continue;
-            const float4 q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
+            const float4* rec2 = sc.isect_cold + 2 * static_cast<size_t>(id);
+            const float4 q2 = __ldg(rec2), q3 = __ldg(rec2 + 1);
             const float wx = (ox + r * dx) - q0.x, wy = (oy + r * dy) - q0.y, wz = (oz + r * dz) - q0.z; // :70-71
             const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
             const float wv = wx * vx + wy * vy + wz * vz;
