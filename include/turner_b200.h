@@ -187,6 +187,8 @@ typedef struct trn_loaded_scene {
     trn_light light;
 } trn_loaded_scene;
 int32_t trn_load_blend(const char* path, trn_loaded_scene* out);
+/* neutral triangle-soup text file (format in turner_b200/csrc/blend_loader.cpp) -> same structure */
+int32_t trn_load_soup(const char* path, trn_loaded_scene* out);
 void trn_loaded_scene_free(trn_loaded_scene* s);
 
 #ifdef __cplusplus

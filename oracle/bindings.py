@@ -168,7 +168,7 @@ class OracleScene:
         n = o.shape[0]
         ids = np.zeros(n, np.uint32)
         rst = np.zeros((n, 3), np.float32)
-        cnt = np.zeros(4, np.uint64)
+        cnt = np.zeros(8, np.uint64)
         lib().orc_intersect(self.h, o, d, n, mode, ids, rst, cnt.ctypes.data if counters else None)
         return (ids, rst, cnt) if counters else (ids, rst)
 

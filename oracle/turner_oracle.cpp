@@ -483,6 +483,10 @@ struct Scene {
 // ------------------------------------------------------------------- traversal
 struct Counters {
     uint64_t inner = 0, leaf_nodes = 0, tri_tests = 0, queries = 0;
+    // of tri_tests: how many re-test a triangle this ray already tested among its last 4 / 8 / all distinct ones
+    // (triangles straddling several leaves); informs the device kernel's mailbox size
+    uint64_t repeat4 = 0, repeat8 = 0, repeat_any = 0;
+    std::vector<uint32_t> seen;
 };
 
 struct Traverser {
@@ -500,7 +504,18 @@ struct Traverser {
         uint32_t res = kMissId;
         auto test = [&](uint32_t id) {
             float r, s, t;
-            if (c) c->tri_tests += 1;
+            if (c) {
+                c->tri_tests += 1;
+                size_t n = c->seen.size();
+                for (size_t k = 0; k < n; ++k)
+                    if (c->seen[n - 1 - k] == id) {
+                        c->repeat_any += 1;
+                        if (k < 8) c->repeat8 += 1;
+                        if (k < 4) c->repeat4 += 1;
+                        break;
+                    }
+                c->seen.push_back(id);
+            }
             bool hit = ray_triangle(ray, sc.tris[id], r, s, t);
             if (hit && r < mr) {
                 mr = r;
@@ -526,7 +541,10 @@ struct Traverser {
         Ray fixed = ray; // fix_direction, kdtree.cpp:503-511
         for (int ax = 0; ax < 3; ++ax)
             if (fixed.d[ax] == 0) fixed.d[ax] = kEps;
-        if (c) c->queries += 1;
+        if (c) {
+            c->queries += 1;
+            c->seen.clear();
+        }
         float tenter, texit;
         if (!ray_box(fixed, sc.box, tenter, texit)) return kMissId;
         if (early_exit && tenter < 0) tenter = 0;
@@ -857,6 +875,7 @@ void orc_intersect(void* h, const float* o, const float* d, uint64_t n, int32_t 
     }
     if (counters) {
         counters[0] = c.inner; counters[1] = c.leaf_nodes; counters[2] = c.tri_tests; counters[3] = c.queries;
+        counters[4] = c.repeat4; counters[5] = c.repeat8; counters[6] = c.repeat_any;
     }
 }
 

@@ -283,3 +283,16 @@ def test_traversal_counters_equal_oracle(api, ob, scenes):
             i_g, r_g, c_g = p.intersect_counted(ro, rd)
             assert np.array_equal(i_g, i_o) and np.array_equal(bits(r_g), bits(r_o))
             assert c_g[:3].tolist() == c_o[:3].tolist(), (sc["name"], inside, c_g, c_o)
+
+
+def test_single_process_multi_gpu_reduce(api, cornell):
+    # trn_render_multi: sample split over all visible GPUs + ncclReduce(sum) onto the first
+    if api.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sc, p, o = cornell
+    cam, cfg = api.make_config(sc, 96, max_depth=3, mc_samples=2, pixel_samples=6, seed=12)
+    one, s1 = p.render(cam, cfg, device=0)
+    n = min(api.device_count(), 4)
+    many, sn = p.render_multi(cam, cfg, list(range(n)))
+    assert sn.rays == s1.rays and sn.prim_rays == s1.prim_rays
+    assert np.allclose(many, one, rtol=1e-5, atol=1e-5)

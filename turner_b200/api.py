@@ -76,7 +76,7 @@ class LoadedScene(C.Structure):
 EXPORTS = [
     "trn_last_error", "trn_device_count", "trn_scene_create", "trn_scene_destroy", "trn_scene_get_info",
     "trn_scene_get_nodes", "trn_intersect", "trn_primary_hits", "trn_render", "trn_render_device", "trn_render_multi",
-    "trn_set_profiling", "trn_set_counting", "trn_intersect_counted", "trn_camera_setup", "trn_tonemap", "trn_write_p3", "trn_load_blend", "trn_loaded_scene_free",
+    "trn_set_profiling", "trn_set_counting", "trn_intersect_counted", "trn_camera_setup", "trn_tonemap", "trn_write_p3", "trn_load_blend", "trn_load_soup", "trn_loaded_scene_free",
 ]
 
 _lib = None
@@ -120,6 +120,8 @@ def lib():
         L.trn_write_p3.restype = C.c_uint64
         L.trn_write_p3.argtypes = [_f32p, C.c_int32, C.c_int32, C.c_char_p, C.c_uint64]
         L.trn_load_blend.argtypes = [C.c_char_p, C.POINTER(LoadedScene)]
+        L.trn_load_soup.argtypes = [C.c_char_p, C.POINTER(LoadedScene)]
+        L.trn_load_soup.restype = C.c_int32
         L.trn_loaded_scene_free.argtypes = [C.POINTER(LoadedScene)]
         for f in ("trn_scene_create", "trn_scene_get_info", "trn_scene_get_nodes", "trn_intersect", "trn_primary_hits",
                   "trn_intersect_counted",
@@ -288,10 +290,23 @@ def write_p3(rgba):
     return buf.raw[:n].decode()
 
 
+def save_soup(scene, path):
+    """write a scene dict in the neutral triangle-soup text format the CLI reads"""
+    f9 = lambda a: " ".join("%.9g" % float(x) for x in a)
+    with open(path, "w") as f:
+        f.write("# turner_b200 triangle soup: %s\n" % scene.get("name", ""))
+        f.write("camera %s %.9g\n" % (f9(scene["camera"]["trafo4x4"]), scene["camera"]["hfov"]))
+        if scene.get("light"):
+            f.write("light %s %s\n" % (f9(scene["light"]["pos"]), f9(scene["light"]["color"])))
+        for v, n, d in zip(scene["vertices"], scene["normals"], scene["diffuse"]):
+            f.write("tri %s %s %s\n" % (f9(v), f9(n), f9(d)))
+
+
 def load_blend(path):
-    """.blend -> scene dict (same shape as turner_b200.scenes)"""
+    """.blend (or, with any other extension, the neutral soup format) -> scene dict (same shape as turner_b200.scenes)"""
     ls = LoadedScene()
-    _check(lib().trn_load_blend(path.encode(), C.byref(ls)))
+    loader = lib().trn_load_blend if path.endswith(".blend") else lib().trn_load_soup
+    _check(loader(path.encode(), C.byref(ls)))
     try:
         n = ls.num_triangles
         sc = {

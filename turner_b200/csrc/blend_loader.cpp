@@ -300,6 +300,70 @@ int32_t trn_load_blend(const char* path, trn_loaded_scene* out) {
     return TRN_OK;
 }
 
+// Neutral triangle-soup text format, one record per line, '#' starts a comment:
+//   camera <16 floats: node transformation, row-major a1..d4> <hfov radians>
+//   light  <x y z> <r g b a>                       (optional, at most one)
+//   tri    <v0 v1 v2: 9 floats> <n0 n1 n2: 9 floats> <r g b a>
+// Values are what main.cpp:25-82,109-136 would hand to the renderer (world space). Floats are parsed with strtof,
+// so "%.9g" text round-trips fp32 exactly.
+int32_t trn_load_soup(const char* path, trn_loaded_scene* out) {
+    if (!path || !out) return trn::fail(TRN_ERR_INVALID, "null argument");
+    std::memset(out, 0, sizeof *out);
+    FILE* f = std::fopen(path, "r");
+    if (!f) return trn::fail(TRN_ERR_IO, std::string("cannot open ") + path);
+    std::vector<float> verts, norms, cols;
+    std::vector<char> line(1 << 16);
+    int lineno = 0;
+    auto parse = [](char* p, float* dst, int n) {
+        for (int i = 0; i < n; ++i) {
+            char* e = nullptr;
+            dst[i] = std::strtof(p, &e);
+            if (e == p) return false;
+            p = e;
+        }
+        return true;
+    };
+    std::string err;
+    while (std::fgets(line.data(), static_cast<int>(line.size()), f)) {
+        ++lineno;
+        char* p = line.data();
+        while (*p == ' ' || *p == '\t') ++p;
+        if (*p == '#' || *p == '\n' || *p == 0) continue;
+        float v[22];
+        if (std::strncmp(p, "tri", 3) == 0 && parse(p + 3, v, 22)) {
+            verts.insert(verts.end(), v, v + 9);
+            norms.insert(norms.end(), v + 9, v + 18);
+            cols.insert(cols.end(), v + 18, v + 22);
+        } else if (std::strncmp(p, "camera", 6) == 0 && parse(p + 6, v, 17)) {
+            std::memcpy(out->cam_trafo4x4, v, 16 * sizeof(float));
+            out->cam_hfov = v[16];
+            out->cam_aspect = 0.f;
+            out->has_camera += 1;
+        } else if (std::strncmp(p, "light", 5) == 0 && parse(p + 5, v, 7)) {
+            std::memcpy(out->light.pos, v, 3 * sizeof(float));
+            std::memcpy(out->light.rgba, v + 3, 4 * sizeof(float));
+            out->num_lights += 1;
+        } else {
+            err = std::string(path) + ":" + std::to_string(lineno) + ": malformed record";
+            break;
+        }
+    }
+    std::fclose(f);
+    if (!err.empty()) return trn::fail(TRN_ERR_IO, err);
+    if (out->has_camera != 1) return trn::fail(TRN_ERR_IO, "scene must contain exactly one camera (main.cpp:110)");
+    if (out->num_lights > 1) return trn::fail(TRN_ERR_IO, "scene must contain at most one light (main.cpp:123)");
+    const size_t n = cols.size() / 4;
+    if (n == 0) return trn::fail(TRN_ERR_IO, "scene has no triangles");
+    out->num_triangles = static_cast<uint32_t>(n);
+    out->verts = static_cast<float*>(std::malloc(n * 9 * sizeof(float)));
+    out->normals = static_cast<float*>(std::malloc(n * 9 * sizeof(float)));
+    out->diffuse = static_cast<float*>(std::malloc(n * 4 * sizeof(float)));
+    std::memcpy(out->verts, verts.data(), n * 9 * sizeof(float));
+    std::memcpy(out->normals, norms.data(), n * 9 * sizeof(float));
+    std::memcpy(out->diffuse, cols.data(), n * 4 * sizeof(float));
+    return TRN_OK;
+}
+
 void trn_loaded_scene_free(trn_loaded_scene* s) {
     if (!s) return;
     std::free(s->verts);

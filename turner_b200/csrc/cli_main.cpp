@@ -281,7 +281,8 @@ int main(int argc, char const* argv[]) {
 
     std::cerr << "Loading scene..." << std::endl; // main.cpp:97
     trn_loaded_scene ls;
-    if (trn_load_blend(o.filename.c_str(), &ls) != TRN_OK) {
+    const bool is_blend = o.filename.size() >= 6 && o.filename.compare(o.filename.size() - 6, 6, ".blend") == 0;
+    if ((is_blend ? trn_load_blend(o.filename.c_str(), &ls) : trn_load_soup(o.filename.c_str(), &ls)) != TRN_OK) {
         std::cout << trn_last_error() << std::endl; // main.cpp:104-107: import errors go to stdout, exit code 1
         return 1;
     }
