@@ -212,6 +212,13 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, trace_persistent_kernel<0>, 128, 0));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, trace_persistent_kernel<1>, 128, 0));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, trace_persistent_kernel<2>, 128, 0));
+        int w0 = 0, w1 = 0, w2 = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w0, trace_persistent_ww_kernel<0>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w1, trace_persistent_ww_kernel<1>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w2, trace_persistent_ww_kernel<2>, 128, 0));
+        b0 = std::min(b0, w0);
+        b1 = std::min(b1, w1);
+        b2 = std::min(b2, w2);
         ds->grid_closest = std::max(1, b0) * prop.multiProcessorCount;
         ds->grid_shadow = std::max(1, b1) * prop.multiProcessorCount;
         ds->grid_plain = std::max(1, b2) * prop.multiProcessorCount;
@@ -240,7 +247,15 @@ static inline unsigned persistent_grid(int full, uint64_t n) {
 
 // production = one-thread-per-ray traversal kernels; TRN_PERSISTENT=1 selects the persistent-warp variant with lane
 // refill (traverse_persistent.cuh; same results, measured slower on both bench workloads -- profiles/README.md)
-static bool use_persistent() { return std::getenv("TRN_PERSISTENT") != nullptr; }
+// Scheduling of rays onto lanes (results are identical in every mode; profiles/README.md has the A/B numbers):
+//   closest-hit waves: persistent warps with lane refill, while-while quantum (mode 2) -- +26 % over one thread per ray
+//   shadow waves:      one thread per ray (mode 0) -- short any-hit walks, refill overhead does not pay
+// TRN_PERSISTENT=0|1|2 forces one mode for both (1 = per-step state machine).
+static int persistent_mode(bool shadow) {
+    const char* v = std::getenv("TRN_PERSISTENT");
+    if (v) return std::atoi(v);
+    return shadow ? 0 : 2;
+}
 
 static uint64_t env_u64(const char* name, uint64_t dflt) {
     const char* v = std::getenv(name);
@@ -401,7 +416,7 @@ struct Renderer {
     uint64_t rays = 0, prim = 0, shadow = 0, launches = 0;
     uint64_t trace_launches = 0, trace_queries = 0, shadow_launches = 0;
     bool counting = g_counting != 0;
-    bool persistent = use_persistent();
+    int mode_closest = persistent_mode(false), mode_shadow = persistent_mode(true);
     uint64_t cap;
 
     Renderer(DeviceScene* d, const FrameParams& f, int integ, float4* a, cudaStream_t s)
@@ -422,7 +437,11 @@ struct Renderer {
             timer.begin(0);
             if (counting)
                 trace_closest_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits, ds->d_visits);
-            else if (persistent)
+            else if (mode_closest == 2)
+                trace_persistent_ww_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, stream>>>(
+                    ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr,
+                    static_cast<int>(env_u64("TRN_REFILL", 28)), static_cast<int>(env_u64("TRN_QUANTA", 2)));
+            else if (mode_closest == 1)
                 trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, stream>>>(
                     ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr);
             else
@@ -453,7 +472,12 @@ struct Renderer {
                 if (counting)
                     trace_shadow_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_counters + cs, acc,
                                                                                        ds->d_visits + 3);
-                else if (persistent)
+                else if (mode_shadow == 2)
+                    trace_persistent_ww_kernel<1><<<persistent_grid(ds->grid_shadow, n), 128, 0, stream>>>(
+                        ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
+                        &ds->d_counters[cs].shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_REFILL", 26)),
+                        static_cast<int>(env_u64("TRN_QUANTA", 2)));
+                else if (mode_shadow == 1)
                     trace_persistent_kernel<1><<<persistent_grid(ds->grid_shadow, n), 128, 0, stream>>>(
                         ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
                         &ds->d_counters[cs].shadow_cursor, nullptr, acc);
@@ -700,12 +724,16 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
         CUDA_TRY(cudaMemcpyAsync(d_d, dirs + 3 * off, size_t(c) * 12, cudaMemcpyHostToDevice, ds->stream));
         if (counts3)
             trace_closest_plain_count_kernel<<<blocks_for(c, 128), 128, 0, ds->stream>>>(ds->dev, d_o, d_d, c, d_h, ds->d_visits);
-        else if (use_persistent()) {
+        else if (persistent_mode(false) != 0) {
             uint32_t cs;
             int rc2 = alloc_slot(ds, ds->stream, &cs);
             if (rc2) return rc2;
-            trace_persistent_kernel<2><<<persistent_grid(ds->grid_plain, c), 128, 0, ds->stream>>>(
-                ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr);
+            if (persistent_mode(false) == 2)
+                trace_persistent_ww_kernel<2><<<persistent_grid(ds->grid_plain, c), 128, 0, ds->stream>>>(
+                    ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr, 28, 2);
+            else
+                trace_persistent_kernel<2><<<persistent_grid(ds->grid_plain, c), 128, 0, ds->stream>>>(
+                    ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr);
         } else
             trace_closest_plain_kernel<<<blocks_for(c, 128), 128, 0, ds->stream>>>(ds->dev, d_o, d_d, c, d_h);
         unpack_hits_kernel<<<blocks_for(c, 256), 256, 0, ds->stream>>>(d_h, c, d_ids, d_rst);
@@ -755,13 +783,18 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
     for (uint64_t first = 0; first < total; first += cap) {
         const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(cap, total - first));
         raygen_kernel<<<blocks_for(n, 256), 256, 0, ds->stream>>>(fp, ds->d_jitter, first, n, ds->waves[0]);
-        if (use_persistent()) {
+        if (persistent_mode(false) != 0) {
             uint32_t cs;
             rc = alloc_slot(ds, ds->stream, &cs);
             if (rc) return rc;
-            trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, ds->stream>>>(
-                ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor,
-                ds->d_hits, nullptr);
+            if (persistent_mode(false) == 2)
+                trace_persistent_ww_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, ds->stream>>>(
+                    ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr,
+                    &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2);
+            else
+                trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, ds->stream>>>(
+                    ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr,
+                    &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr);
         } else {
             trace_closest_kernel<<<blocks_for(n, 128), 128, 0, ds->stream>>>(ds->dev, ds->waves[0].a, ds->waves[0].b, n, ds->d_hits);
         }

@@ -18,6 +18,7 @@ constexpr float kEpsDir = 0.00001f;            // EPS, lib/types.h:13 (fix_direc
 constexpr uint32_t kMiss = 0x40000000u;         // OptionalId miss, lib/kdtree.h:156-161
 constexpr int kStackDepth = 64;                 // >= tree height + 1 (checked at scene creation)
 constexpr float kFltMax = 3.402823466e+38f;
+constexpr float kCellSlack = 1e-4f;             // relative slack of the per-cell hit range (see traverse_pairs)
 
 // ------------------------------------------------------------------ device scene
 struct DevScene {
@@ -236,6 +237,7 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
     const float fdy = dy == 0.f ? kEpsDir : dy;
     const float fdz = dz == 0.f ? kEpsDir : dz;
     const float ix = 1 / fdx, iy = 1 / fdy, iz = 1 / fdz;
+    const bool axis_parallel = dx == 0.f || dy == 0.f || dz == 0.f;
 
     float tx1 = (sc.lo[0] - ox) * ix, tx2 = (sc.hi[0] - ox) * ix;
     float tenter = fminf(tx1, tx2), texit = fmaxf(tx1, tx2);
@@ -289,6 +291,13 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
 
         const uint32_t first = n.x, count = n.y >> 2;
         if (COUNT) vc->leaf_nodes += (count + 1) >> 1;
+        // Only plane hits inside this cell's parameter range (plus slack) go on to the barycentric part: a hit of
+        // this triangle outside the cell is found again in the cell that contains it (the triangle is referenced
+        // there too), so nothing is lost and ~4 of 5 barycentric evaluations are saved.
+        // Not for rays with an exact-zero direction component: their traversal interval belongs to the "fixed"
+        // direction (lib/kdtree.cpp:503-511), not to the ray the triangles are tested with.
+        const float r_lo = axis_parallel ? -kFltMax : tenter - kCellSlack * (fabsf(tenter) + 1.f);
+        const float r_hi = axis_parallel ? kFltMax : texit + kCellSlack * (fabsf(texit) + 1.f);
         for (uint32_t i = 0; i < count; ++i) {
             if (COUNT) vc->tri_tests += 1;
             const uint32_t id = __ldg(&sc.prefs[first + i]);
@@ -301,6 +310,7 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
             const float r = nom / denom;
             if (!(r >= 0.f)) continue;
             if (ANY_HIT ? !(r <= tmax_any) : !(r < out.r)) continue;
+            if (!(r >= r_lo && r <= r_hi)) continue;
             const float4* rec2 = sc.isect_cold + 2 * static_cast<size_t>(id);
             const float4 q2 = __ldg(rec2), q3 = __ldg(rec2 + 1);
             const float wx = (ox + r * dx) - q0.x, wy = (oy + r * dy) - q0.y, wz = (oz + r * dz) - q0.z; // :70-71
