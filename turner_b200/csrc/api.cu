@@ -25,6 +25,13 @@
 #include <thread>
 #include <vector>
 
+// launch trace_persistent_ww_kernel<MODE, two_pass>
+#define TRN_LAUNCH_WW(MODE, two_pass, grid, stream, ...)                                              \
+    do {                                                                                              \
+        if (two_pass) trace_persistent_ww_kernel<MODE, true><<<(grid), 128, 0, (stream)>>>(__VA_ARGS__);  \
+        else trace_persistent_ww_kernel<MODE, false><<<(grid), 128, 0, (stream)>>>(__VA_ARGS__);          \
+    } while (0)
+
 namespace trn {
 
 thread_local std::string g_last_error;
@@ -66,6 +73,7 @@ struct DeviceScene {
     WaveCounters* h_counters = nullptr;  // pinned mirror
     uint32_t counter_slots = 0;
     uint32_t ring_pos = 0;
+    bool two_pass = true; // leaf evaluation schedule of the persistent kernels (small leaves: two-pass)
     int grid_closest = 0, grid_shadow = 0, grid_plain = 0; // persistent grids: resident CTAs per SM x SMs
     unsigned long long* d_hitcount = nullptr;
     unsigned long long* d_visits = nullptr; // [6]: closest inner/leaf/tri, shadow inner/leaf/tri
@@ -198,6 +206,15 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
         ds->dev.lo[c] = sc->tree.box[c];
         ds->dev.hi[c] = sc->tree.box[3 + c];
     }
+    {
+        // average triangles per non-empty leaf decides the leaf schedule (a one-leaf scene like cornell_box: one pass)
+        uint64_t leaves = 0;
+        for (uint64_t nd : sc->tree.pair_nodes) {
+            const uint32_t y = static_cast<uint32_t>(nd >> 32);
+            if ((y & 3u) == 3u && (y >> 2) > 0) ++leaves;
+        }
+        ds->two_pass = leaves > 0 && static_cast<double>(sc->tree.pair_leaf_refs.size()) / static_cast<double>(leaves) <= 6.0;
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_sync, cudaEventDisableTiming));
     ds->counter_slots = 4096;
@@ -213,9 +230,9 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, trace_persistent_kernel<1>, 128, 0));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, trace_persistent_kernel<2>, 128, 0));
         int w0 = 0, w1 = 0, w2 = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w0, trace_persistent_ww_kernel<0>, 128, 0));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w1, trace_persistent_ww_kernel<1>, 128, 0));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w2, trace_persistent_ww_kernel<2>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w0, trace_persistent_ww_kernel<0, true>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w1, trace_persistent_ww_kernel<1, true>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w2, trace_persistent_ww_kernel<2, true>, 128, 0));
         b0 = std::min(b0, w0);
         b1 = std::min(b1, w1);
         b2 = std::min(b2, w2);
@@ -438,7 +455,7 @@ struct Renderer {
             if (counting)
                 trace_closest_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits, ds->d_visits);
             else if (mode_closest == 2)
-                trace_persistent_ww_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, stream>>>(
+                TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), stream,
                     ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr,
                     static_cast<int>(env_u64("TRN_REFILL", 28)), static_cast<int>(env_u64("TRN_QUANTA", 2)));
             else if (mode_closest == 1)
@@ -473,7 +490,7 @@ struct Renderer {
                     trace_shadow_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_counters + cs, acc,
                                                                                        ds->d_visits + 3);
                 else if (mode_shadow == 2)
-                    trace_persistent_ww_kernel<1><<<persistent_grid(ds->grid_shadow, n), 128, 0, stream>>>(
+                    TRN_LAUNCH_WW(1, ds->two_pass, persistent_grid(ds->grid_shadow, n), stream,
                         ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
                         &ds->d_counters[cs].shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_REFILL", 26)),
                         static_cast<int>(env_u64("TRN_QUANTA", 2)));
@@ -729,7 +746,7 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
             int rc2 = alloc_slot(ds, ds->stream, &cs);
             if (rc2) return rc2;
             if (persistent_mode(false) == 2)
-                trace_persistent_ww_kernel<2><<<persistent_grid(ds->grid_plain, c), 128, 0, ds->stream>>>(
+                TRN_LAUNCH_WW(2, ds->two_pass, persistent_grid(ds->grid_plain, c), ds->stream,
                     ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr, 28, 2);
             else
                 trace_persistent_kernel<2><<<persistent_grid(ds->grid_plain, c), 128, 0, ds->stream>>>(
@@ -788,7 +805,7 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
             rc = alloc_slot(ds, ds->stream, &cs);
             if (rc) return rc;
             if (persistent_mode(false) == 2)
-                trace_persistent_ww_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, ds->stream>>>(
+                TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), ds->stream,
                     ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr,
                     &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2);
             else

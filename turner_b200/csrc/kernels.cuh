@@ -365,9 +365,10 @@ __global__ void __launch_bounds__(256) raygen_kernel(FrameParams fp, const float
     const float dx = m[0] * vx + m[1] * vy + m[2] * vz;
     const float dy = m[3] * vx + m[4] * vy + m[5] * vz;
     const float dz = m[6] * vx + m[7] * vy + m[8] * vz;
-    out.a[rel] = make_float4(fp.cam.pos[0], fp.cam.pos[1], fp.cam.pos[2], dx);
-    out.b[rel] = make_float4(dy, dz, __uint_as_float(rel), __uint_as_float(0u));
-    out.T[rel] = make_float4(1.f, 1.f, 1.f, 1.f);
+    // waves are streamed once: evict-first stores/loads (.cs) keep the scene arrays resident in L2
+    __stcs(&out.a[rel], make_float4(fp.cam.pos[0], fp.cam.pos[1], fp.cam.pos[2], dx));
+    __stcs(&out.b[rel], make_float4(dy, dz, __uint_as_float(rel), __uint_as_float(0u)));
+    __stcs(&out.T[rel], make_float4(1.f, 1.f, 1.f, 1.f));
 }
 
 // closest hit for a wave of rays; one thread per ray
@@ -376,11 +377,11 @@ __global__ void __launch_bounds__(128) trace_closest_kernel(DevScene sc, const f
                                                             uint4* __restrict__ hits) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= count) return;
-    const float4 a = ra[idx];
-    const float4 b = rb[idx];
+    const float4 a = __ldcs(&ra[idx]);
+    const float4 b = __ldcs(&rb[idx]);
     HitRec h;
     traverse_pairs<false>(sc, a.x, a.y, a.z, a.w, b.x, b.y, 0.f, h);
-    hits[idx] = make_uint4(h.id, __float_as_uint(h.r), __float_as_uint(h.s), __float_as_uint(h.t));
+    __stcs(&hits[idx], make_uint4(h.id, __float_as_uint(h.r), __float_as_uint(h.s), __float_as_uint(h.t)));
 }
 
 // plain (o, d) arrays in, for trn_intersect
@@ -481,10 +482,10 @@ __global__ void __launch_bounds__(256) shade_bounce_kernel(DevScene sc, FramePar
     uint4 h;
     uint32_t rel = 0, node = 0, pixel = 0, sample_i = 0;
     if (valid) {
-        a = cur.a[idx];
-        b = cur.b[idx];
-        T = cur.T[idx];
-        h = hits[idx];
+        a = __ldcs(&cur.a[idx]);
+        b = __ldcs(&cur.b[idx]);
+        T = __ldcs(&cur.T[idx]);
+        h = __ldcs(&hits[idx]);
         rel = __float_as_uint(b.z);
         node = __float_as_uint(b.w);
         pixel = pixel_of(fp, first_local_index, rel, sample_i);
@@ -540,9 +541,9 @@ __global__ void __launch_bounds__(256) shade_bounce_kernel(DevScene sc, FramePar
         sbase = __shfl_sync(0xffffffffu, sbase, 0);
         if (want_shadow) {
             const uint32_t slot = sbase + __popc(smask & ((1u << lane) - 1u));
-            shadow.a[slot] = make_float4(p2x, p2y, p2z, ldx);
-            shadow.b[slot] = make_float4(ldy, ldz, ldist, __uint_as_float(pixel));
-            shadow.c[slot] = contrib;
+            __stcs(&shadow.a[slot], make_float4(p2x, p2y, p2z, ldx));
+            __stcs(&shadow.b[slot], make_float4(ldy, ldz, ldist, __uint_as_float(pixel)));
+            __stcs(&shadow.c[slot], contrib);
         }
     }
 
@@ -611,9 +612,9 @@ __global__ void __launch_bounds__(256) shade_bounce_kernel(DevScene sc, FramePar
         const float dz = m20 * lx + m21 * ly + m22 * lz;
         const float wgt = (2.f * u1) / fm; // pathtracer.cpp:84,88,100-101: rho * 2 * (cos / m)
         const uint32_t slot = cbase + static_cast<uint32_t>(k) * nh + rank;
-        next.a[slot] = make_float4(p2x, p2y, p2z, dx);
-        next.b[slot] = make_float4(dy, dz, __uint_as_float(rel), __uint_as_float(child));
-        next.T[slot] = make_float4(T.x * (rho.x * wgt), T.y * (rho.y * wgt), T.z * (rho.z * wgt), T.w * (rho.w * wgt));
+        __stcs(&next.a[slot], make_float4(p2x, p2y, p2z, dx));
+        __stcs(&next.b[slot], make_float4(dy, dz, __uint_as_float(rel), __uint_as_float(child)));
+        __stcs(&next.T[slot], make_float4(T.x * (rho.x * wgt), T.y * (rho.y * wgt), T.z * (rho.z * wgt), T.w * (rho.w * wgt)));
     }
 }
 
@@ -652,11 +653,11 @@ __global__ void __launch_bounds__(128) trace_shadow_kernel(DevScene sc, ShadowWa
                                                            float4* __restrict__ acc) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= counters->shadow_count) return;
-    const float4 a = sw.a[idx];
-    const float4 b = sw.b[idx];
+    const float4 a = __ldcs(&sw.a[idx]);
+    const float4 b = __ldcs(&sw.b[idx]);
     HitRec h;
     const bool occluded = traverse_pairs<true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, b.z, h);
-    if (!occluded) accumulate(acc, __float_as_uint(b.w), sw.c[idx]);
+    if (!occluded) accumulate(acc, __float_as_uint(b.w), __ldcs(&sw.c[idx]));
 }
 
 __global__ void __launch_bounds__(128) trace_shadow_count_kernel(DevScene sc, ShadowWave sw,

@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(128) trace_persistent_kernel(DevScene sc, cons
                         ox = po[3 * idx]; oy = po[3 * idx + 1]; oz = po[3 * idx + 2];
                         dx = pd[3 * idx]; dy = pd[3 * idx + 1]; dz = pd[3 * idx + 2];
                     } else {
-                        const float4 a = ra[idx];
-                        const float4 b = rb[idx];
+                        const float4 a = __ldcs(&ra[idx]);
+                        const float4 b = __ldcs(&rb[idx]);
                         ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
                         if (ANY) tmax_any = b.z;
                     }
@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(128) trace_persistent_kernel(DevScene sc, cons
                     best_s = 0.f;
                     best_t = 0.f;
                     if (t1 < t0) { // misses the scene box: done on the spot
-                        if (ANY) accumulate(acc, __float_as_uint(rb[idx].w), rc[idx]);
-                        else hits[idx] = make_uint4(kMiss, __float_as_uint(kFltMax), 0u, 0u);
+                        if (ANY) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx]));
+                        else __stcs(&hits[idx], make_uint4(kMiss, __float_as_uint(kFltMax), 0u, 0u));
                     } else {
                         tenter = t0 < 0.f ? 0.f : t0;
                         texit = t1;
@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(128) trace_persistent_kernel(DevScene sc, cons
                 }
                 if (finished) {
                     busy = false;
-                    if (ANY) accumulate(acc, __float_as_uint(rb[idx].w), rc[idx]); // reached the end unoccluded
-                    else hits[idx] = make_uint4(best_id, __float_as_uint(best_r), __float_as_uint(best_s), __float_as_uint(best_t));
+                    if (ANY) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx])); // reached the end unoccluded
+                    else __stcs(&hits[idx], make_uint4(best_id, __float_as_uint(best_r), __float_as_uint(best_s), __float_as_uint(best_t)));
                 }
             }
         }
@@ -239,10 +239,38 @@ __global__ void __launch_bounds__(128) trace_persistent_kernel(DevScene sc, cons
 }
 
 
+// Barycentric part of intersect_ray_triangle (lib/intersection.h:70-86) for a triangle whose plane distance r already
+// passed 0 <= r; re-checks r < best (strict: the first-visited triangle keeps a tie). Returns true only in ANY mode
+// when the triangle is hit (occluder found).
+template <bool ANY>
+__device__ __forceinline__ bool test_candidate(const DevScene& sc, uint32_t id, float r, float ox, float oy, float oz, float dx,
+                                               float dy, float dz, uint32_t& best_id, float& best_r, float& best_s, float& best_t) {
+    if (!ANY && !(r < best_r)) return false;
+    const float4* rec = sc.isect_hot + 2 * static_cast<size_t>(id);
+    const float4* rec2 = sc.isect_cold + 2 * static_cast<size_t>(id);
+    const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec2), q3 = __ldg(rec2 + 1);
+    const float wx = (ox + r * dx) - q0.x, wy = (oy + r * dy) - q0.y, wz = (oz + r * dz) - q0.z;
+    const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
+    const float wv = wx * vx + wy * vy + wz * vz;
+    const float wu = wx * ux + wy * uy + wz * uz;
+    const float s = (q3.x * wv - q3.y * wu) / q3.w;
+    if (s < 0.f) return false;
+    const float t = (q3.x * wu - q3.z * wv) / q3.w;
+    if (t < 0.f || 1.f < s + t) return false;
+    best_id = id;
+    best_r = r;
+    best_s = s;
+    best_t = t;
+    return ANY;
+}
+
+
 // Variant 2 ("while-while" quantum): same persistent warps + lane refill, but one scheduling quantum of a lane is
 // "walk down to the next leaf, test its triangles, pop" -- the loop body of traverse_pairs<> -- instead of a
 // single state-machine step. Fewer bookkeeping instructions per unit of work, coarser balancing.
-template <int MODE>
+// TWO_PASS: leaves are evaluated as "all plane tests, then the recorded survivors" (best for trees with small leaves);
+// otherwise in one pass (best when a leaf holds many triangles, e.g. a scene that is a single leaf). Chosen per scene.
+template <int MODE, bool TWO_PASS>
 __global__ void __launch_bounds__(128) trace_persistent_ww_kernel(DevScene sc, const float4* __restrict__ ra,
                                                                   const float4* __restrict__ rb,
                                                                   const float4* __restrict__ rc, const float* __restrict__ po,
@@ -290,8 +318,8 @@ __global__ void __launch_bounds__(128) trace_persistent_ww_kernel(DevScene sc, c
                         ox = po[3 * idx]; oy = po[3 * idx + 1]; oz = po[3 * idx + 2];
                         dx = pd[3 * idx]; dy = pd[3 * idx + 1]; dz = pd[3 * idx + 2];
                     } else {
-                        const float4 a = ra[idx];
-                        const float4 b = rb[idx];
+                        const float4 a = __ldcs(&ra[idx]);
+                        const float4 b = __ldcs(&rb[idx]);
                         ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
                         if (ANY) tmax_any = b.z;
                     }
@@ -314,8 +342,8 @@ __global__ void __launch_bounds__(128) trace_persistent_ww_kernel(DevScene sc, c
                     best_s = 0.f;
                     best_t = 0.f;
                     if (t1 < t0) {
-                        if (ANY) accumulate(acc, __float_as_uint(rb[idx].w), rc[idx]);
-                        else hits[idx] = make_uint4(kMiss, __float_as_uint(kFltMax), 0u, 0u);
+                        if (ANY) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx]));
+                        else __stcs(&hits[idx], make_uint4(kMiss, __float_as_uint(kFltMax), 0u, 0u));
                     } else {
                         tenter = t0 < 0.f ? 0.f : t0;
                         texit = t1;
@@ -346,28 +374,58 @@ __global__ void __launch_bounds__(128) trace_persistent_ww_kernel(DevScene sc, c
                 const bool flip = (__float_as_uint(i_ax) >> 31) != 0u;
                 const uint2 near = flip ? make_uint2(pair.z, pair.w) : make_uint2(pair.x, pair.y);
                 const uint2 far = flip ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
-                if (texit < t) {
-                    n = near;
-                } else if (t < tenter) {
-                    n = far;
-                } else if (far.y == 3u) {
-                    n = near;
-                    texit = t;
-                } else if (near.y == 3u) {
-                    n = far;
-                    tenter = t;
-                } else {
-                    stack[sp++] = make_uint4(far.x, far.y, __float_as_uint(t), __float_as_uint(texit));
-                    n = near;
-                    texit = t;
-                }
+                // lib/kdtree.cpp:555-563 without divergent branches: near only | far only | both (far pushed), with the
+                // cut-off voids (count-0 leaves, y == 3) never entered nor pushed
+                const bool near_only = texit < t;
+                const bool far_only = !near_only && (t < tenter);
+                const bool both = !near_only && !far_only;
+                const bool go_far = far_only || (both && near.y == 3u);
+                if (both && near.y != 3u && far.y != 3u) stack[sp++] = make_uint4(far.x, far.y, __float_as_uint(t), __float_as_uint(texit));
+                n = go_far ? far : near;
+                tenter = (both && go_far) ? t : tenter;
+                texit = (both && !go_far) ? t : texit;
             }
             const uint32_t first = n.x, cnt = n.y >> 2;
             bool occluded = false;
             const bool axis_parallel = dx == 0.f || dy == 0.f || dz == 0.f; // see traverse_pairs<>
             const float r_lo = axis_parallel ? -kFltMax : tenter - kCellSlack * (fabsf(tenter) + 1.f);
             const float r_hi = axis_parallel ? kFltMax : texit + kCellSlack * (fabsf(texit) + 1.f);
-            for (uint32_t i = 0; i < cnt; ++i) {
+            // Two passes over the leaf so that the lanes of the warp stay together: first the plane test of every
+            // triangle (lib/intersection.h:40-49), which only RECORDS the few survivors (0 <= r < best, r inside the
+            // cell); then the barycentric part (intersection.h:70-86) for the recorded ones, in visiting order and
+            // re-checking r < best, i.e. with exactly the accept/replace decisions of the one-pass loop.
+            uint32_t c0_id = 0, c1_id = 0;
+            float c0_r = 0.f, c1_r = 0.f;
+            int ncand = 0;
+            const uint32_t cnt_two_pass = TWO_PASS ? cnt : 0u;
+            for (uint32_t i = 0; i < cnt_two_pass; ++i) {
+                const uint32_t id = __ldg(&sc.prefs[first + i]);
+                const float4* rec = sc.isect_hot + 2 * static_cast<size_t>(id);
+                const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
+                const float nx = q0.w, ny = q1.x, nz = q1.y;
+                const float denom = nx * dx + ny * dy + nz * dz;
+                const float nom = nx * (q0.x - ox) + ny * (q0.y - oy) + nz * (q0.z - oz);
+                const float r = nom / denom;
+                const bool cand = denom != 0.f && r >= 0.f && (ANY ? (r <= tmax_any) : (r < best_r)) && r >= r_lo && r <= r_hi;
+                if (cand) {
+                    if (ncand == 2) { // rare: drain the two recorded survivors first (keeps visiting order)
+                        if (test_candidate<ANY>(sc, c0_id, c0_r, ox, oy, oz, dx, dy, dz, best_id, best_r, best_s, best_t)) occluded = true;
+                        if (!occluded && test_candidate<ANY>(sc, c1_id, c1_r, ox, oy, oz, dx, dy, dz, best_id, best_r, best_s, best_t)) occluded = true;
+                        ncand = 0;
+                    }
+                    if (ncand == 0) {
+                        c0_id = id;
+                        c0_r = r;
+                    } else {
+                        c1_id = id;
+                        c1_r = r;
+                    }
+                    ++ncand;
+                }
+            }
+            if (ncand > 0 && !occluded && test_candidate<ANY>(sc, c0_id, c0_r, ox, oy, oz, dx, dy, dz, best_id, best_r, best_s, best_t)) occluded = true;
+            if (ncand > 1 && !occluded && test_candidate<ANY>(sc, c1_id, c1_r, ox, oy, oz, dx, dy, dz, best_id, best_r, best_s, best_t)) occluded = true;
+            for (uint32_t i = cnt_two_pass; !TWO_PASS && i < cnt && !occluded; ++i) {
                 const uint32_t id = __ldg(&sc.prefs[first + i]);
                 const float4* rec = sc.isect_hot + 2 * static_cast<size_t>(id);
                 const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
@@ -379,24 +437,7 @@ __global__ void __launch_bounds__(128) trace_persistent_ww_kernel(DevScene sc, c
                 if (!(r >= 0.f)) continue;
                 if (ANY ? !(r <= tmax_any) : !(r < best_r)) continue;
                 if (!(r >= r_lo && r <= r_hi)) continue;
-                const float4* rec2 = sc.isect_cold + 2 * static_cast<size_t>(id);
-                const float4 q2 = __ldg(rec2), q3 = __ldg(rec2 + 1);
-                const float wx = (ox + r * dx) - q0.x, wy = (oy + r * dy) - q0.y, wz = (oz + r * dz) - q0.z;
-                const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
-                const float wv = wx * vx + wy * vy + wz * vz;
-                const float wu = wx * ux + wy * uy + wz * uz;
-                const float s = (q3.x * wv - q3.y * wu) / q3.w;
-                if (s < 0.f) continue;
-                const float t = (q3.x * wu - q3.z * wv) / q3.w;
-                if (t < 0.f || 1.f < s + t) continue;
-                best_id = id;
-                best_r = r;
-                best_s = s;
-                best_t = t;
-                if (ANY) {
-                    occluded = true;
-                    break;
-                }
+                if (test_candidate<ANY>(sc, id, r, ox, oy, oz, dx, dy, dz, best_id, best_r, best_s, best_t)) occluded = true;
             }
             bool finished = occluded || (best_id != kMiss && best_r <= texit) || sp == 0;
             if (!finished) {
@@ -409,9 +450,9 @@ __global__ void __launch_bounds__(128) trace_persistent_ww_kernel(DevScene sc, c
             if (finished) {
                 busy = false;
                 if (ANY) {
-                    if (!occluded) accumulate(acc, __float_as_uint(rb[idx].w), rc[idx]);
+                    if (!occluded) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx]));
                 } else {
-                    hits[idx] = make_uint4(best_id, __float_as_uint(best_r), __float_as_uint(best_s), __float_as_uint(best_t));
+                    __stcs(&hits[idx], make_uint4(best_id, __float_as_uint(best_r), __float_as_uint(best_s), __float_as_uint(best_t)));
                 }
             }
         }
