@@ -250,7 +250,8 @@ def main():
 
     # ---- e2e: the same metric through the host-buffer C-ABI call (trn_render: frame parameters in, image out to
     # host memory inside the timed region)
-    host_img = np.zeros((H, W, 4), np.float32)
+    host_pinned = torch.zeros(H, W, 4, dtype=torch.float32).pin_memory()  # pinned host memory for the per-step D2H
+    host_img = host_pinned.numpy()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -296,3 +296,38 @@ def test_single_process_multi_gpu_reduce(api, cornell):
     many, sn = p.render_multi(cam, cfg, list(range(n)))
     assert sn.rays == s1.rays and sn.prim_rays == s1.prim_rays
     assert np.allclose(many, one, rtol=1e-5, atol=1e-5)
+
+
+def test_stress_closest_hit_one_million_rays_mid_mesh(api, ob, scenes):
+    # heavier soak of the result-neutral shortcuts (early exit, empty-space cuts, per-cell hit range, two-pass leaves,
+    # lane refill): 1M mixed rays on a 28k-triangle mesh against the reference's exhaustive schedule
+    sc = scenes.cubesphere(48)
+    o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+    p = api.Scene.from_dict(sc)
+    rng = np.random.RandomState(77)
+    V = sc["vertices"].reshape(-1, 3, 3)
+    n = 250000
+    # (a) rays leaving the surface (secondary-ray shape), (b) grazing rays tangent to the sphere, (c) shell -> box, (d) inside
+    idx = rng.randint(0, V.shape[0], n)
+    bary = rng.dirichlet([1, 1, 1], n)
+    pts = (V[idx] * bary[:, :, None]).sum(1)
+    nrm = pts / np.linalg.norm(pts, axis=1, keepdims=True)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d *= np.sign((d * nrm).sum(1, keepdims=True))
+    sets = [((pts + 1e-4 * nrm), d)]
+    t = np.cross(nrm, rng.normal(size=(n, 3)))
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    sets.append((pts * 1.02 - 3 * t, t + 0.01 * rng.normal(size=(n, 3))))
+    sets.append(scenes.random_rays(sc, n, seed=5, inside=False))
+    sets.append(scenes.random_rays(sc, n, seed=6, inside=True))
+    total = 0
+    for ro, rd in sets:
+        ro = np.ascontiguousarray(ro, np.float32)
+        rd = np.ascontiguousarray(rd, np.float32)
+        i_o, r_o = o.intersect(ro, rd, 0)
+        i_g, r_g = p.intersect(ro, rd)
+        assert np.array_equal(i_g, i_o), int((i_g != i_o).sum())
+        assert np.array_equal(bits(r_g), bits(r_o))
+        total += ro.shape[0]
+    assert total == 1_000_000

@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "traverse_persistent.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -69,6 +70,9 @@ struct DeviceScene {
     ShadowWave shadow{};
     void* shadow_mem = nullptr;
     uint4* d_hits = nullptr;
+    uint32_t *d_keys = nullptr, *d_keys_alt = nullptr, *d_order = nullptr, *d_order_alt = nullptr; // ray sorting
+    void* d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
     WaveCounters* d_counters = nullptr;  // ring of counters, one per (launch) use
     WaveCounters* h_counters = nullptr;  // pinned mirror
     uint32_t counter_slots = 0;
@@ -99,6 +103,11 @@ struct DeviceScene {
         for (void* p : wave_mem) cudaFree(p);
         cudaFree(shadow_mem);
         cudaFree(d_hits);
+        cudaFree(d_keys);
+        cudaFree(d_keys_alt);
+        cudaFree(d_order);
+        cudaFree(d_order_alt);
+        cudaFree(d_sort_tmp);
         cudaFree(d_counters);
         if (h_counters) cudaFreeHost(h_counters);
         cudaFree(d_hitcount);
@@ -121,6 +130,10 @@ struct trn_scene {
     std::vector<uint32_t> leaf_refs;
     std::map<int, std::unique_ptr<trn::DeviceScene>> devices;
     std::mutex mu;
+    // NCCL communicators of the last device set used by trn_render_multi (ncclCommInitAll costs seconds)
+    std::vector<int> nccl_devs;
+    std::vector<void*> nccl_comms;
+    int (*nccl_destroy)(void*) = nullptr;
 };
 
 namespace trn {
@@ -290,9 +303,22 @@ static int ensure_waves(DeviceScene* ds, uint64_t cap, int levels) {
         ds->shadow_mem = nullptr;
         cudaFree(ds->d_hits);
         ds->d_hits = nullptr;
+        cudaFree(ds->d_keys); cudaFree(ds->d_keys_alt); cudaFree(ds->d_order); cudaFree(ds->d_order_alt); cudaFree(ds->d_sort_tmp);
+        ds->d_keys = ds->d_keys_alt = ds->d_order = ds->d_order_alt = nullptr;
+        ds->d_sort_tmp = nullptr;
         ds->wave_cap = cap;
     }
     if (!ds->d_hits) CUDA_TRY(cudaMalloc(&ds->d_hits, cap * sizeof(uint4)));
+    if (!ds->d_keys) {
+        CUDA_TRY(cudaMalloc(&ds->d_keys, cap * 4));
+        CUDA_TRY(cudaMalloc(&ds->d_keys_alt, cap * 4));
+        CUDA_TRY(cudaMalloc(&ds->d_order, cap * 4));
+        CUDA_TRY(cudaMalloc(&ds->d_order_alt, cap * 4));
+        cub::DoubleBuffer<uint32_t> k(ds->d_keys, ds->d_keys_alt), v(ds->d_order, ds->d_order_alt);
+        ds->sort_tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, ds->sort_tmp_bytes, k, v, static_cast<int>(std::min<uint64_t>(cap, 0x7fffffffull)), 0, 18);
+        CUDA_TRY(cudaMalloc(&ds->d_sort_tmp, std::max<size_t>(ds->sort_tmp_bytes, 16)));
+    }
     if (!ds->shadow_mem) {
         CUDA_TRY(cudaMalloc(&ds->shadow_mem, cap * 3 * sizeof(float4)));
         float4* p = static_cast<float4*>(ds->shadow_mem);
@@ -434,6 +460,7 @@ struct Renderer {
     uint64_t trace_launches = 0, trace_queries = 0, shadow_launches = 0;
     bool counting = g_counting != 0;
     int mode_closest = persistent_mode(false), mode_shadow = persistent_mode(true);
+    bool sort_rays = env_u64("TRN_SORT", 0) != 0 && ds->two_pass; // experiment: (octant, Morton) order for secondary waves; measured no gain (profiles/README.md)
     uint64_t cap;
 
     Renderer(DeviceScene* d, const FrameParams& f, int integ, float4* a, cudaStream_t s)
@@ -451,13 +478,25 @@ struct Renderer {
             uint32_t cs;
             int rc = next_slot(&cs);
             if (rc) return rc;
+            // secondary waves of a real tree are consumed in (octant, Morton) order; primaries are coherent as generated
+            const uint32_t* order = nullptr;
+            if (!counting && mode_closest == 2 && depth > 0 && sort_rays && n >= 4096) {
+                timer.begin(3);
+                ray_sort_keys_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_keys, ds->d_order);
+                cub::DoubleBuffer<uint32_t> k(ds->d_keys, ds->d_keys_alt), v(ds->d_order, ds->d_order_alt);
+                size_t tmp = ds->sort_tmp_bytes;
+                CUDA_TRY(cub::DeviceRadixSort::SortPairs(ds->d_sort_tmp, tmp, k, v, static_cast<int>(n), 0, 18, stream));
+                order = v.Current();
+                timer.end();
+                launches += 4;
+            }
             timer.begin(0);
             if (counting)
                 trace_closest_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits, ds->d_visits);
             else if (mode_closest == 2)
                 TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), stream,
                     ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr,
-                    static_cast<int>(env_u64("TRN_REFILL", 28)), static_cast<int>(env_u64("TRN_QUANTA", 2)));
+                    static_cast<int>(env_u64("TRN_REFILL", 28)), static_cast<int>(env_u64("TRN_QUANTA", 2)), order);
             else if (mode_closest == 1)
                 trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, stream>>>(
                     ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr);
@@ -493,7 +532,7 @@ struct Renderer {
                     TRN_LAUNCH_WW(1, ds->two_pass, persistent_grid(ds->grid_shadow, n), stream,
                         ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
                         &ds->d_counters[cs].shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_REFILL", 26)),
-                        static_cast<int>(env_u64("TRN_QUANTA", 2)));
+                        static_cast<int>(env_u64("TRN_QUANTA", 2)), nullptr);
                 else if (mode_shadow == 1)
                     trace_persistent_kernel<1><<<persistent_grid(ds->grid_shadow, n), 128, 0, stream>>>(
                         ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
@@ -679,6 +718,8 @@ int32_t trn_scene_create(const float* verts, const float* normals, const float* 
 
 void trn_scene_destroy(trn_scene* scene) {
     if (!scene) return;
+    if (scene->nccl_destroy)
+        for (void* c : scene->nccl_comms) scene->nccl_destroy(c);
     for (auto& kv : scene->devices) kv.second->release();
     delete scene;
 }
@@ -747,7 +788,7 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
             if (rc2) return rc2;
             if (persistent_mode(false) == 2)
                 TRN_LAUNCH_WW(2, ds->two_pass, persistent_grid(ds->grid_plain, c), ds->stream,
-                    ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr, 28, 2);
+                    ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr, 28, 2, nullptr);
             else
                 trace_persistent_kernel<2><<<persistent_grid(ds->grid_plain, c), 128, 0, ds->stream>>>(
                     ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr);
@@ -807,7 +848,7 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
             if (persistent_mode(false) == 2)
                 TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), ds->stream,
                     ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr,
-                    &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2);
+                    &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2, nullptr);
             else
                 trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, ds->stream>>>(
                     ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr,
@@ -889,10 +930,21 @@ int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_d
         rc = ensure_accum(dss[g], pixels);
         if (rc) return rc;
     }
-    std::vector<void*> comms(num_devices, nullptr);
     std::vector<int> devs(devices, devices + num_devices);
-    int nrc = nccl.CommInitAll(comms.data(), num_devices, devs.data());
-    if (nrc != 0) return fail(TRN_ERR_NCCL, std::string("ncclCommInitAll: ") + (nccl.GetErrorString ? nccl.GetErrorString(nrc) : "?"));
+    int nrc = 0;
+    if (scene->nccl_devs != devs) {
+        for (void* c : scene->nccl_comms) nccl.CommDestroy(c);
+        scene->nccl_comms.assign(num_devices, nullptr);
+        scene->nccl_devs.clear();
+        nrc = nccl.CommInitAll(scene->nccl_comms.data(), num_devices, devs.data());
+        if (nrc != 0) {
+            scene->nccl_comms.clear();
+            return fail(TRN_ERR_NCCL, std::string("ncclCommInitAll: ") + (nccl.GetErrorString ? nccl.GetErrorString(nrc) : "?"));
+        }
+        scene->nccl_devs = devs;
+        scene->nccl_destroy = nccl.CommDestroy;
+    }
+    std::vector<void*>& comms = scene->nccl_comms;
 
     auto t0 = std::chrono::steady_clock::now();
     std::vector<trn_stats> st(num_devices);
@@ -914,10 +966,7 @@ int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_d
     }
     for (auto& w : workers) w.join();
     for (int g = 0; g < num_devices; ++g)
-        if (rcs[g]) {
-            for (void* c : comms) nccl.CommDestroy(c);
-            return fail(rcs[g], errs[g]);
-        }
+        if (rcs[g]) return fail(rcs[g], errs[g]);
     // one ncclReduce(sum) of the float accumulation buffers onto devices[0]
     nccl.GroupStart();
     for (int g = 0; g < num_devices; ++g) {
@@ -926,17 +975,13 @@ int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_d
         if (nrc != 0) break;
     }
     int erc = nccl.GroupEnd();
-    if (nrc != 0 || erc != 0) {
-        for (void* c : comms) nccl.CommDestroy(c);
-        return fail(TRN_ERR_NCCL, "ncclReduce failed");
-    }
+    if (nrc != 0 || erc != 0) return fail(TRN_ERR_NCCL, "ncclReduce failed");
     for (int g = 0; g < num_devices; ++g) {
         cudaSetDevice(dss[g]->device);
         CUDA_TRY(cudaStreamSynchronize(dss[g]->stream));
     }
     CUDA_TRY(cudaSetDevice(dss[0]->device));
     CUDA_TRY(cudaMemcpy(out_rgba_sum, dss[0]->d_accum, pixels * sizeof(float4), cudaMemcpyDeviceToHost));
-    for (void* c : comms) nccl.CommDestroy(c);
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         for (auto& s : st) {

@@ -270,14 +270,18 @@ __device__ __forceinline__ bool test_candidate(const DevScene& sc, uint32_t id, 
 // single state-machine step. Fewer bookkeeping instructions per unit of work, coarser balancing.
 // TWO_PASS: leaves are evaluated as "all plane tests, then the recorded survivors" (best for trees with small leaves);
 // otherwise in one pass (best when a leaf holds many triangles, e.g. a scene that is a single leaf). Chosen per scene.
+#ifndef TRN_WW_MINBLOCKS
+#define TRN_WW_MINBLOCKS 9
+#endif
 template <int MODE, bool TWO_PASS>
-__global__ void __launch_bounds__(128) trace_persistent_ww_kernel(DevScene sc, const float4* __restrict__ ra,
+__global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_kernel(DevScene sc, const float4* __restrict__ ra,
                                                                   const float4* __restrict__ rb,
                                                                   const float4* __restrict__ rc, const float* __restrict__ po,
                                                                   const float* __restrict__ pd, uint32_t count_arg,
                                                                   const uint32_t* __restrict__ count_ptr,
                                                                   uint32_t* __restrict__ cursor, uint4* __restrict__ hits,
-                                                                  float4* __restrict__ acc, int refill_below, int quanta) {
+                                                                  float4* __restrict__ acc, int refill_below, int quanta,
+                                                                  const uint32_t* __restrict__ order) {
     constexpr bool ANY = MODE == 1;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -314,6 +318,7 @@ __global__ void __launch_bounds__(128) trace_persistent_ww_kernel(DevScene sc, c
                 const uint32_t rank = __popc(need & lt_mask);
                 if (!busy && rank < take) {
                     idx = pool_next + rank;
+                    if (order) idx = __ldcs(&order[idx]); // rays are consumed in sorted order, results go to their own slot
                     if (MODE == 2) {
                         ox = po[3 * idx]; oy = po[3 * idx + 1]; oz = po[3 * idx + 2];
                         dx = pd[3 * idx]; dy = pd[3 * idx + 1]; dz = pd[3 * idx + 2];
@@ -457,6 +462,38 @@ __global__ void __launch_bounds__(128) trace_persistent_ww_kernel(DevScene sc, c
             }
         }
     }
+}
+
+
+// Sort key of a secondary ray: direction octant (3 bits, major) and the Morton code of its origin on a 32^3 grid over
+// the scene box (15 bits). Rays that are neighbours in this order start close together and make the same near/far
+// decisions, so the lanes of a warp walk the same nodes (profiles/README.md: lanes per instruction, L1 hit rate).
+__device__ __forceinline__ uint32_t spread5(uint32_t v) { // 5 bits -> every third bit
+    v = (v | (v << 8)) & 0x0000F00Fu;
+    v = (v | (v << 4)) & 0x000C30C3u;
+    v = (v | (v << 2)) & 0x00249249u;
+    return v;
+}
+__global__ void __launch_bounds__(256) ray_sort_keys_kernel(DevScene sc, const float4* __restrict__ ra,
+                                                            const float4* __restrict__ rb, uint32_t count,
+                                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const float4 a = ra[idx];
+    const float4 b = rb[idx];
+    uint32_t q[3];
+    const float o[3] = {a.x, a.y, a.z};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float ext = sc.hi[c] - sc.lo[c];
+        float u = ext > 0.f ? (o[c] - sc.lo[c]) / ext : 0.f;
+        u = fminf(fmaxf(u, 0.f), 0.999999f);
+        q[c] = static_cast<uint32_t>(u * 32.f);
+    }
+    const uint32_t morton = spread5(q[0]) | (spread5(q[1]) << 1) | (spread5(q[2]) << 2);
+    const uint32_t octant = (a.w < 0.f ? 1u : 0u) | (b.x < 0.f ? 2u : 0u) | (b.y < 0.f ? 4u : 0u);
+    keys[idx] = (octant << 15) | morton;
+    vals[idx] = idx;
 }
 
 } // namespace trn
