@@ -660,6 +660,8 @@ struct NcclApi {
 };
 
 static int load_nccl(NcclApi& api) {
+    // NCCL's version/debug banner goes to stdout by default; stdout is the image (main.cpp:242)
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     const char* names[] = {std::getenv("TRN_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
         if (!n || !*n) continue;
