@@ -77,6 +77,7 @@ struct DeviceScene {
     WaveCounters* h_counters = nullptr;  // pinned mirror
     uint32_t counter_slots = 0;
     uint32_t ring_pos = 0;
+    uint32_t treelet_pairs = 0; // node pairs of the top treelet present in pnodes (<= kTreeletNodes / 2)
     bool two_pass = true; // leaf evaluation schedule of the persistent kernels (small leaves: two-pass)
     int grid_closest = 0, grid_shadow = 0, grid_plain = 0; // persistent grids: resident CTAs per SM x SMs
     unsigned long long* d_hitcount = nullptr;
@@ -226,6 +227,7 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
             const uint32_t y = static_cast<uint32_t>(nd >> 32);
             if ((y & 3u) == 3u && (y >> 2) > 0) ++leaves;
         }
+        ds->treelet_pairs = static_cast<uint32_t>(std::min<size_t>(sc->tree.pair_nodes.size(), KdTree::kTreeletNodes) / 2);
         ds->two_pass = leaves > 0 && static_cast<double>(sc->tree.pair_leaf_refs.size()) / static_cast<double>(leaves) <= 6.0;
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
@@ -496,7 +498,7 @@ struct Renderer {
             else if (mode_closest == 2)
                 TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), stream,
                     ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr,
-                    static_cast<int>(env_u64("TRN_REFILL", 28)), static_cast<int>(env_u64("TRN_QUANTA", 2)), order);
+                    static_cast<int>(env_u64("TRN_REFILL", 28)), static_cast<int>(env_u64("TRN_QUANTA", 2)), order, ds->treelet_pairs);
             else if (mode_closest == 1)
                 trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, stream>>>(
                     ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr);
@@ -532,7 +534,7 @@ struct Renderer {
                     TRN_LAUNCH_WW(1, ds->two_pass, persistent_grid(ds->grid_shadow, n), stream,
                         ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
                         &ds->d_counters[cs].shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_REFILL", 26)),
-                        static_cast<int>(env_u64("TRN_QUANTA", 2)), nullptr);
+                        static_cast<int>(env_u64("TRN_QUANTA", 2)), nullptr, ds->treelet_pairs);
                 else if (mode_shadow == 1)
                     trace_persistent_kernel<1><<<persistent_grid(ds->grid_shadow, n), 128, 0, stream>>>(
                         ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
@@ -790,7 +792,7 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
             if (rc2) return rc2;
             if (persistent_mode(false) == 2)
                 TRN_LAUNCH_WW(2, ds->two_pass, persistent_grid(ds->grid_plain, c), ds->stream,
-                    ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr, 28, 2, nullptr);
+                    ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr, 28, 2, nullptr, ds->treelet_pairs);
             else
                 trace_persistent_kernel<2><<<persistent_grid(ds->grid_plain, c), 128, 0, ds->stream>>>(
                     ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr);
@@ -850,7 +852,7 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
             if (persistent_mode(false) == 2)
                 TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), ds->stream,
                     ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr,
-                    &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2, nullptr);
+                    &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2, nullptr, ds->treelet_pairs);
             else
                 trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, ds->stream>>>(
                     ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr,

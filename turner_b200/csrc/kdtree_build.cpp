@@ -292,30 +292,40 @@ void flatten_pairs(BuildNode* root, KdTree& out) {
         BuildNode* node;
         uint32_t slot;
     };
-    std::vector<Item> stack;
-    stack.push_back({root, 0});
     out.num_cut_nodes = 0;
-    while (!stack.empty()) {
-        Item it = stack.back();
-        stack.pop_back();
+    auto emit = [&](const Item& it, std::vector<Item>& children) {
         BuildNode* n = it.node;
         if (!n) {
             nodes[it.slot] = static_cast<uint64_t>(3u) << 32; // empty leaf: count 0
-            continue;
-        }
-        if (n->axis >= 0) {
+        } else if (n->axis >= 0) {
             if (n->cut) ++out.num_cut_nodes;
             const uint32_t pair = static_cast<uint32_t>(nodes.size());
             nodes.push_back(0);
             nodes.push_back(0);
             nodes[it.slot] = (static_cast<uint64_t>((pair << 2) | static_cast<uint32_t>(n->axis)) << 32) | float_bits(n->split);
-            stack.push_back({n->right, pair + 1});
-            stack.push_back({n->left, pair});
+            children.push_back({n->left, pair});
+            children.push_back({n->right, pair + 1});
         } else {
             const uint32_t first = static_cast<uint32_t>(refs.size());
             refs.insert(refs.end(), n->ids.begin(), n->ids.end());
             nodes[it.slot] = (static_cast<uint64_t>((static_cast<uint32_t>(n->ids.size()) << 2) | 3u) << 32) | first;
         }
+    };
+    // top of the tree breadth-first, so that the first kTreeletNodes nodes are the top treelet (stageable as one block)
+    std::vector<Item> level{{root, 0}}, next_level;
+    while (!level.empty() && nodes.size() + 2 * level.size() <= KdTree::kTreeletNodes) {
+        next_level.clear();
+        for (const Item& it : level) emit(it, next_level);
+        level.swap(next_level);
+    }
+    // the rest depth-first (a subtree stays contiguous)
+    std::vector<Item> stack(level.rbegin(), level.rend()), kids;
+    while (!stack.empty()) {
+        Item it = stack.back();
+        stack.pop_back();
+        kids.clear();
+        emit(it, kids);
+        for (auto k = kids.rbegin(); k != kids.rend(); ++k) stack.push_back(*k);
     }
 }
 

@@ -40,6 +40,9 @@ struct KdTree {
     // children:   inner: x = split bits,       y = (index of the child pair << 2) | axis
     //             leaf:  x = first reference,  y = (count << 2) | 3        (count 0 = cut-off void)
     // Node 0 is the root (node 1 pads the pair). Leaves are visited in the reference's order.
+    // The first kTreeletNodes entries are the top of the tree in breadth-first order (the "top treelet" a kernel can
+    // stage in shared memory as one contiguous block); below that each subtree is laid out depth-first.
+    static constexpr uint32_t kTreeletNodes = 2048;
     std::vector<uint64_t> pair_nodes;      // low 32 bits = x, high 32 bits = y
     std::vector<uint32_t> pair_leaf_refs;  // triangle ids, leaf after leaf
     uint64_t num_cut_nodes = 0;

@@ -270,6 +270,9 @@ __device__ __forceinline__ bool test_candidate(const DevScene& sc, uint32_t id, 
 // single state-machine step. Fewer bookkeeping instructions per unit of work, coarser balancing.
 // TWO_PASS: leaves are evaluated as "all plane tests, then the recorded survivors" (best for trees with small leaves);
 // otherwise in one pass (best when a leaf holds many triangles, e.g. a scene that is a single leaf). Chosen per scene.
+#ifndef TRN_TREELET_NODES
+#define TRN_TREELET_NODES 0 // nodes of the top treelet staged in shared memory by the persistent kernels (0 = off)
+#endif
 #ifndef TRN_WW_MINBLOCKS
 #define TRN_WW_MINBLOCKS 9
 #endif
@@ -281,11 +284,18 @@ __global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_ker
                                                                   const uint32_t* __restrict__ count_ptr,
                                                                   uint32_t* __restrict__ cursor, uint4* __restrict__ hits,
                                                                   float4* __restrict__ acc, int refill_below, int quanta,
-                                                                  const uint32_t* __restrict__ order) {
+                                                                  const uint32_t* __restrict__ order, uint32_t treelet_pairs) {
     constexpr bool ANY = MODE == 1;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t count = count_ptr ? *count_ptr : count_arg;
+#if TRN_TREELET_NODES > 0
+    // top treelet staged in shared memory: the first TRN_TREELET_NODES nodes of the breadth-first-on-top layout
+    __shared__ uint4 s_pairs[TRN_TREELET_NODES / 2];
+    for (uint32_t k = threadIdx.x; k < TRN_TREELET_NODES / 2; k += blockDim.x)
+        s_pairs[k] = k < treelet_pairs ? __ldg(reinterpret_cast<const uint4*>(sc.pnodes) + k) : make_uint4(0u, 3u, 0u, 3u);
+    __syncthreads();
+#endif
 
     uint4 stack[kStackDepth];
     int sp = 0;
@@ -372,7 +382,13 @@ __global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_ker
             while ((n.y & 3u) != 3u) {
                 const int ax = static_cast<int>(n.y & 3u);
                 const float split = __uint_as_float(n.x);
+#if TRN_TREELET_NODES > 0
+                const uint32_t child = n.y >> 2;
+                const uint4 pair = child < TRN_TREELET_NODES ? s_pairs[child >> 1]
+                                                             : __ldg(reinterpret_cast<const uint4*>(sc.pnodes + child));
+#else
                 const uint4 pair = __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
+#endif
                 const float o_ax = sel3(ax, ox, oy, oz);
                 const float i_ax = sel3(ax, ix, iy, iz);
                 const float t = (split - o_ax) * i_ax;
