@@ -52,7 +52,11 @@ typedef struct trn_light {
     float rgba[4];
 } trn_light;
 
-enum { TRN_PATHTRACER = 0 /* pathtracer.cpp:14-102 */, TRN_RAYCASTER = 1 /* raycaster.cpp:7-24 */ };
+enum {
+    TRN_PATHTRACER = 0, /* pathtracer.cpp:14-102 */
+    TRN_RAYCASTER = 1,  /* raycaster.cpp:7-24 */
+    TRN_RAYTRACER = 2   /* raytracer.cpp:6-67 (Whitted: Lambert + mirror recursion + shadow attenuation; needs one light) */
+};
 
 /* TracerConfig (config.h:103-153) + image size + the sample split. */
 typedef struct trn_render_config {
@@ -71,6 +75,7 @@ typedef struct trn_render_config {
      * i = sample_begin, sample_begin + sample_stride, ... < pixel_samples. 0/1 = all. */
     int32_t sample_begin;
     int32_t sample_stride;
+    float shadow_intensity; /* raytracer only: --shadow in [0,1] (config.h:113,123) */
 } trn_render_config;
 
 typedef struct trn_stats {
@@ -116,6 +121,10 @@ int32_t trn_device_count(void);
  * Builds the kd-tree on the host (same SAH build as lib/kdtree.cpp:124-467, node-for-node) and keeps a host
  * copy; device copies are created lazily per device on first use. */
 int32_t trn_scene_create(const float* verts, const float* normals, const float* diffuse, uint32_t n, trn_scene** out);
+/* same plus the mirror material the raytracer integrator reads (main.cpp:44-47): reflective n*4 rgba
+ * (AI_MATKEY_COLOR_REFLECTIVE) and reflectivity n (AI_MATKEY_REFLECTIVITY); either may be NULL (= 0) */
+int32_t trn_scene_create_ex(const float* verts, const float* normals, const float* diffuse, const float* reflective,
+                            const float* reflectivity, uint32_t n, trn_scene** out);
 void trn_scene_destroy(trn_scene* scene);
 int32_t trn_scene_get_info(const trn_scene* scene, trn_scene_info* info);
 /* the flattened tree in the reference's FlatNode encoding (lib/kdtree.h:62-154), num_nodes uint64 values */
@@ -179,6 +188,8 @@ typedef struct trn_loaded_scene {
     float* verts;   /* n*9 */
     float* normals; /* n*9 */
     float* diffuse; /* n*4 */
+    float* reflective;   /* n*4 */
+    float* reflectivity; /* n */
     int32_t has_camera;
     float cam_trafo4x4[16];
     float cam_hfov;

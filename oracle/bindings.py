@@ -44,6 +44,7 @@ class RenderCfg(C.Structure):
         ("cam_pos", C.c_float * 3),
         ("cam_rot", C.c_float * 9),
         ("delta_x", C.c_float), ("delta_y", C.c_float),
+        ("shadow_intensity", C.c_float),
     ]
 
 
@@ -62,6 +63,8 @@ def lib():
         L = C.CDLL(os.path.join(HERE, "libturner_oracle.so"))
         L.orc_scene_create.restype = C.c_void_p
         L.orc_scene_create.argtypes = [_f32p, _f32p, _f32p, C.c_uint32]
+        L.orc_scene_create_ex.restype = C.c_void_p
+        L.orc_scene_create_ex.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_uint32]
         L.orc_scene_create_prebuilt.restype = C.c_void_p
         L.orc_scene_create_prebuilt.argtypes = [_f32p, _f32p, _f32p, C.c_uint32, _u64p, C.c_uint64, _f32p]
         L.orc_scene_destroy.argtypes = [C.c_void_p]
@@ -107,7 +110,8 @@ def camera_setup(trafo4x4, hfov, aspect, width):
 
 
 def make_cfg(scene, width, max_depth=3, mc_samples=8, pixel_samples=1, num_threads=1, integrator=0, rng_mode=0,
-             seed=1, sample_begin=0, sample_stride=1, bg=(0, 0, 0, 1), max_visibility=2.0, aspect=1.0):
+             seed=1, sample_begin=0, sample_stride=1, bg=(0, 0, 0, 1), max_visibility=2.0, aspect=1.0,
+             shadow_intensity=0.5):
     """scene: dict with 'camera' {'trafo4x4','hfov'} and 'light' (or None), as in tests/golden/*.json"""
     cam = scene["camera"]
     pos, rot, dx, dy, height = camera_setup(cam["trafo4x4"], cam["hfov"], aspect, width)
@@ -126,16 +130,21 @@ def make_cfg(scene, width, max_depth=3, mc_samples=8, pixel_samples=1, num_threa
     cfg.cam_pos = (C.c_float * 3)(*pos)
     cfg.cam_rot = (C.c_float * 9)(*rot)
     cfg.delta_x, cfg.delta_y = dx, dy
+    cfg.shadow_intensity = shadow_intensity
     return cfg
 
 
 class OracleScene:
-    def __init__(self, verts, normals, diffuse, nodes=None, box=None):
+    def __init__(self, verts, normals, diffuse, nodes=None, box=None, reflective=None, reflectivity=None):
         self.verts = _f32(verts).reshape(-1, 9)
         self.normals = _f32(normals).reshape(-1, 9)
         self.diffuse = _f32(diffuse).reshape(-1, 4)
         n = self.verts.shape[0]
-        if nodes is None:
+        if reflective is not None:
+            assert nodes is None
+            self.h = lib().orc_scene_create_ex(self.verts, self.normals, self.diffuse, _f32(reflective).reshape(-1, 4),
+                                               _f32(reflectivity).reshape(-1), n)
+        elif nodes is None:
             self.h = lib().orc_scene_create(self.verts, self.normals, self.diffuse, n)
         else:
             nodes = np.ascontiguousarray(nodes, dtype=np.uint64)
@@ -216,7 +225,7 @@ class RefConfig(C.Structure):
                 ("pixel_samples", C.c_int32), ("num_threads", C.c_int32), ("gamma_enabled", C.c_int32),
                 ("bg", C.c_float * 4), ("exposure", C.c_float), ("inverse_gamma", C.c_float),
                 ("max_visibility", C.c_float), ("num_lights", C.c_int32), ("light_pos", C.c_float * 3),
-                ("light_color", C.c_float * 4)]
+                ("light_color", C.c_float * 4), ("shadow_intensity", C.c_float)]
 
 
 class RefStats(C.Structure):
@@ -237,6 +246,8 @@ def ref_lib(kind="pathtracer"):
         L = C.CDLL(os.path.join(HERE, "_ref", "libturner_ref_%s.so" % kind))
         L.ref_scene_create.restype = C.c_void_p
         L.ref_scene_create.argtypes = [_f32p, _f32p, _f32p, C.c_uint32]
+        L.ref_scene_create_ex.restype = C.c_void_p
+        L.ref_scene_create_ex.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p, C.c_uint32]
         L.ref_scene_create_prebuilt.restype = C.c_void_p
         L.ref_scene_create_prebuilt.argtypes = [_f32p, _f32p, _f32p, C.c_uint32, _u64p, C.c_uint64, _f32p]
         L.ref_scene_destroy.argtypes = [C.c_void_p]
@@ -272,12 +283,13 @@ def ref_camera(scene, aspect=1.0):
 
 
 def ref_config(scene, width, max_depth=3, mc_samples=8, pixel_samples=1, num_threads=1, bg=(0, 0, 0, 1),
-               exposure=1.0, gamma_enabled=True, inverse_gamma=0.454545, max_visibility=2.0):
+               exposure=1.0, gamma_enabled=True, inverse_gamma=0.454545, max_visibility=2.0, shadow_intensity=0.5):
     c = RefConfig()
     c.width, c.max_depth, c.mc_samples, c.pixel_samples, c.num_threads = width, max_depth, mc_samples, pixel_samples, num_threads
     c.gamma_enabled = 1 if gamma_enabled else 0
     c.bg = (C.c_float * 4)(*bg)
     c.exposure, c.inverse_gamma, c.max_visibility = exposure, inverse_gamma, max_visibility
+    c.shadow_intensity = shadow_intensity
     light = scene.get("light")
     c.num_lights = 1 if light else 0
     if light:
@@ -289,13 +301,18 @@ def ref_config(scene, width, max_depth=3, mc_samples=8, pixel_samples=1, num_thr
 class RefScene:
     """the reference's own KDTree (+ trace()) behind oracle/ref_driver.cpp"""
 
-    def __init__(self, verts, normals, diffuse, kind="pathtracer", nodes=None, box=None):
+    def __init__(self, verts, normals, diffuse, kind="pathtracer", nodes=None, box=None, reflective=None,
+                 reflectivity=None):
         self.L = ref_lib(kind)
         self.verts = _f32(verts).reshape(-1, 9)
         self.normals = _f32(normals).reshape(-1, 9)
         self.diffuse = _f32(diffuse).reshape(-1, 4)
         n = self.verts.shape[0]
-        if nodes is None:
+        if reflective is not None:
+            assert nodes is None
+            self.h = self.L.ref_scene_create_ex(self.verts, self.normals, self.diffuse, _f32(reflective).reshape(-1, 4),
+                                                _f32(reflectivity).reshape(-1), n)
+        elif nodes is None:
             self.h = self.L.ref_scene_create(self.verts, self.normals, self.diffuse, n)
         else:
             nodes = np.ascontiguousarray(nodes, dtype=np.uint64)

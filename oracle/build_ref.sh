@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# TEST INFRASTRUCTURE ONLY. Builds oracle/_ref/libturner_ref_{pathtracer,raycaster}.so
+# TEST INFRASTRUCTURE ONLY. Builds oracle/_ref/libturner_ref_{pathtracer,raycaster,raytracer}.so
 # from the reference's own sources where they lie under /root/reference:
 #   lib/kdtree.cpp + pathtracer.cpp (or raycaster.cpp) + oracle/ref_driver.cpp
 # Nothing from /root/reference is copied into the repo. Because the reference's
@@ -53,4 +53,5 @@ CXX="${CXX:-g++}"
 FLAGS="-std=c++14 -O2 -DNDEBUG -ffp-contract=off -fPIC -shared -pthread -w -s -nostdlib++ -I$HERE/ref_shims -I$TMP"
 $CXX $FLAGS "$TMP/lib/kdtree.cpp" "$TMP/pathtracer.cpp" "$HERE/ref_driver.cpp" -l:libstdc++.so.6 -o "$OUT/libturner_ref_pathtracer.so"
 $CXX $FLAGS "$TMP/lib/kdtree.cpp" "$TMP/raycaster.cpp" "$HERE/ref_driver.cpp" -l:libstdc++.so.6 -o "$OUT/libturner_ref_raycaster.so"
+$CXX $FLAGS "$TMP/lib/kdtree.cpp" "$TMP/raytracer.cpp" "$HERE/ref_driver.cpp" -l:libstdc++.so.6 -o "$OUT/libturner_ref_raytracer.so"
 echo "built $OUT/libturner_ref_pathtracer.so $OUT/libturner_ref_raycaster.so"

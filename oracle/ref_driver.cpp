@@ -70,7 +70,8 @@ struct RefScene {
     KDTree tree;
 };
 
-Triangles make_triangles(const float* verts, const float* normals, const float* diffuse, uint32_t n) {
+Triangles make_triangles(const float* verts, const float* normals, const float* diffuse, uint32_t n,
+                         const float* reflective = nullptr, const float* reflectivity = nullptr) {
     Triangles tris;
     tris.reserve(n);
     for (uint32_t i = 0; i < n; ++i) {
@@ -84,8 +85,10 @@ Triangles make_triangles(const float* verts, const float* normals, const float* 
                                 aiColor4D(),
                                 dif,
                                 dif,
-                                aiColor4D(),
-                                0.f});
+                                reflective ? aiColor4D(reflective[4 * size_t(i)], reflective[4 * size_t(i) + 1],
+                                                       reflective[4 * size_t(i) + 2], reflective[4 * size_t(i) + 3])
+                                           : aiColor4D(),
+                                reflectivity ? reflectivity[i] : 0.f});
     }
     return tris;
 }
@@ -114,6 +117,7 @@ struct RefConfig {
     int32_t num_lights; // 0 or 1
     float light_pos[3];
     float light_color[4];
+    float shadow_intensity; // raytracer only (config.h:113)
 };
 
 struct RefStats {
@@ -129,6 +133,13 @@ const char* ref_usage() { return USAGE; }
 void* ref_scene_create(const float* verts, const float* normals, const float* diffuse, uint32_t n) {
     auto* s = new RefScene;
     s->tree = KDTree(make_triangles(verts, normals, diffuse, n)); // reference builder, lib/kdtree.cpp:474-490
+    return s;
+}
+
+void* ref_scene_create_ex(const float* verts, const float* normals, const float* diffuse, const float* reflective,
+                          const float* reflectivity, uint32_t n) {
+    auto* s = new RefScene;
+    s->tree = KDTree(make_triangles(verts, normals, diffuse, n, reflective, reflectivity));
     return s;
 }
 
@@ -257,6 +268,7 @@ int ref_render(void* h, const RefCamera* rc, const RefConfig* cfg, float* out_li
     conf.max_visibility = cfg->max_visibility;
     conf.num_pixel_samples = cfg->pixel_samples;
     conf.num_monte_carlo_samples = cfg->mc_samples;
+    conf.shadow_intensity = cfg->shadow_intensity;
 
     std::vector<Light> lights;
     if (cfg->num_lights == 1) {

@@ -115,7 +115,7 @@ struct Tri {
 };
 static_assert(sizeof(Tri) == 192, "reference Triangle is 192 bytes");
 
-inline Tri make_tri(const float* vp, const float* np, const float* dc) {
+inline Tri make_tri(const float* vp, const float* np, const float* dc, const float* mirror_rgba = nullptr, float reflectivity = 0.f) {
     Tri t;
     std::memset(&t, 0, sizeof(t));
     for (int k = 0; k < 3; ++k) {
@@ -124,6 +124,8 @@ inline Tri make_tri(const float* vp, const float* np, const float* dc) {
     }
     t.diffuse = {dc[0], dc[1], dc[2], dc[3]};
     t.emissive = t.diffuse; // main.cpp:43 reads DIFFUSE into emissive
+    if (mirror_rgba) t.reflective = {mirror_rgba[0], mirror_rgba[1], mirror_rgba[2], mirror_rgba[3]}; // main.cpp:44
+    t.reflectivity = reflectivity;                                                                    // main.cpp:46-47
     t.u = sub(t.p[1], t.p[0]);
     t.v = sub(t.p[2], t.p[0]);
     t.fn = normalize(cross_d(t.u, t.v));
@@ -709,6 +711,7 @@ struct RenderCfg {
     float cam_pos[3];
     float cam_rot[9]; // row-major 3x3 (a1..c3)
     float delta_x, delta_y;
+    float shadow_intensity; // raytracer only (config.h:113)
 };
 
 struct RenderStats {
@@ -775,6 +778,41 @@ struct Tracer {
         return cmul(tri.diffuse, cadd(cscale(static_cast<float>(M_1_PI), direct), cscale(2.f, indirect)));
     }
 
+    // raytracer.cpp:6-67 (Whitted: direct Lambert + mirror recursion + shadow attenuation); needs one light
+    C4 raytrace(const Ray& ray, int depth) {
+        rays += 1; // counted before the depth check (raytracer.cpp:9-13)
+        if (depth > cfg.max_depth) return {0, 0, 0, 0};
+        float dist, s, t;
+        uint32_t id = tv.intersect(ray, dist, s, t);
+        if (id == kMissId) return {cfg.bg[0], cfg.bg[1], cfg.bg[2], cfg.bg[3]};
+        const V3 lp = {cfg.light_pos[0], cfg.light_pos[1], cfg.light_pos[2]};
+        const C4 lc = {cfg.light_color[0], cfg.light_color[1], cfg.light_color[2], cfg.light_color[3]};
+        V3 p = add(ray.o, smul(dist, ray.d));
+        V3 light_dir = normalize(sub(lp, p));
+        const Tri& tri = sc.tris[id];
+        float br = 1.f - s - t;
+        V3 normal = normalize(add(add(smul(br, tri.n[0]), smul(s, tri.n[1])), smul(t, tri.n[2])));
+        // lambertian(L, N, C, I) = max(0, L.N) * C * I, lib/lambertian.h:15-19
+        C4 direct = cmul(cscale(std::max(0.f, dot(light_dir, normal)), tri.diffuse), lc);
+        V3 p2 = add(p, smul(0.0001f, normal));
+        C4 color = direct;
+        if (tri.reflectivity > 0) {
+            V3 rdir = sub(ray.d, smul(2.f * dot(normal, ray.d), normal));
+            C4 rc = raytrace({p2, rdir}, depth + 1);
+            color = cadd(cscale(1.f - tri.reflectivity, direct), cmul(cscale(tri.reflectivity, tri.reflective), rc));
+        }
+        light_dir = normalize(sub(lp, p2));
+        float dist_to_light = length(sub(lp, p2));
+        float dn;
+        shadow_rays += 1;
+        uint32_t sh = tv.intersect({p2, light_dir}, dn, s, t);
+        if (sh != kMissId && dn < dist_to_light) {
+            C4 d = cscale(cfg.shadow_intensity, color);
+            color = {color.r - d.r, color.g - d.g, color.b - d.b, color.a - d.a};
+        }
+        return color;
+    }
+
     // raycaster.cpp:7-24
     C4 raycast(const Ray& ray) {
         float dist, s, t;
@@ -803,10 +841,19 @@ extern "C" {
 
 using orc::Scene;
 
+// reflective (n*4) / reflectivity (n) may be null (= 0): only the raytracer integrator reads them
+void* orc_scene_create_ex(const float* verts, const float* normals, const float* diffuse, const float* reflective,
+                          const float* reflectivity, uint32_t n);
 void* orc_scene_create(const float* verts, const float* normals, const float* diffuse, uint32_t n) {
+    return orc_scene_create_ex(verts, normals, diffuse, nullptr, nullptr, n);
+}
+void* orc_scene_create_ex(const float* verts, const float* normals, const float* diffuse, const float* reflective,
+                          const float* reflectivity, uint32_t n) {
     auto* s = new Scene;
     s->tris.reserve(n);
-    for (uint32_t i = 0; i < n; ++i) s->tris.push_back(orc::make_tri(verts + 9 * size_t(i), normals + 9 * size_t(i), diffuse + 4 * size_t(i)));
+    for (uint32_t i = 0; i < n; ++i)
+        s->tris.push_back(orc::make_tri(verts + 9 * size_t(i), normals + 9 * size_t(i), diffuse + 4 * size_t(i),
+                                        reflective ? reflective + 4 * size_t(i) : nullptr, reflectivity ? reflectivity[i] : 0.f));
     auto t0 = std::chrono::steady_clock::now();
     // KDTree::KDTree, kdtree.cpp:474-490
     s->box = orc::tri_bbox(s->tris[0]);
@@ -984,7 +1031,8 @@ int orc_render(void* h, const orc::RenderCfg* cfgp, float* out_sum, float* out_s
                     orc::Ray ray{{cfg.cam_pos[0], cfg.cam_pos[1], cfg.cam_pos[2]}, dir};
                     nprim += 1;
                     uint64_t sample_index = (uint64_t(y) * cfg.width + x) * cfg.pixel_samples + i;
-                    orc::C4 c = cfg.integrator == 0 ? tr.trace(ray, 0, sample_index, 0) : tr.raycast(ray);
+                    orc::C4 c = cfg.integrator == 0 ? tr.trace(ray, 0, sample_index, 0)
+                                                    : (cfg.integrator == 1 ? tr.raycast(ray) : tr.raytrace(ray, 0));
                     sum = orc::cadd(sum, c);
                     sq = orc::cadd(sq, orc::cmul(c, c));
                 }

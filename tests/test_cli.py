@@ -10,6 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PT = os.path.join(ROOT, "turner_b200", "pathtracer")
 RC = os.path.join(ROOT, "turner_b200", "raycaster")
+RT = os.path.join(ROOT, "turner_b200", "raytracer")
 
 
 def run(exe, *args):
@@ -57,6 +58,10 @@ def test_flag_grammar_of_the_reference_usage(api):
     assert run(PT, "--help").returncode == 0 and "--monte-carlo-samples" in run(PT, "--help").stdout
     assert run(PT, "file", "--bogus").returncode != 0
     assert run(PT, "file", "-p", "0").returncode == 2          # the reference asserts (config.h:124); here exit code 2
+    r = run(RT, "-d", "5", "--shadow", "0.25", "file", "-v")   # tests/test_config.cpp raytracer case
+    assert "Max recursion depth: 5" in r.stderr and "Shadow intensity: 0.25" in r.stderr
+    assert run(RT, "file", "-p", "2").returncode != 0          # raytracer USAGE has no -p
+    assert run(RT, "file", "--shadow", "1.5").returncode == 2
 
 
 def test_without_gpu_the_cli_fails_loudly(api, soup):
@@ -110,3 +115,17 @@ def test_raycaster_end_to_end_exact(api, ob, scenes, soup):
     ref, _, ost = o.render(ob.make_cfg(sc, W, integrator=1, max_visibility=1.5, bg=(0.25, 0.25, 0.25, 1), num_threads=4))
     assert r.stdout == ob.write_p3(ob.tonemap(ref, 1))  # one sample per pixel: the P3 text is byte-identical
     assert "Rays           : %d" % ost.num_rays in r.stderr
+
+
+@pytest.mark.gpu
+def test_raytracer_end_to_end_matches_oracle(api, ob, scenes, soup):
+    W = 96
+    r = run(RT, soup, "-w", str(W), "-d", "4", "--shadow", "0.4")
+    assert r.returncode == 0, r.stderr
+    sc = scenes.fixture("cornell_box")
+    o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"], reflective=sc["reflective"], reflectivity=sc["reflectivity"])
+    ref, _, ost = o.render(ob.make_cfg(sc, W, max_depth=4, integrator=2, shadow_intensity=0.4, num_threads=4))
+    assert "Rays           : %d" % ost.num_rays in r.stderr
+    px = np.array(r.stdout.split("\n255\n", 1)[1].split(), dtype=np.int64)
+    want = np.array(ob.write_p3(ob.tonemap(ref, 1)).split("\n255\n", 1)[1].split(), dtype=np.int64)
+    assert (np.abs(px - want) <= 1).all() and (px == want).mean() > 0.999

@@ -331,3 +331,29 @@ def test_stress_closest_hit_one_million_rays_mid_mesh(api, ob, scenes):
         assert np.array_equal(bits(r_g), bits(r_o))
         total += ro.shape[0]
     assert total == 1_000_000
+
+
+def test_raytracer_integrator_vs_oracle(api, ob, scenes):
+    # raytracer.cpp:6-67 on the same traversal kernels. No RNG besides the primary jitter, so the
+    # only differences are fp32 association (throughput form, atomics): tolerance 2e-5 * (1 + value); ray counts exact.
+    for name, depth, shadow, bg, allmirror in [("cornell_box", 3, 0.5, (0, 0, 0, 1), False), ("cornell_box", 5, 0.7, (0.2, 0.3, 0.4, 1), True),
+                                               ("cornell_box", 1, 1.0, (0, 0, 0, 1), True), ("colored_cube", 3, 0.5, (0.1, 0.1, 0.1, 1), False)]:
+        sc = dict(scenes.fixture(name))
+        if allmirror:
+            sc["reflectivity"] = np.full_like(sc["reflectivity"], 0.6)
+        o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"], reflective=sc["reflective"], reflectivity=sc["reflectivity"])
+        p = api.Scene.from_dict(sc)
+        W, pps = 160, 3
+        cam, cfg = api.make_config(sc, W, max_depth=depth, pixel_samples=pps, integrator=api.RAYTRACER, bg=bg, shadow_intensity=shadow)
+        img, st = p.render(cam, cfg)
+        ref, _, ost = o.render(ob.make_cfg(sc, W, max_depth=depth, pixel_samples=pps, integrator=2, bg=bg, shadow_intensity=shadow,
+                                           num_threads=8))
+        assert st.rays == ost.num_rays and st.prim_rays == ost.num_prim_rays, (name, st.rays, ost.num_rays)
+        assert st.shadow_rays == ost.num_shadow_rays
+        assert np.all(np.abs(img - ref) <= 2e-5 * (1 + np.abs(ref))), (name, float(np.abs(img - ref).max()))
+    # needs exactly one light (raytracer.cpp:15)
+    fs = scenes.fixture("furnace_test")
+    pf = api.Scene.from_dict(fs)
+    cam, cfg = api.make_config(fs, 16, integrator=api.RAYTRACER)
+    with pytest.raises(api.TurnerError):
+        pf.render(cam, cfg)

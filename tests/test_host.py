@@ -77,7 +77,7 @@ def test_blend_loader_equals_fixtures(api, scenes):
     for name in ("cornell_box", "furnace_test", "colored_cube", "orthogonal_planes"):
         a = api.load_blend("/root/reference/scenes/%s.blend" % name)
         b = scenes.fixture(name)
-        for k in ("vertices", "normals", "diffuse"):
+        for k in ("vertices", "normals", "diffuse", "reflective", "reflectivity"):
             assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (name, k)
         assert np.array_equal(np.float32(a["camera"]["trafo4x4"]), np.float32(b["camera"]["trafo4x4"]))
         assert np.float32(a["camera"]["hfov"]) == np.float32(b["camera"]["hfov"])

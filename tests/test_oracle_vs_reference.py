@@ -107,3 +107,30 @@ def test_prebuilt_tree_loads_through_reference_serialize_hook(ob, scenes, ref_ok
     assert r.height == o.height and r.num_nodes == o.num_nodes
     ro, rd = scenes.random_rays(sc, 5000, seed=3)
     assert np.array_equal(o.intersect(ro, rd)[0], r.intersect(ro, rd)[0])
+
+
+@pytest.mark.parametrize("name,depth,shadow,bg", [
+    ("cornell_box", 3, 0.5, (0, 0, 0, 1)), ("cornell_box", 1, 0.3, (0.2, 0.3, 0.4, 1)), ("cornell_box", 6, 1.0, (0, 0, 0, 1)),
+    ("colored_cube", 3, 0.5, (0.1, 0.1, 0.1, 1)), ("orthogonal_planes", 2, 0.0, (0, 0, 0, 1)),
+])
+def test_raytracer_radiance_identical(ob, scenes, ref_ok, name, depth, shadow, bg):
+    # raytracer.cpp:6-67 (Whitted integrator) against the reference's own TU
+    sc = scenes.fixture(name)
+    kw = dict(reflective=sc["reflective"], reflectivity=sc["reflectivity"])
+    o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"], **kw)
+    r = ob.RefScene(sc["vertices"], sc["normals"], sc["diffuse"], kind="raytracer", **kw)
+    a, _, st = o.render(ob.make_cfg(sc, 80, max_depth=depth, integrator=2, shadow_intensity=shadow, bg=bg, pixel_samples=2))
+    b, _, fin, rst = r.render(ob.ref_camera(sc), ob.ref_config(sc, 80, max_depth=depth, shadow_intensity=shadow, bg=bg,
+                                                               pixel_samples=2), want_final=True)
+    assert np.array_equal(bits(a), bits(b)) and st.num_rays == rst.num_rays
+    assert ob.write_p3(ob.tonemap(a, 2)) == ob.ref_write_p3(fin)
+    # a mirror that is a perfect, unshadowed reflector of a mirror: every recursion level is exercised
+    if name == "cornell_box":
+        sc2 = dict(sc)
+        sc2["reflectivity"] = np.full_like(sc["reflectivity"], 0.8)
+        o2 = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"], reflective=sc["reflective"], reflectivity=sc2["reflectivity"])
+        r2 = ob.RefScene(sc["vertices"], sc["normals"], sc["diffuse"], kind="raytracer", reflective=sc["reflective"],
+                         reflectivity=sc2["reflectivity"])
+        a2, _, s2 = o2.render(ob.make_cfg(sc, 48, max_depth=depth, integrator=2, shadow_intensity=shadow, bg=bg))
+        b2, _, _, rs2 = r2.render(ob.ref_camera(sc), ob.ref_config(sc, 48, max_depth=depth, shadow_intensity=shadow, bg=bg))
+        assert np.array_equal(bits(a2), bits(b2)) and s2.num_rays == rs2.num_rays and s2.num_rays > 48 * 48 * min(depth, 3)

@@ -122,7 +122,7 @@ def extract(path):
         objects.append(bf.by_ptr[obp])
         ptr = nxt
 
-    verts, norms, cols = [], [], []
+    verts, norms, cols, mirs, refls = [], [], [], [], []
     camera, light = None, None
     for ob in objects:
         (otype,) = bf.field(ob, "Object", "type", "h")
@@ -162,9 +162,16 @@ def extract(path):
                 for i in range(totcol):
                     (mp,) = struct.unpack_from("<Q", d, mb[5] + 8 * i)
                     ma = bf.by_ptr[mp]
-                    mats.append([bf.field(ma, "Material", c, "f")[0] for c in ("r", "g", "b")] + [1.0])
+                    rgb = [bf.field(ma, "Material", c, "f")[0] for c in ("r", "g", "b")]
+                    # assimp omits AI_MATKEY_COLOR_DIFFUSE for an all-zero colour -> Get() leaves aiColor4D() = 0,0,0,0
+                    dif = rgb + [1.0] if any(rgb) else [0.0, 0.0, 0.0, 0.0]
+                    mir = [bf.field(ma, "Material", c, "f")[0] for c in ("mirr", "mirg", "mirb")] + [1.0]
+                    (mode,) = bf.field(ma, "Material", "mode", "i")
+                    (ray_mirror,) = bf.field(ma, "Material", "ray_mirror", "f")
+                    refl = ray_mirror if (mode & 0x40000) else 0.0  # MA_RAYMIRROR -> AI_MATKEY_REFLECTIVITY
+                    mats.append((dif, mir, refl))
             if not mats:
-                mats = [[0.6, 0.6, 0.6, 1.0]]  # assimp's default material
+                mats = [([0.6, 0.6, 0.6, 1.0], [0.0, 0.0, 0.0, 0.0], 0.0)]  # assimp's default material
             co = [bf.field(mvert, "MVert", "co", "3f", i) for i in range(totvert)]
             no = [bf.field(mvert, "MVert", "no", "3h", i) for i in range(totvert)]
             polys = []
@@ -197,9 +204,11 @@ def extract(path):
                     for a, b, c in tris:
                         verts.append([float(x) for k in (a, b, c) for x in xf_point(co[vi[k]])])
                         norms.append([float(x) for k in (a, b, c) for x in xf_normal(no[vi[k]])])
-                        cols.append([float(np.float32(x)) for x in col])
+                        cols.append([float(np.float32(x)) for x in col[0]])
+                        mirs.append([float(np.float32(x)) for x in col[1]])
+                        refls.append(float(np.float32(col[2])))
     return {"source": path.split("/")[-1], "num_triangles": len(verts), "vertices": verts, "normals": norms,
-            "diffuse": cols, "camera": camera, "light": light}
+            "diffuse": cols, "reflective": mirs, "reflectivity": refls, "camera": camera, "light": light}
 
 
 if __name__ == "__main__":

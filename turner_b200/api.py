@@ -17,7 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libturner_b200.so")
 MISS_ID = 0x40000000
-PATHTRACER, RAYCASTER = 0, 1
+PATHTRACER, RAYCASTER, RAYTRACER = 0, 1, 2
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
@@ -46,6 +46,7 @@ class RenderConfig(C.Structure):
         ("num_lights", C.c_int32), ("light", Light),
         ("seed", C.c_uint64),
         ("sample_begin", C.c_int32), ("sample_stride", C.c_int32),
+        ("shadow_intensity", C.c_float),
     ]
 
 
@@ -69,12 +70,13 @@ class SceneInfo(C.Structure):
 
 class LoadedScene(C.Structure):
     _fields_ = [("num_triangles", C.c_uint32), ("verts", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)),
-                ("diffuse", C.POINTER(C.c_float)), ("has_camera", C.c_int32), ("cam_trafo4x4", C.c_float * 16),
+                ("diffuse", C.POINTER(C.c_float)), ("reflective", C.POINTER(C.c_float)),
+                ("reflectivity", C.POINTER(C.c_float)), ("has_camera", C.c_int32), ("cam_trafo4x4", C.c_float * 16),
                 ("cam_hfov", C.c_float), ("cam_aspect", C.c_float), ("num_lights", C.c_int32), ("light", Light)]
 
 
 EXPORTS = [
-    "trn_last_error", "trn_device_count", "trn_scene_create", "trn_scene_destroy", "trn_scene_get_info",
+    "trn_last_error", "trn_device_count", "trn_scene_create", "trn_scene_create_ex", "trn_scene_destroy", "trn_scene_get_info",
     "trn_scene_get_nodes", "trn_intersect", "trn_primary_hits", "trn_render", "trn_render_device", "trn_render_multi",
     "trn_set_profiling", "trn_set_counting", "trn_intersect_counted", "trn_camera_setup", "trn_tonemap", "trn_write_p3", "trn_load_blend", "trn_load_soup", "trn_loaded_scene_free",
 ]
@@ -101,6 +103,8 @@ def lib():
         L.trn_last_error.restype = C.c_char_p
         L.trn_device_count.restype = C.c_int32
         L.trn_scene_create.argtypes = [_f32p, _f32p, _f32p, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.trn_scene_create_ex.argtypes = [_f32p, _f32p, _f32p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.trn_scene_create_ex.restype = C.c_int32
         L.trn_scene_destroy.argtypes = [C.c_void_p]
         L.trn_scene_get_info.argtypes = [C.c_void_p, C.POINTER(SceneInfo)]
         L.trn_scene_get_nodes.argtypes = [C.c_void_p, _u64p]
@@ -159,7 +163,7 @@ def camera_setup(trafo4x4, hfov, aspect, width):
 
 
 def make_config(scene, width, max_depth=3, mc_samples=8, pixel_samples=1, integrator=PATHTRACER, bg=(0, 0, 0, 1),
-                max_visibility=2.0, aspect=1.0, seed=1, sample_begin=0, sample_stride=1):
+                max_visibility=2.0, aspect=1.0, seed=1, sample_begin=0, sample_stride=1, shadow_intensity=0.5):
     """TracerConfig defaults of the reference's USAGE text (pathtracer.h:3-25); returns (Camera, RenderConfig)"""
     cam, height = camera_setup(scene["camera"]["trafo4x4"], scene["camera"]["hfov"], aspect, width)
     cfg = RenderConfig()
@@ -174,25 +178,32 @@ def make_config(scene, width, max_depth=3, mc_samples=8, pixel_samples=1, integr
         cfg.light.rgba = (C.c_float * 4)(*light["color"])
     cfg.seed = seed
     cfg.sample_begin, cfg.sample_stride = sample_begin, sample_stride
+    cfg.shadow_intensity = shadow_intensity
     return cam, cfg
 
 
 class Scene:
     """KDTree(triangles_from_scene(scene)) (main.cpp:25-82,156-157): triangles + kd-tree, host + device copies"""
 
-    def __init__(self, vertices, normals, diffuse):
+    def __init__(self, vertices, normals, diffuse, reflective=None, reflectivity=None):
         v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 9)
         n = np.ascontiguousarray(normals, np.float32).reshape(-1, 9)
         d = np.ascontiguousarray(diffuse, np.float32).reshape(-1, 4)
         assert v.shape[0] == n.shape[0] == d.shape[0]
         self.h = C.c_void_p()
-        _check(lib().trn_scene_create(v, n, d, v.shape[0], C.byref(self.h)))
+        if reflective is None and reflectivity is None:
+            _check(lib().trn_scene_create(v, n, d, v.shape[0], C.byref(self.h)))
+        else:
+            m = np.ascontiguousarray(reflective, np.float32).reshape(-1, 4)
+            k = np.ascontiguousarray(reflectivity, np.float32).reshape(-1)
+            assert m.shape[0] == k.shape[0] == v.shape[0]
+            _check(lib().trn_scene_create_ex(v, n, d, m.ctypes.data, k.ctypes.data, v.shape[0], C.byref(self.h)))
         self.info = SceneInfo()
         _check(lib().trn_scene_get_info(self.h, C.byref(self.info)))
 
     @classmethod
     def from_dict(cls, scene):
-        return cls(scene["vertices"], scene["normals"], scene["diffuse"])
+        return cls(scene["vertices"], scene["normals"], scene["diffuse"], scene.get("reflective"), scene.get("reflectivity"))
 
     def close(self):
         if getattr(self, "h", None):
@@ -298,8 +309,11 @@ def save_soup(scene, path):
         f.write("camera %s %.9g\n" % (f9(scene["camera"]["trafo4x4"]), scene["camera"]["hfov"]))
         if scene.get("light"):
             f.write("light %s %s\n" % (f9(scene["light"]["pos"]), f9(scene["light"]["color"])))
-        for v, n, d in zip(scene["vertices"], scene["normals"], scene["diffuse"]):
-            f.write("tri %s %s %s\n" % (f9(v), f9(n), f9(d)))
+        nt = len(scene["vertices"])
+        mir = scene.get("reflective", np.zeros((nt, 4), np.float32))
+        ref = scene.get("reflectivity", np.zeros(nt, np.float32))
+        for v, n, d, m, k in zip(scene["vertices"], scene["normals"], scene["diffuse"], mir, ref):
+            f.write("tri %s %s %s %s %.9g\n" % (f9(v), f9(n), f9(d), f9(m), float(k)))
 
 
 def load_blend(path):
@@ -314,6 +328,8 @@ def load_blend(path):
             "vertices": np.ctypeslib.as_array(ls.verts, (n, 9)).copy(),
             "normals": np.ctypeslib.as_array(ls.normals, (n, 9)).copy(),
             "diffuse": np.ctypeslib.as_array(ls.diffuse, (n, 4)).copy(),
+            "reflective": np.ctypeslib.as_array(ls.reflective, (n, 4)).copy(),
+            "reflectivity": np.ctypeslib.as_array(ls.reflectivity, (n,)).copy(),
             "camera": {"trafo4x4": list(ls.cam_trafo4x4), "hfov": float(ls.cam_hfov)} if ls.has_camera else None,
             "light": {"pos": list(ls.light.pos), "color": list(ls.light.rgba)} if ls.num_lights else None,
         }

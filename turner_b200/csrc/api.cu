@@ -63,6 +63,8 @@ struct DeviceScene {
     void* d_isect_hot = nullptr;
     void* d_isect_cold = nullptr;
     void* d_shade = nullptr;
+    void* d_mirror = nullptr;
+    uint32_t* d_child_slot = nullptr; // raytracer: child-ray slot of every shadow query
     // work buffers (sized lazily, reused across calls)
     uint64_t wave_cap = 0;        // rays per wave buffer
     std::vector<RayWave> waves;   // one per depth level in use
@@ -101,6 +103,8 @@ struct DeviceScene {
         cudaFree(d_isect_hot);
         cudaFree(d_isect_cold);
         cudaFree(d_shade);
+        cudaFree(d_mirror);
+        cudaFree(d_child_slot);
         for (void* p : wave_mem) cudaFree(p);
         cudaFree(shadow_mem);
         cudaFree(d_hits);
@@ -209,6 +213,7 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
         CUDA_TRY(up(&ds->d_isect_cold, cold.data(), cold.size() * sizeof(float)));
     }
     CUDA_TRY(up(&ds->d_shade, sc->tris.shade.data(), sc->tris.shade.size() * sizeof(float)));
+    CUDA_TRY(up(&ds->d_mirror, sc->tris.mirror.data(), sc->tris.mirror.size() * sizeof(float)));
     ds->dev.nodes = static_cast<const uint2*>(ds->d_nodes);
     ds->dev.leaf_refs = static_cast<const uint32_t*>(ds->d_refs);
     ds->dev.pnodes = static_cast<const uint2*>(ds->d_pnodes);
@@ -216,6 +221,7 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     ds->dev.isect_hot = static_cast<const float4*>(ds->d_isect_hot);
     ds->dev.isect_cold = static_cast<const float4*>(ds->d_isect_cold);
     ds->dev.shade = static_cast<const float4*>(ds->d_shade);
+    ds->dev.mirror = static_cast<const float4*>(ds->d_mirror);
     for (int c = 0; c < 3; ++c) {
         ds->dev.lo[c] = sc->tree.box[c];
         ds->dev.hi[c] = sc->tree.box[3 + c];
@@ -305,12 +311,15 @@ static int ensure_waves(DeviceScene* ds, uint64_t cap, int levels) {
         ds->shadow_mem = nullptr;
         cudaFree(ds->d_hits);
         ds->d_hits = nullptr;
+        cudaFree(ds->d_child_slot);
+        ds->d_child_slot = nullptr;
         cudaFree(ds->d_keys); cudaFree(ds->d_keys_alt); cudaFree(ds->d_order); cudaFree(ds->d_order_alt); cudaFree(ds->d_sort_tmp);
         ds->d_keys = ds->d_keys_alt = ds->d_order = ds->d_order_alt = nullptr;
         ds->d_sort_tmp = nullptr;
         ds->wave_cap = cap;
     }
     if (!ds->d_hits) CUDA_TRY(cudaMalloc(&ds->d_hits, cap * sizeof(uint4)));
+    if (!ds->d_child_slot) CUDA_TRY(cudaMalloc(&ds->d_child_slot, cap * sizeof(uint32_t)));
     if (!ds->d_keys) {
         CUDA_TRY(cudaMalloc(&ds->d_keys, cap * 4));
         CUDA_TRY(cudaMalloc(&ds->d_keys_alt, cap * 4));
@@ -367,8 +376,14 @@ static int validate(const trn_camera* cam, const trn_render_config* cfg) {
     if (!cam || !cfg) return fail(TRN_ERR_INVALID, "null camera/config");
     if (cfg->width < 1 || cfg->height < 1) return fail(TRN_ERR_INVALID, "width/height must be >= 1");
     if (cfg->pixel_samples < 1) return fail(TRN_ERR_INVALID, "pixel_samples must be >= 1 (config.h:124)");
-    if (cfg->integrator != TRN_PATHTRACER && cfg->integrator != TRN_RAYCASTER)
+    if (cfg->integrator != TRN_PATHTRACER && cfg->integrator != TRN_RAYCASTER && cfg->integrator != TRN_RAYTRACER)
         return fail(TRN_ERR_INVALID, "unknown integrator");
+    if (cfg->integrator == TRN_RAYTRACER) {
+        if (cfg->max_depth < 1) return fail(TRN_ERR_INVALID, "max_depth must be > 0 (config.h:121)");
+        if (cfg->num_lights != 1) return fail(TRN_ERR_INVALID, "the raytracer needs exactly one light (raytracer.cpp:15 takes lights.front())");
+        if (!(cfg->shadow_intensity >= 0.f && cfg->shadow_intensity <= 1.f))
+            return fail(TRN_ERR_INVALID, "shadow_intensity must be in [0,1] (config.h:123)");
+    }
     if (cfg->integrator == TRN_PATHTRACER) {
         if (cfg->max_depth < 1) return fail(TRN_ERR_INVALID, "max_depth must be > 0 (config.h:121)");
         if (cfg->mc_samples < 1) return fail(TRN_ERR_INVALID, "mc_samples must be >= 1");
@@ -405,6 +420,7 @@ static FrameParams make_frame(const trn_camera* cam, const trn_render_config* cf
     std::memcpy(fp.light_pos, cfg->light.pos, sizeof fp.light_pos);
     std::memcpy(fp.light_rgba, cfg->light.rgba, sizeof fp.light_rgba);
     fp.max_visibility = cfg->max_visibility;
+    fp.shadow_intensity = cfg->shadow_intensity;
     fp.seed = cfg->seed;
     return fp;
 }
@@ -472,6 +488,7 @@ struct Renderer {
 
     int process(int depth, const RayWave& wave, uint32_t count, uint64_t first_local_index) {
         const int m = fp.mc_samples;
+        if (integrator == TRN_RAYTRACER) return process_raytrace(depth, wave, count, first_local_index);
         const bool spawn = integrator == TRN_PATHTRACER && depth < fp.max_depth;
         const uint64_t chunk_max = spawn ? std::max<uint64_t>(1, cap / static_cast<uint64_t>(m)) : cap;
         for (uint64_t off = 0; off < count; off += chunk_max) {
@@ -556,9 +573,48 @@ struct Renderer {
         return TRN_OK;
     }
 
+    // raytracer.cpp:6-67: fan-out <= 1 (mirror), the shadow query also scales the child's throughput
+    int process_raytrace(int depth, const RayWave& wave, uint32_t n, uint64_t first_local_index) {
+        uint32_t cs;
+        int rc = next_slot(&cs);
+        if (rc) return rc;
+        timer.begin(0);
+        if (mode_closest == 2)
+            TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), stream, ds->dev, wave.a, wave.b, nullptr, nullptr,
+                          nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2, nullptr, ds->treelet_pairs);
+        else
+            trace_closest_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, wave.a, wave.b, n, ds->d_hits);
+        timer.end();
+        ++launches;
+        ++trace_launches;
+        trace_queries += n;
+        rays += n;
+        const bool may_spawn = depth < fp.max_depth;
+        RayWave next = may_spawn ? ds->waves[depth + 1] : RayWave{nullptr, nullptr, nullptr};
+        timer.begin(2);
+        shade_raytrace_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(ds->dev, fp, first_local_index, wave, ds->d_hits, n, depth, next,
+                                                                     ds->shadow, ds->d_child_slot, ds->d_counters + cs, ds->d_hitcount,
+                                                                     acc);
+        timer.end();
+        ++launches;
+        CUDA_TRY(cudaMemcpyAsync(ds->h_counters + cs, ds->d_counters + cs, sizeof(WaveCounters), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaEventRecord(ds->ev_sync, stream));
+        timer.begin(1);
+        trace_shadow_raytrace_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_child_slot, ds->d_counters + cs,
+                                                                            fp.shadow_intensity, next.T, acc);
+        timer.end();
+        ++launches;
+        ++shadow_launches;
+        CUDA_TRY(cudaEventSynchronize(ds->ev_sync));
+        const WaveCounters wc = ds->h_counters[cs];
+        shadow += wc.shadow_count;
+        if (may_spawn && wc.next_count) return process_raytrace(depth + 1, next, wc.next_count, first_local_index);
+        return TRN_OK;
+    }
+
     int run() {
         const uint64_t total = static_cast<uint64_t>(fp.width) * fp.height * static_cast<uint64_t>(fp.n_local);
-        if (integrator == TRN_RAYCASTER) CUDA_TRY(cudaMemsetAsync(ds->d_hitcount, 0, sizeof(unsigned long long), stream));
+        if (integrator != TRN_PATHTRACER) CUDA_TRY(cudaMemsetAsync(ds->d_hitcount, 0, sizeof(unsigned long long), stream));
         if (counting) CUDA_TRY(cudaMemsetAsync(ds->d_visits, 0, 12 * sizeof(unsigned long long), stream));
         // primaries per batch: as many as fit one wave
         const uint64_t batch = cap;
@@ -578,6 +634,12 @@ struct Renderer {
             CUDA_TRY(cudaStreamSynchronize(stream));
             rays = hc; // raycaster.cpp:17 counts a ray only when it hits
         }
+        if (integrator == TRN_RAYTRACER) {
+            unsigned long long cut = 0;
+            CUDA_TRY(cudaMemcpyAsync(&cut, ds->d_hitcount, sizeof cut, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            rays += cut; // calls the depth check rejects are counted too (raytracer.cpp:9-13)
+        }
         CUDA_TRY(cudaGetLastError());
         return TRN_OK;
     }
@@ -594,7 +656,7 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
     CUDA_TRY(cudaSetDevice(ds->device));
     if (ds_out) *ds_out = ds;
     FrameParams fp = make_frame(cam, cfg);
-    const int levels = cfg->integrator == TRN_PATHTRACER ? cfg->max_depth + 1 : 1;
+    const int levels = cfg->integrator == TRN_RAYCASTER ? 1 : cfg->max_depth + 1;
     const uint64_t cap = env_u64("TRN_WAVE_CAP", 16ull << 20);
     rc = ensure_waves(ds, cap, levels);
     if (rc) return rc;
@@ -704,13 +766,18 @@ void trn_set_profiling(int32_t enabled) { g_profiling = enabled; }
 void trn_set_counting(int32_t enabled) { g_counting = enabled; }
 
 int32_t trn_scene_create(const float* verts, const float* normals, const float* diffuse, uint32_t n, trn_scene** out) {
+    return trn_scene_create_ex(verts, normals, diffuse, nullptr, nullptr, n, out);
+}
+
+int32_t trn_scene_create_ex(const float* verts, const float* normals, const float* diffuse, const float* reflective,
+                            const float* reflectivity, uint32_t n, trn_scene** out) {
     if (!verts || !normals || !diffuse || !out) return fail(TRN_ERR_INVALID, "null argument");
     if (n == 0) return fail(TRN_ERR_INVALID, "scene needs at least one triangle (lib/kdtree.cpp:475)");
     if (n >= TRN_MISS_ID) return fail(TRN_ERR_LIMIT, "triangle count must be < 2^30 (lib/kdtree.cpp:476)");
     for (size_t i = 0; i < size_t(n) * 9; ++i)
         if (!std::isfinite(verts[i])) return fail(TRN_ERR_INVALID, "non-finite vertex coordinate");
     std::unique_ptr<trn_scene> sc(new trn_scene);
-    precompute_triangles(verts, normals, diffuse, n, sc->tris);
+    precompute_triangles(verts, normals, diffuse, n, sc->tris, reflective, reflectivity);
     build_kdtree(sc->tris, sc->tree, static_cast<int>(env_u64("TRN_BUILD_THREADS", 0)));
     if (sc->tree.height + 1 > static_cast<uint64_t>(kStackDepth))
         return fail(TRN_ERR_LIMIT, "kd-tree height " + std::to_string(sc->tree.height) + " exceeds the traversal stack (" +

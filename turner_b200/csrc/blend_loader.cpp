@@ -196,7 +196,7 @@ int32_t trn_load_blend(const char* path, trn_loaded_scene* out) {
         }
     if (!scene) return trn::fail(TRN_ERR_IO, "no Scene block");
 
-    std::vector<float> verts, norms, cols;
+    std::vector<float> verts, norms, cols, mirs, refls;
     int num_cameras = 0;
     uint64_t base_ptr = bf.rd<uint64_t>(scene->offset + bf.foff("Scene", "base")); // ListBase.first
     while (base_ptr) {
@@ -242,19 +242,34 @@ int32_t trn_load_blend(const char* path, trn_loaded_scene* out) {
             const Block* mpoly = bf.at(bf.get<uint64_t>(data, "Mesh", "mpoly"));
             const Block* mloop = bf.at(bf.get<uint64_t>(data, "Mesh", "mloop"));
             if (!mvert || !mpoly || !mloop) continue;
-            std::vector<std::array<float, 4>> mats;
+            struct Mat {
+                std::array<float, 4> dif, mir;
+                float refl;
+            };
+            const Mat dflt = {{0.6f, 0.6f, 0.6f, 1.f}, {0.f, 0.f, 0.f, 0.f}, 0.f}; // assimp's default material
+            std::vector<Mat> mats;
             const Block* matarr = bf.at(bf.get<uint64_t>(data, "Mesh", "mat"));
             if (matarr)
                 for (int i = 0; i < totcol; ++i) {
                     const Block* ma = bf.at(bf.rd<uint64_t>(matarr->offset + 8 * static_cast<size_t>(i)));
-                    if (ma) mats.push_back({bf.get<float>(ma, "Material", "r"), bf.get<float>(ma, "Material", "g"), bf.get<float>(ma, "Material", "b"), 1.f});
-                    else mats.push_back({0.6f, 0.6f, 0.6f, 1.f});
+                    if (!ma) {
+                        mats.push_back(dflt);
+                        continue;
+                    }
+                    Mat m;
+                    const float r = bf.get<float>(ma, "Material", "r"), g = bf.get<float>(ma, "Material", "g"), b = bf.get<float>(ma, "Material", "b");
+                    // an all-zero diffuse colour is not exported -> Get() leaves the default aiColor4D (0,0,0,0)
+                    m.dif = (r || g || b) ? std::array<float, 4>{r, g, b, 1.f} : std::array<float, 4>{0.f, 0.f, 0.f, 0.f};
+                    m.mir = {bf.get<float>(ma, "Material", "mirr"), bf.get<float>(ma, "Material", "mirg"), bf.get<float>(ma, "Material", "mirb"), 1.f};
+                    // AI_MATKEY_REFLECTIVITY is only exported when ray mirroring is on (MA_RAYMIRROR = 0x40000)
+                    m.refl = (bf.get<int32_t>(ma, "Material", "mode") & 0x40000) ? bf.get<float>(ma, "Material", "ray_mirror") : 0.f;
+                    mats.push_back(m);
                 }
-            if (mats.empty()) mats.push_back({0.6f, 0.6f, 0.6f, 1.f}); // assimp's default material
+            if (mats.empty()) mats.push_back(dflt);
             int max_slot = 0;
             for (int i = 0; i < totpoly; ++i) max_slot = std::max<int>(max_slot, bf.get<int16_t>(mpoly, "MPoly", "mat_nr", i));
             for (int slot = 0; slot <= max_slot; ++slot) {
-                const auto& col = mats[static_cast<size_t>(slot) < mats.size() ? slot : 0];
+                const Mat& col = mats[static_cast<size_t>(slot) < mats.size() ? slot : 0];
                 for (int i = 0; i < totpoly; ++i) {
                     if (bf.get<int16_t>(mpoly, "MPoly", "mat_nr", i) != slot) continue;
                     const int32_t ls = bf.get<int32_t>(mpoly, "MPoly", "loopstart", i);
@@ -276,7 +291,9 @@ int32_t trn_load_blend(const char* path, trn_loaded_scene* out) {
                                 norms.push_back(T[r][0] * no[0] + T[r][1] * no[1] + T[r][2] * no[2]);           // aiMatrix3x3(T) * n
                             }
                         }
-                        cols.insert(cols.end(), col.begin(), col.end());
+                        cols.insert(cols.end(), col.dif.begin(), col.dif.end());
+                        mirs.insert(mirs.end(), col.mir.begin(), col.mir.end());
+                        refls.push_back(col.refl);
                     }
                 }
             }
@@ -297,13 +314,17 @@ int32_t trn_load_blend(const char* path, trn_loaded_scene* out) {
             out->normals[t * 9 + k] = norms[t * 9 + k];
         }
     std::memcpy(out->diffuse, cols.data(), n * 4 * sizeof(float));
+    out->reflective = static_cast<float*>(std::malloc(n * 4 * sizeof(float)));
+    out->reflectivity = static_cast<float*>(std::malloc(n * sizeof(float)));
+    std::memcpy(out->reflective, mirs.data(), n * 4 * sizeof(float));
+    std::memcpy(out->reflectivity, refls.data(), n * sizeof(float));
     return TRN_OK;
 }
 
 // Neutral triangle-soup text format, one record per line, '#' starts a comment:
 //   camera <16 floats: node transformation, row-major a1..d4> <hfov radians>
 //   light  <x y z> <r g b a>                       (optional, at most one)
-//   tri    <v0 v1 v2: 9 floats> <n0 n1 n2: 9 floats> <r g b a>
+//   tri    <v0 v1 v2: 9 floats> <n0 n1 n2: 9 floats> <r g b a> [<reflective r g b a> <reflectivity>]
 // Values are what main.cpp:25-82,109-136 would hand to the renderer (world space). Floats are parsed with strtof,
 // so "%.9g" text round-trips fp32 exactly.
 int32_t trn_load_soup(const char* path, trn_loaded_scene* out) {
@@ -311,7 +332,7 @@ int32_t trn_load_soup(const char* path, trn_loaded_scene* out) {
     std::memset(out, 0, sizeof *out);
     FILE* f = std::fopen(path, "r");
     if (!f) return trn::fail(TRN_ERR_IO, std::string("cannot open ") + path);
-    std::vector<float> verts, norms, cols;
+    std::vector<float> verts, norms, cols, mirs, refls;
     std::vector<char> line(1 << 16);
     int lineno = 0;
     auto parse = [](char* p, float* dst, int n) {
@@ -329,11 +350,14 @@ int32_t trn_load_soup(const char* path, trn_loaded_scene* out) {
         char* p = line.data();
         while (*p == ' ' || *p == '\t') ++p;
         if (*p == '#' || *p == '\n' || *p == 0) continue;
-        float v[22];
+        float v[27];
         if (std::strncmp(p, "tri", 3) == 0 && parse(p + 3, v, 22)) {
             verts.insert(verts.end(), v, v + 9);
             norms.insert(norms.end(), v + 9, v + 18);
             cols.insert(cols.end(), v + 18, v + 22);
+            if (!parse(p + 3, v, 27)) std::fill(v + 22, v + 27, 0.f); // optional mirror material
+            mirs.insert(mirs.end(), v + 22, v + 26);
+            refls.push_back(v[26]);
         } else if (std::strncmp(p, "camera", 6) == 0 && parse(p + 6, v, 17)) {
             std::memcpy(out->cam_trafo4x4, v, 16 * sizeof(float));
             out->cam_hfov = v[16];
@@ -361,6 +385,10 @@ int32_t trn_load_soup(const char* path, trn_loaded_scene* out) {
     std::memcpy(out->verts, verts.data(), n * 9 * sizeof(float));
     std::memcpy(out->normals, norms.data(), n * 9 * sizeof(float));
     std::memcpy(out->diffuse, cols.data(), n * 4 * sizeof(float));
+    out->reflective = static_cast<float*>(std::malloc(n * 4 * sizeof(float)));
+    out->reflectivity = static_cast<float*>(std::malloc(n * sizeof(float)));
+    std::memcpy(out->reflective, mirs.data(), n * 4 * sizeof(float));
+    std::memcpy(out->reflectivity, refls.data(), n * sizeof(float));
     return TRN_OK;
 }
 
@@ -369,6 +397,8 @@ void trn_loaded_scene_free(trn_loaded_scene* s) {
     std::free(s->verts);
     std::free(s->normals);
     std::free(s->diffuse);
+    std::free(s->reflective);
+    std::free(s->reflectivity);
     std::memset(s, 0, sizeof *s);
 }
 

@@ -1,7 +1,7 @@
-// `pathtracer` / `raycaster` executables: the reference's command line, stderr report and P3 output
+// `pathtracer` / `raycaster` / `raytracer` executables: the reference's command line, stderr report and P3 output
 // (main.cpp:88-244, pathtracer.h / raycaster.h USAGE, config.h, lib/output.h:101-113,
 // lib/progress_bar.h) in front of the CUDA render loop in libturner_b200.so.
-// One source, two binaries: -DTRN_CLI_PATHTRACER or -DTRN_CLI_RAYCASTER (the reference links
+// One source, three binaries: -DTRN_CLI_PATHTRACER, -DTRN_CLI_RAYCASTER or -DTRN_CLI_RAYTRACER (the reference links
 // main.cpp against one integrator TU the same way, CMakeLists.txt:43-67).
 //
 // Deliberately not replicated: ./kdtree.cache (main.cpp:142-167 loads whatever tree is lying in the CWD,
@@ -22,10 +22,13 @@
 namespace {
 
 #if defined(TRN_CLI_RAYCASTER)
-constexpr bool kPathtracer = false;
+constexpr bool kPathtracer = false, kRaytracer = false;
 const char* kProgram = "raycaster";
+#elif defined(TRN_CLI_RAYTRACER)
+constexpr bool kPathtracer = false, kRaytracer = true;
+const char* kProgram = "raytracer";
 #else
-constexpr bool kPathtracer = true;
+constexpr bool kPathtracer = true, kRaytracer = false;
 const char* kProgram = "pathtracer";
 #endif
 
@@ -52,6 +55,10 @@ std::string usage_text() {
              "  -d --max-depth=<int>              Maximum recursion depth [default: 3].\n"
              "  -p --pixel-samples=<int>          Samples per pixel [default: 1].\n"
              "  -m --monte-carlo-samples=<int>    Monte Carlo samples per hit [default: 8].\n";
+    } else if (kRaytracer) {
+        u << "Raytracer options:\n"
+             "  -d --max-depth=<int>              Maximum recursion depth [default: 3].\n"
+             "  --shadow=<float>                  Intensity of shadow [default: 0.5].\n";
     } else {
         u << "Raycaster options:\n"
              "  --max-visibility=<float>          Anything farther away is dark [default: 2.0].\n";
@@ -90,25 +97,25 @@ struct OptSpec {
     const char* shortname; // "-w" or nullptr
     const char* longname;  // "--width"
     bool takes_value;
-    bool pathtracer_only;
-    bool raycaster_only;
+    int programs; // bit 0 pathtracer, bit 1 raycaster, bit 2 raytracer
 };
+constexpr int kThisProgram = kPathtracer ? 1 : (kRaytracer ? 4 : 2);
 
 const OptSpec kSpecs[] = {
-    {"-w", "--width", true, false, false},          {"-a", "--aspect", true, false, false},
-    {nullptr, "--background", true, false, false},  {"-t", "--threads", true, false, false},
-    {nullptr, "--inverse-gamma", true, false, false}, {nullptr, "--no-gamma-correction", false, false, false},
-    {nullptr, "--exposure", true, false, false},    {"-v", "--verbose", false, false, false},
-    {nullptr, "--gpus", true, false, false},        {nullptr, "--seed", true, false, false},
-    {nullptr, "--dump-linear", true, false, false}, {nullptr, "--dump-hits", true, false, false},
-    {"-h", "--help", false, false, false},          {"-d", "--max-depth", true, true, false},
-    {"-p", "--pixel-samples", true, true, false},   {"-m", "--monte-carlo-samples", true, true, false},
-    {nullptr, "--max-visibility", true, false, true},
+    {"-w", "--width", true, 7},          {"-a", "--aspect", true, 7},
+    {nullptr, "--background", true, 7},  {"-t", "--threads", true, 7},
+    {nullptr, "--inverse-gamma", true, 7}, {nullptr, "--no-gamma-correction", false, 7},
+    {nullptr, "--exposure", true, 7},    {"-v", "--verbose", false, 7},
+    {nullptr, "--gpus", true, 7},        {nullptr, "--seed", true, 7},
+    {nullptr, "--dump-linear", true, 7}, {nullptr, "--dump-hits", true, 7},
+    {"-h", "--help", false, 7},          {"-d", "--max-depth", true, 1 | 4},
+    {"-p", "--pixel-samples", true, 1},  {"-m", "--monte-carlo-samples", true, 1},
+    {nullptr, "--max-visibility", true, 2}, {nullptr, "--shadow", true, 4},
 };
 
 const OptSpec* find_spec(const std::string& name) {
     for (const auto& s : kSpecs) {
-        if ((s.pathtracer_only && !kPathtracer) || (s.raycaster_only && kPathtracer)) continue;
+        if (!(s.programs & kThisProgram)) continue;
         if (name == s.longname || (s.shortname && name == s.shortname)) return &s;
     }
     return nullptr;
@@ -133,6 +140,7 @@ void apply(Options& o, const OptSpec& s, const std::string& v) {
         else if (n == "--pixel-samples") o.pixel_samples = std::stol(v);
         else if (n == "--monte-carlo-samples") o.mc_samples = std::stol(v);
         else if (n == "--max-visibility") o.max_visibility = std::stof(v);
+        else if (n == "--shadow") o.shadow_intensity = std::stof(v);
         else if (n == "--help") {
             std::cout << usage_text();
             std::exit(0);
@@ -275,6 +283,7 @@ int main(int argc, char const* argv[]) {
     require(0 <= o.max_visibility, "0 <= max-visibility"); // config.h:122
     require(1 <= o.pixel_samples, "1 <= pixel-samples"); // config.h:124
     require(1 <= o.mc_samples, "1 <= monte-carlo-samples (0 divides by zero in the reference, pathtracer.cpp:88)");
+    require(0 <= o.shadow_intensity && o.shadow_intensity <= 1, "0 <= shadow <= 1"); // config.h:123
     require(1 <= o.width, "1 <= width");
     require(1 <= o.gpus, "1 <= gpus");
     if (o.verbose) print_config(o);
@@ -299,7 +308,7 @@ int main(int argc, char const* argv[]) {
     setenv("TRN_BUILD_THREADS", std::to_string(o.threads).c_str(), 0);
     trn_scene* scene = nullptr;
     const auto t_kd = std::chrono::steady_clock::now();
-    if (trn_scene_create(ls.verts, ls.normals, ls.diffuse, ls.num_triangles, &scene) != TRN_OK) {
+    if (trn_scene_create_ex(ls.verts, ls.normals, ls.diffuse, ls.reflective, ls.reflectivity, ls.num_triangles, &scene) != TRN_OK) {
         std::cerr << trn_last_error() << std::endl;
         return 2;
     }
@@ -315,7 +324,8 @@ int main(int argc, char const* argv[]) {
     cfg.max_depth = static_cast<int32_t>(o.max_depth);
     cfg.mc_samples = static_cast<int32_t>(o.mc_samples);
     cfg.pixel_samples = static_cast<int32_t>(o.pixel_samples);
-    cfg.integrator = kPathtracer ? TRN_PATHTRACER : TRN_RAYCASTER;
+    cfg.integrator = kPathtracer ? TRN_PATHTRACER : (kRaytracer ? TRN_RAYTRACER : TRN_RAYCASTER);
+    cfg.shadow_intensity = o.shadow_intensity;
     std::memcpy(cfg.bg_rgba, bg, sizeof bg);
     cfg.max_visibility = o.max_visibility;
     cfg.num_lights = ls.num_lights;

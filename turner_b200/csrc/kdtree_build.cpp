@@ -385,8 +385,11 @@ void free_tree(BuildNode* root) {
 
 } // namespace
 
-void precompute_triangles(const float* verts, const float* normals, const float* diffuse, uint32_t n, HostTriangles& out) {
+void precompute_triangles(const float* verts, const float* normals, const float* diffuse, uint32_t n, HostTriangles& out,
+                          const float* reflective, const float* reflectivity) {
     out.count = n;
+    out.mirror.assign(size_t(n) * 4, 0.f);
+    if (reflective) std::memcpy(out.mirror.data(), reflective, size_t(n) * 4 * sizeof(float));
     out.verts.assign(verts, verts + size_t(n) * 9);
     out.isect.resize(size_t(n) * 16);
     out.shade.resize(size_t(n) * 16);
@@ -413,7 +416,8 @@ void precompute_triangles(const float* verts, const float* normals, const float*
         r[15] = uv * uv - uu * vv;
         float* s = &out.shade[size_t(i) * 16];
         std::memcpy(s, normals + size_t(i) * 9, 9 * sizeof(float));
-        s[9] = s[10] = s[11] = 0.f;
+        s[9] = reflectivity ? reflectivity[i] : 0.f;
+        s[10] = s[11] = 0.f;
         std::memcpy(s + 12, diffuse + size_t(i) * 4, 4 * sizeof(float));
     }
 }

@@ -19,11 +19,13 @@ struct HostTriangles {
     // shading record: n0.xyz n1.xyz n2.xyz pad*3 rgba (lib/triangle.h:95-98)
     std::vector<float> shade; // n*16
     std::vector<float> verts; // n*9, as given
+    std::vector<float> mirror; // n*4 reflective rgba (raytracer only); reflectivity sits in shade[9]
     uint32_t count = 0;
 };
 
 // fills isect/shade from raw arrays (verts n*9, normals n*9, diffuse n*4)
-void precompute_triangles(const float* verts, const float* normals, const float* diffuse, uint32_t n, HostTriangles& out);
+void precompute_triangles(const float* verts, const float* normals, const float* diffuse, uint32_t n, HostTriangles& out,
+                          const float* reflective = nullptr, const float* reflectivity = nullptr);
 
 struct KdTree {
     float box[6]; // min xyz, max xyz (KDTree::box())

@@ -29,7 +29,8 @@ struct DevScene {
     // edge words), cold = 2 x float4: u.z v.xyz | uv vv uu denom (only for candidates that pass 0 <= r < best)
     const float4* isect_hot;
     const float4* isect_cold;
-    const float4* shade;       // 4 x float4 per triangle: n0.xyz n1.x | n1.yz n2.xy | n2.z - - - | rgba
+    const float4* shade;       // 4 x float4 per triangle: n0.xyz n1.x | n1.yz n2.xy | n2.z reflectivity - - | rgba
+    const float4* mirror;      // reflective rgba per triangle (raytracer integrator only)
     float lo[3], hi[3];        // KDTree::box()
     // production layout: sibling pairs + empty-space cuts (kdtree_build.h); `nodes`/`leaf_refs` above hold the
     // reference-shaped tree and are uploaded only for the instrumented reference-schedule twin
@@ -67,6 +68,7 @@ struct FrameParams {
     float light_pos[3];
     float light_rgba[4];
     float max_visibility;
+    float shadow_intensity;
     uint64_t seed;
 };
 
@@ -675,6 +677,132 @@ __global__ void __launch_bounds__(128) trace_shadow_count_kernel(DevScene sc, Sh
     }
     flush_counts(vc, g);
     flush_counts(vp, g + 6);
+}
+
+// ------------------------------------------------------------------ raytracer integrator (raytracer.cpp:6-67)
+// Throughput form of the recursion  color = F * ((1-k) * direct + k * R * trace(reflected)),  F = shadowed ? (x - x*sh) : x:
+//   pixel += T * F * base,  base = k > 0 ? (1-k)*direct : direct;   child throughput T' = T * F * (k*R).
+// The shade kernel emits the shadow query (carrying T*base and the slot of the child ray); the shadow kernel applies F
+// to the contribution AND to the child's throughput before the child's own shading reads it (stream order).
+__global__ void __launch_bounds__(256) shade_raytrace_kernel(DevScene sc, FrameParams fp, uint64_t first_local_index,
+                                                             RayWave cur, const uint4* __restrict__ hits, uint32_t count,
+                                                             int depth, RayWave next, ShadowWave shadow,
+                                                             uint32_t* __restrict__ child_slot,
+                                                             WaveCounters* __restrict__ counters,
+                                                             unsigned long long* __restrict__ cut_rays,
+                                                             float4* __restrict__ acc) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    bool is_hit = false, spawn = false, cut = false;
+    float4 a, b, T = make_float4(0, 0, 0, 0), contrib = make_float4(0, 0, 0, 0), Tc = make_float4(0, 0, 0, 0);
+    float p2x = 0, p2y = 0, p2z = 0, ldx = 0, ldy = 0, ldz = 0, ldist = 0, rx = 0, ry = 0, rz = 0;
+    uint32_t rel = 0, pixel = 0;
+    if (idx < count) {
+        a = __ldcs(&cur.a[idx]);
+        b = __ldcs(&cur.b[idx]);
+        T = __ldcs(&cur.T[idx]);
+        const uint4 h = __ldcs(&hits[idx]);
+        rel = __float_as_uint(b.z);
+        uint32_t sample_i;
+        pixel = pixel_of(fp, first_local_index, rel, sample_i);
+        is_hit = h.x != kMiss;
+        if (!is_hit) {
+            accumulate(acc, pixel, make_float4(T.x * fp.bg[0], T.y * fp.bg[1], T.z * fp.bg[2], T.w * fp.bg[3]));
+        } else {
+            const float r = __uint_as_float(h.y), s = __uint_as_float(h.z), t = __uint_as_float(h.w);
+            const float dx = a.w, dy = b.x, dz = b.y;
+            const float px = a.x + r * dx, py = a.y + r * dy, pz = a.z + r * dz;
+            float lx = fp.light_pos[0] - px, ly = fp.light_pos[1] - py, lz = fp.light_pos[2] - pz;
+            const float linv = 1 / sqrtf(lx * lx + ly * ly + lz * lz);
+            lx = linv * lx; ly = linv * ly; lz = linv * lz;
+            const float4* srec = sc.shade + 4 * static_cast<size_t>(h.x);
+            const float4 s0 = __ldg(srec), s1 = __ldg(srec + 1), s2 = __ldg(srec + 2), rho = __ldg(srec + 3);
+            const float br = 1.f - s - t;
+            const float mx = (br * s0.x + s * s0.w) + t * s1.z;
+            const float my = (br * s0.y + s * s1.x) + t * s1.w;
+            const float mz = (br * s0.z + s * s1.y) + t * s2.x;
+            const float ninv = 1 / sqrtf(mx * mx + my * my + mz * mz);
+            const float nx = ninv * mx, ny = ninv * my, nz = ninv * mz;
+            // lambertian(L, N, C, I), lib/lambertian.h:15-19
+            const float ca = fmaxf(0.f, lx * nx + ly * ny + lz * nz);
+            const float4 direct = make_float4((ca * rho.x) * fp.light_rgba[0], (ca * rho.y) * fp.light_rgba[1],
+                                              (ca * rho.z) * fp.light_rgba[2], (ca * rho.w) * fp.light_rgba[3]);
+            p2x = px + 0.0001f * nx; p2y = py + 0.0001f * ny; p2z = pz + 0.0001f * nz;
+            const float k = s2.y;
+            float4 base = direct;
+            if (k > 0.f) { // raytracer.cpp:44-54
+                const float4 R = __ldg(sc.mirror + h.x);
+                const float two_nd = 2.f * (nx * dx + ny * dy + nz * dz);
+                rx = dx - two_nd * nx; ry = dy - two_nd * ny; rz = dz - two_nd * nz;
+                const float omk = 1.f - k;
+                base = make_float4(omk * direct.x, omk * direct.y, omk * direct.z, omk * direct.w);
+                Tc = make_float4(T.x * (k * R.x), T.y * (k * R.y), T.z * (k * R.z), T.w * (k * R.w));
+                spawn = depth < fp.max_depth;
+                cut = !spawn; // the reference still counts the call that the depth check rejects (raytracer.cpp:9-13)
+            }
+            contrib = make_float4(T.x * base.x, T.y * base.y, T.z * base.z, T.w * base.w);
+            float qx = fp.light_pos[0] - p2x, qy = fp.light_pos[1] - p2y, qz = fp.light_pos[2] - p2z; // :57-59
+            ldist = sqrtf(qx * qx + qy * qy + qz * qz);
+            const float qinv = 1 / ldist;
+            ldx = qinv * qx; ldy = qinv * qy; ldz = qinv * qz;
+        }
+    }
+    // children (compacted)
+    const unsigned cmask = __ballot_sync(0xffffffffu, spawn);
+    uint32_t cslot = 0xFFFFFFFFu;
+    if (cmask) {
+        uint32_t cbase = 0;
+        if (lane == 0) cbase = atomicAdd(&counters->next_count, __popc(cmask));
+        cbase = __shfl_sync(0xffffffffu, cbase, 0);
+        if (spawn) {
+            cslot = cbase + __popc(cmask & ((1u << lane) - 1u));
+            __stcs(&next.a[cslot], make_float4(p2x, p2y, p2z, rx));
+            __stcs(&next.b[cslot], make_float4(ry, rz, __uint_as_float(rel), __uint_as_float(0u)));
+            next.T[cslot] = Tc; // re-read (and possibly scaled) by the shadow kernel: keep it cacheable
+        }
+    }
+    const unsigned kmask = __ballot_sync(0xffffffffu, cut);
+    if (kmask && lane == 0) atomicAdd(cut_rays, static_cast<unsigned long long>(__popc(kmask)));
+    // shadow query of every hit (compacted)
+    const unsigned smask = __ballot_sync(0xffffffffu, is_hit);
+    if (smask) {
+        uint32_t sbase = 0;
+        if (lane == 0) sbase = atomicAdd(&counters->shadow_count, __popc(smask));
+        sbase = __shfl_sync(0xffffffffu, sbase, 0);
+        if (is_hit) {
+            const uint32_t slot = sbase + __popc(smask & ((1u << lane) - 1u));
+            // shadowed <=> closest hit strictly nearer than the light (raytracer.cpp:63): any-hit with r <= pred(dist)
+            const float tmax = ldist > 0.f ? __uint_as_float(__float_as_uint(ldist) - 1u) : -1.f;
+            __stcs(&shadow.a[slot], make_float4(p2x, p2y, p2z, ldx));
+            __stcs(&shadow.b[slot], make_float4(ldy, ldz, tmax, __uint_as_float(pixel)));
+            __stcs(&shadow.c[slot], contrib);
+            child_slot[slot] = cslot;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) trace_shadow_raytrace_kernel(DevScene sc, ShadowWave sw,
+                                                                    const uint32_t* __restrict__ child_slot,
+                                                                    const WaveCounters* __restrict__ counters,
+                                                                    float shadow_intensity, float4* __restrict__ nextT,
+                                                                    float4* __restrict__ acc) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= counters->shadow_count) return;
+    const float4 a = __ldcs(&sw.a[idx]);
+    const float4 b = __ldcs(&sw.b[idx]);
+    HitRec h;
+    const bool shadowed = traverse_pairs<true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, b.z, h);
+    float4 c = __ldcs(&sw.c[idx]);
+    const uint32_t cs = child_slot[idx];
+    if (shadowed) { // color -= color * shadow_intensity (raytracer.cpp:64-66), applied to both addends of color
+        c = make_float4(c.x - shadow_intensity * c.x, c.y - shadow_intensity * c.y, c.z - shadow_intensity * c.z, c.w - shadow_intensity * c.w);
+        if (cs != 0xFFFFFFFFu) {
+            const float4 t = nextT[cs];
+            nextT[cs] = make_float4(t.x - shadow_intensity * t.x, t.y - shadow_intensity * t.y, t.z - shadow_intensity * t.z,
+                                    t.w - shadow_intensity * t.w);
+        }
+    }
+    accumulate(acc, __float_as_uint(b.w), c);
 }
 
 __global__ void unpack_hits_kernel(const uint4* __restrict__ hits, uint32_t count, uint32_t* __restrict__ ids,

@@ -4,6 +4,8 @@ A scene is a dict:
   vertices [N,9] f32   world-space v0,v1,v2 per triangle (what main.cpp:53-55 produces)
   normals  [N,9] f32   per-vertex normals, un-normalised (main.cpp:57-59)
   diffuse  [N,4] f32   rgba of AI_MATKEY_COLOR_DIFFUSE (main.cpp:42)
+  reflective [N,4], reflectivity [N]  optional: AI_MATKEY_COLOR_REFLECTIVE / AI_MATKEY_REFLECTIVITY (main.cpp:44-47;
+                       only the raytracer integrator reads them)
   camera   {'trafo4x4': 16 floats row-major (assimp a1..d4), 'hfov': radians}
   light    {'pos': [3], 'color': [4]} or None
 
@@ -28,6 +30,8 @@ def load_json(path):
         "vertices": np.asarray(d["vertices"], dtype=np.float32).reshape(-1, 9),
         "normals": np.asarray(d["normals"], dtype=np.float32).reshape(-1, 9),
         "diffuse": np.asarray(d["diffuse"], dtype=np.float32).reshape(-1, 4),
+        "reflective": np.asarray(d.get("reflective", np.zeros((len(d["diffuse"]), 4))), dtype=np.float32).reshape(-1, 4),
+        "reflectivity": np.asarray(d.get("reflectivity", np.zeros(len(d["diffuse"]))), dtype=np.float32).reshape(-1),
         "camera": d["camera"],
         "light": d.get("light"),
     }
