@@ -118,7 +118,8 @@ def cpu_reference_run(name, sc, nodes, box, steps=1, warmup=0):
         kind = "reference"
         # the tree is loaded through the reference's own serialize() hook (what main.cpp:147-152 does with
         # kdtree.cache); it is node-for-node the tree its builder makes (tests/test_host.py), which takes ~60 s at 1M
-        r = ob.RefScene(sc["vertices"], sc["normals"], sc["diffuse"], nodes=nodes, box=box)
+        r = (ob.RefScene(sc["vertices"], sc["normals"], sc["diffuse"], nodes=nodes, box=box) if nodes is not None
+             else ob.RefScene(sc["vertices"], sc["normals"], sc["diffuse"]))
         cam = ob.ref_camera(sc)
         cfg = ob.ref_config(sc, W, w["max_depth"], w["mc_samples"], 1, num_threads=cores)
         for it in range(warmup + steps):
@@ -128,7 +129,8 @@ def cpu_reference_run(name, sc, nodes, box, steps=1, warmup=0):
                 t_total += st.runtime_ms / 1e3
     else:
         kind = "port"
-        o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"], nodes=nodes, box=box)
+        o = (ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"], nodes=nodes, box=box) if nodes is not None
+             else ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"]))
         cfg = ob.make_cfg(sc, W, w["max_depth"], w["mc_samples"], 1, num_threads=cores)
         for it in range(warmup + steps):
             _, _, st = o.render(cfg)
@@ -157,17 +159,14 @@ def main():
               "sample_split": "rank g renders sample (step*N+g) mod %d; one reduce(sum) of W*H*4 f32 at the end" % w["pixel_samples"],
               "l2": "flushed between steps (256 MiB memset inside the timed region)", "seed": 1}
 
-    from turner_b200 import api
-
     if args.impl == "reference":
         # the reference arm: rank 0 alone times the reference's CPU path; other ranks exit
         if rank != 0:
             return 0
         sc = load_scene(args.workload)
-        os.environ.setdefault("TRN_BUILD_THREADS", str(os.cpu_count() or 1))
-        scene = api.Scene.from_dict(sc)  # host kd build only (no GPU work): supplies the reference-identical tree
-        base = cpu_reference_run(args.workload, sc, scene.nodes(), np.array(scene.info.box, np.float32),
-                                 steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        # nothing of turner_b200 on this arm: the reference builds its own kd-tree with its own builder (~1 min at 1M
+        # triangles, untimed like "Loading time" in the reference's report) and renders with its own trace()
+        base = cpu_reference_run(args.workload, sc, None, None, steps=max(1, args.steps), warmup=min(args.warmup, 1))
         line = {"impl": "reference", "metric": "Mrays/s (incl. secondary)", "value": base["value"], "unit": "Mrays/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * base["seconds"] / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
@@ -180,7 +179,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from turner_b200 import dist as tdist
+    from turner_b200 import api, dist as tdist
 
     if api.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")

@@ -146,11 +146,11 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
 int32_t trn_render(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
                    float* out_rgba_sum, trn_stats* stats);
 
-/* Same, but ADDS into a caller-owned DEVICE buffer (width*height*4 floats on `device`) on the given CUDA stream
- * (cudaStream_t passed as void*; NULL = legacy default stream) and returns once the work is enqueued and the
- * host-side bookkeeping is done; the caller synchronises. For callers that own device memory / streams / a
- * process-per-GPU reduce (torch.distributed). stats->ms_render is then measured with events on that stream and
- * the call blocks on the last event only if `stats` is non-NULL. */
+/* Same, but ADDS into a caller-owned DEVICE buffer (width*height*4 floats on `device`), launching on the given CUDA
+ * stream (cudaStream_t passed as void*; NULL = legacy default stream). For callers that own device memory / streams /
+ * a process-per-GPU reduce (torch.distributed). The host drives the wavefront depth by depth (it reads each wave's size
+ * back), so the call returns when the last kernels are enqueued; it waits for them only if `stats` is non-NULL
+ * (ms_render is then measured with events on that stream). */
 int32_t trn_render_device(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
                           float* d_accum_rgba, void* cuda_stream, trn_stats* stats);
 

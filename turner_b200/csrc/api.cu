@@ -52,6 +52,14 @@ int fail(int code, const std::string& msg) {
                                           std::to_string(__LINE__) + ")");                                      \
     } while (0)
 
+// scoped device allocation (freed on every return path)
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
 // ------------------------------------------------------------ per-device state
 struct DeviceScene {
     int device = -1;
@@ -837,15 +845,16 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(ds->device));
     const uint64_t chunk = 8ull << 20;
-    float *d_o = nullptr, *d_d = nullptr, *d_rst = nullptr;
-    uint4* d_h = nullptr;
-    uint32_t* d_ids = nullptr;
     const uint64_t cn = std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1));
-    CUDA_TRY(cudaMalloc(&d_o, cn * 12));
-    CUDA_TRY(cudaMalloc(&d_d, cn * 12));
-    CUDA_TRY(cudaMalloc(&d_rst, cn * 12));
-    CUDA_TRY(cudaMalloc(&d_h, cn * 16));
-    CUDA_TRY(cudaMalloc(&d_ids, cn * 4));
+    DevBuf b_o, b_d, b_rst, b_h, b_ids;
+    CUDA_TRY(b_o.alloc(cn * 12));
+    CUDA_TRY(b_d.alloc(cn * 12));
+    CUDA_TRY(b_rst.alloc(cn * 12));
+    CUDA_TRY(b_h.alloc(cn * 16));
+    CUDA_TRY(b_ids.alloc(cn * 4));
+    float *d_o = b_o.as<float>(), *d_d = b_d.as<float>(), *d_rst = b_rst.as<float>();
+    uint4* d_h = b_h.as<uint4>();
+    uint32_t* d_ids = b_ids.as<uint32_t>();
     if (counts3) CUDA_TRY(cudaMemsetAsync(ds->d_visits, 0, 12 * sizeof(unsigned long long), ds->stream));
     for (uint64_t off = 0; off < n; off += chunk) {
         const uint32_t c = static_cast<uint32_t>(std::min<uint64_t>(chunk, n - off));
@@ -877,11 +886,6 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
         counts3[0] = v[0]; counts3[1] = v[1]; counts3[2] = v[2];
         counts3[3] = v[6]; counts3[4] = v[7]; counts3[5] = v[8];
     }
-    cudaFree(d_o);
-    cudaFree(d_d);
-    cudaFree(d_rst);
-    cudaFree(d_h);
-    cudaFree(d_ids);
     return TRN_OK;
 }
 
@@ -903,12 +907,13 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
     if (rc) return rc;
     rc = ensure_jitter(ds, cfg->width, cfg->pixel_samples);
     if (rc) return rc;
-    uint32_t* d_ids = nullptr;
-    float* d_rst = nullptr;
     const uint64_t total = static_cast<uint64_t>(fp.width) * fp.height * static_cast<uint64_t>(fp.n_local);
     const uint64_t cn = std::min<uint64_t>(cap, total);
-    CUDA_TRY(cudaMalloc(&d_ids, cn * 4));
-    CUDA_TRY(cudaMalloc(&d_rst, cn * 12));
+    DevBuf b_ids, b_rst;
+    CUDA_TRY(b_ids.alloc(cn * 4));
+    CUDA_TRY(b_rst.alloc(cn * 12));
+    uint32_t* d_ids = b_ids.as<uint32_t>();
+    float* d_rst = b_rst.as<float>();
     for (uint64_t first = 0; first < total; first += cap) {
         const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(cap, total - first));
         raygen_kernel<<<blocks_for(n, 256), 256, 0, ds->stream>>>(fp, ds->d_jitter, first, n, ds->waves[0]);
@@ -933,8 +938,6 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
         CUDA_TRY(cudaStreamSynchronize(ds->stream));
     }
     CUDA_TRY(cudaGetLastError());
-    cudaFree(d_ids);
-    cudaFree(d_rst);
     return TRN_OK;
 }
 

@@ -608,7 +608,9 @@ __global__ void __launch_bounds__(256) shade_bounce_kernel(DevScene sc, FramePar
         const float z = u1;
         const float rr = sqrtf(fmaxf(0.f, 1.f - z * z));
         const float phi = 6.28318530717958647692f * u2;
-        const float lx = rr * cosf(phi), ly = rr * sinf(phi), lz = z;
+        float sphi, cphi;
+        sincosf(phi, &sphi, &cphi); // one shared range reduction; same accuracy class as sinf/cosf (not the fast intrinsic)
+        const float lx = rr * cphi, ly = rr * sphi, lz = z;
         const float dx = m00 * lx + m01 * ly + m02 * lz;
         const float dy = m10 * lx + m11 * ly + m12 * lz;
         const float dz = m20 * lx + m21 * ly + m22 * lz;
