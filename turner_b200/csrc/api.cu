@@ -286,6 +286,10 @@ static int alloc_slot(DeviceScene* ds, cudaStream_t stream, uint32_t* out) {
     return TRN_OK;
 }
 
+// rays a warp of a persistent kernel reserves per atomicAdd on the work cursor
+static uint64_t env_u64(const char* name, uint64_t dflt);
+static inline uint32_t pool_chunk_for(const struct DeviceScene* ds, uint64_t n);
+
 static inline unsigned persistent_grid(int full, uint64_t n) {
     const uint64_t need = (n + 127) / 128;
     return static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(full), need)));
@@ -301,6 +305,14 @@ static int persistent_mode(bool shadow) {
     const char* v = std::getenv("TRN_PERSISTENT");
     if (v) return std::atoi(v);
     return shadow ? 0 : 2;
+}
+
+static inline uint32_t pool_chunk_for(const DeviceScene* ds, uint64_t n) {
+    (void)ds;
+    (void)n;
+    // measured (profiles/README.md): 32 beats 64 on the mesh, and 64 beats 188..512 on cornell_box's 16 M-ray waves --
+    // the cursor atomic is not a hot spot, a balanced tail is what matters
+    return static_cast<uint32_t>(env_u64("TRN_POOL_CHUNK", 32));
 }
 
 static uint64_t env_u64(const char* name, uint64_t dflt) {
@@ -523,7 +535,7 @@ struct Renderer {
             else if (mode_closest == 2)
                 TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), stream,
                     ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr,
-                    static_cast<int>(env_u64("TRN_REFILL", 28)), static_cast<int>(env_u64("TRN_QUANTA", 2)), order, ds->treelet_pairs);
+                    static_cast<int>(env_u64("TRN_REFILL", 28)), static_cast<int>(env_u64("TRN_QUANTA", 2)), order, ds->treelet_pairs, pool_chunk_for(ds, n));
             else if (mode_closest == 1)
                 trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, stream>>>(
                     ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr);
@@ -559,7 +571,7 @@ struct Renderer {
                     TRN_LAUNCH_WW(1, ds->two_pass, persistent_grid(ds->grid_shadow, n), stream,
                         ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
                         &ds->d_counters[cs].shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_REFILL", 26)),
-                        static_cast<int>(env_u64("TRN_QUANTA", 2)), nullptr, ds->treelet_pairs);
+                        static_cast<int>(env_u64("TRN_QUANTA", 2)), nullptr, ds->treelet_pairs, pool_chunk_for(ds, n));
                 else if (mode_shadow == 1)
                     trace_persistent_kernel<1><<<persistent_grid(ds->grid_shadow, n), 128, 0, stream>>>(
                         ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
@@ -589,7 +601,7 @@ struct Renderer {
         timer.begin(0);
         if (mode_closest == 2)
             TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), stream, ds->dev, wave.a, wave.b, nullptr, nullptr,
-                          nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2, nullptr, ds->treelet_pairs);
+                          nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2, nullptr, ds->treelet_pairs, pool_chunk_for(ds, n));
         else
             trace_closest_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, wave.a, wave.b, n, ds->d_hits);
         timer.end();
@@ -868,7 +880,7 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
             if (rc2) return rc2;
             if (persistent_mode(false) == 2)
                 TRN_LAUNCH_WW(2, ds->two_pass, persistent_grid(ds->grid_plain, c), ds->stream,
-                    ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr, 28, 2, nullptr, ds->treelet_pairs);
+                    ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr, 28, 2, nullptr, ds->treelet_pairs, pool_chunk_for(ds, c));
             else
                 trace_persistent_kernel<2><<<persistent_grid(ds->grid_plain, c), 128, 0, ds->stream>>>(
                     ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr);
@@ -924,7 +936,7 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
             if (persistent_mode(false) == 2)
                 TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), ds->stream,
                     ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr,
-                    &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2, nullptr, ds->treelet_pairs);
+                    &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2, nullptr, ds->treelet_pairs, pool_chunk_for(ds, n));
             else
                 trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, ds->stream>>>(
                     ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr,

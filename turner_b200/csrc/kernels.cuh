@@ -535,30 +535,43 @@ __global__ void __launch_bounds__(256) shade_bounce_kernel(DevScene sc, FramePar
         }
     }
 
-    // ---- compaction: shadow rays
-    const unsigned smask = __ballot_sync(0xffffffffu, want_shadow);
-    if (smask) {
-        uint32_t sbase = 0;
-        if (lane == 0) sbase = atomicAdd(&counters->shadow_count, __popc(smask));
-        sbase = __shfl_sync(0xffffffffu, sbase, 0);
-        if (want_shadow) {
-            const uint32_t slot = sbase + __popc(smask & ((1u << lane) - 1u));
-            __stcs(&shadow.a[slot], make_float4(p2x, p2y, p2z, ldx));
-            __stcs(&shadow.b[slot], make_float4(ldy, ldz, ldist, __uint_as_float(pixel)));
-            __stcs(&shadow.c[slot], contrib);
-        }
-    }
-
-    // ---- compaction: children
+    // ---- compaction: slots of the shadow rays and of the children in the next wave. Ballot/popc inside the warp, one
+    // shared-memory exchange per CTA, then ONE atomicAdd per queue per CTA (8x fewer same-address atomics than per warp:
+    // on one-leaf scenes the shade kernel runs 20 M warps per step and the queue counters serialise in L2).
     const bool spawn = is_hit && depth < fp.max_depth;
-    const unsigned hmask = __ballot_sync(0xffffffffu, spawn);
-    if (hmask == 0) return;
     const int m = fp.mc_samples;
+    const unsigned smask = __ballot_sync(0xffffffffu, want_shadow);
+    const unsigned hmask = __ballot_sync(0xffffffffu, spawn);
     const uint32_t nh = __popc(hmask);
-    uint32_t cbase = 0;
-    if (lane == 0) cbase = atomicAdd(&counters->next_count, nh * static_cast<uint32_t>(m));
-    cbase = __shfl_sync(0xffffffffu, cbase, 0);
+    __shared__ uint32_t s_shadow[8], s_child[8], s_base[2];
+    const unsigned warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_shadow[warp] = __popc(smask);
+        s_child[warp] = nh * static_cast<uint32_t>(m);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t ts = 0, tc = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t a_ = s_shadow[w], b_ = s_child[w];
+            s_shadow[w] = ts; // exclusive prefix inside the CTA
+            s_child[w] = tc;
+            ts += a_;
+            tc += b_;
+        }
+        s_base[0] = ts ? atomicAdd(&counters->shadow_count, ts) : 0u;
+        s_base[1] = tc ? atomicAdd(&counters->next_count, tc) : 0u;
+    }
+    __syncthreads();
+    if (want_shadow) {
+        const uint32_t slot = s_base[0] + s_shadow[warp] + __popc(smask & ((1u << lane) - 1u));
+        __stcs(&shadow.a[slot], make_float4(p2x, p2y, p2z, ldx));
+        __stcs(&shadow.b[slot], make_float4(ldy, ldz, ldist, __uint_as_float(pixel)));
+        __stcs(&shadow.c[slot], contrib);
+    }
     if (!spawn) return;
+    const uint32_t cbase = s_base[1] + s_child[warp];
     const uint32_t rank = __popc(hmask & ((1u << lane) - 1u));
 
     // aiMatrix3x3::FromToMatrix((0,0,1) -> normal), assimp matrix3x3.inl (Moeller-Hughes), pathtracer.cpp:68-70
@@ -749,30 +762,44 @@ __global__ void __launch_bounds__(256) shade_raytrace_kernel(DevScene sc, FrameP
             ldx = qinv * qx; ldy = qinv * qy; ldz = qinv * qz;
         }
     }
-    // children (compacted)
+    // slots for the mirror children and the shadow queries: warp ballot/popc, one atomicAdd per queue per CTA
     const unsigned cmask = __ballot_sync(0xffffffffu, spawn);
-    uint32_t cslot = 0xFFFFFFFFu;
-    if (cmask) {
-        uint32_t cbase = 0;
-        if (lane == 0) cbase = atomicAdd(&counters->next_count, __popc(cmask));
-        cbase = __shfl_sync(0xffffffffu, cbase, 0);
-        if (spawn) {
-            cslot = cbase + __popc(cmask & ((1u << lane) - 1u));
-            __stcs(&next.a[cslot], make_float4(p2x, p2y, p2z, rx));
-            __stcs(&next.b[cslot], make_float4(ry, rz, __uint_as_float(rel), __uint_as_float(0u)));
-            next.T[cslot] = Tc; // re-read (and possibly scaled) by the shadow kernel: keep it cacheable
-        }
-    }
     const unsigned kmask = __ballot_sync(0xffffffffu, cut);
-    if (kmask && lane == 0) atomicAdd(cut_rays, static_cast<unsigned long long>(__popc(kmask)));
-    // shadow query of every hit (compacted)
     const unsigned smask = __ballot_sync(0xffffffffu, is_hit);
-    if (smask) {
-        uint32_t sbase = 0;
-        if (lane == 0) sbase = atomicAdd(&counters->shadow_count, __popc(smask));
-        sbase = __shfl_sync(0xffffffffu, sbase, 0);
+    __shared__ uint32_t s_child[8], s_shadow[8], s_cut[8], s_base[2];
+    const unsigned warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_child[warp] = __popc(cmask);
+        s_shadow[warp] = __popc(smask);
+        s_cut[warp] = __popc(kmask);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tc = 0, ts = 0, tk = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t c_ = s_child[w], s_ = s_shadow[w];
+            s_child[w] = tc;
+            s_shadow[w] = ts;
+            tc += c_;
+            ts += s_;
+            tk += s_cut[w];
+        }
+        s_base[0] = tc ? atomicAdd(&counters->next_count, tc) : 0u;
+        s_base[1] = ts ? atomicAdd(&counters->shadow_count, ts) : 0u;
+        if (tk) atomicAdd(cut_rays, static_cast<unsigned long long>(tk));
+    }
+    __syncthreads();
+    uint32_t cslot = 0xFFFFFFFFu;
+    if (spawn) {
+        cslot = s_base[0] + s_child[warp] + __popc(cmask & ((1u << lane) - 1u));
+        __stcs(&next.a[cslot], make_float4(p2x, p2y, p2z, rx));
+        __stcs(&next.b[cslot], make_float4(ry, rz, __uint_as_float(rel), __uint_as_float(0u)));
+        next.T[cslot] = Tc; // re-read (and possibly scaled) by the shadow kernel: keep it cacheable
+    }
+    {
         if (is_hit) {
-            const uint32_t slot = sbase + __popc(smask & ((1u << lane) - 1u));
+            const uint32_t slot = s_base[1] + s_shadow[warp] + __popc(smask & ((1u << lane) - 1u));
             // shadowed <=> closest hit strictly nearer than the light (raytracer.cpp:63): any-hit with r <= pred(dist)
             const float tmax = ldist > 0.f ? __uint_as_float(__float_as_uint(ldist) - 1u) : -1.f;
             __stcs(&shadow.a[slot], make_float4(p2x, p2y, p2z, ldx));

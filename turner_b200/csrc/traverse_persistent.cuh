@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_ker
                                                                   const uint32_t* __restrict__ count_ptr,
                                                                   uint32_t* __restrict__ cursor, uint4* __restrict__ hits,
                                                                   float4* __restrict__ acc, int refill_below, int quanta,
-                                                                  const uint32_t* __restrict__ order, uint32_t treelet_pairs) {
+                                                                  const uint32_t* __restrict__ order, uint32_t treelet_pairs,
+                                                                  uint32_t pool_chunk) {
     constexpr bool ANY = MODE == 1;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -313,13 +314,13 @@ __global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_ker
         if (nbusy < refill_below && !exhausted) {
             if (pool_next == pool_end) {
                 uint32_t b = 0;
-                if (lane == 0) b = atomicAdd(cursor, kPoolChunk);
+                if (lane == 0) b = atomicAdd(cursor, pool_chunk);
                 b = __shfl_sync(0xffffffffu, b, 0);
                 if (b >= count) {
                     exhausted = true;
                 } else {
                     pool_next = b;
-                    pool_end = min(b + kPoolChunk, count);
+                    pool_end = min(b + pool_chunk, count);
                 }
             }
             if (!exhausted) {
