@@ -357,3 +357,37 @@ def test_raytracer_integrator_vs_oracle(api, ob, scenes):
     cam, cfg = api.make_config(fs, 16, integrator=api.RAYTRACER)
     with pytest.raises(api.TurnerError):
         pf.render(cam, cfg)
+
+
+def test_adversarial_axis_aligned_tiles(api, ob, scenes):
+    # walls tiled with quads whose edges lie exactly on kd split planes; rays from inside, many exactly through tile
+    # corners / along tile edges / axis-parallel: ids must still equal the reference's exhaustive traversal
+    for n in (4, 16):
+        sc = scenes.tiled_box(n)
+        o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+        p = api.Scene.from_dict(sc)
+        rng = np.random.RandomState(n)
+        m = 200000
+        org = rng.uniform(0.05, 0.95, (m, 3)).astype(np.float32)
+        d = rng.normal(size=(m, 3)).astype(np.float32)
+        # a quarter of the rays aim exactly at tile corners, a quarter are snapped to multiples of 1/8 (edge walkers)
+        k = m // 4
+        corner = rng.randint(0, n + 1, (k, 3)).astype(np.float32) / n
+        face = rng.randint(0, 3, k)
+        corner[np.arange(k), face] = rng.randint(0, 2, k)
+        d[:k] = corner - org[:k]
+        d[k:2 * k] = np.round(d[k:2 * k] * 4) / 8
+        org[k:2 * k] = np.round(org[k:2 * k] * 8) / 8
+        i_o, r_o = o.intersect(org, d, 0)
+        i_g, r_g = p.intersect(org, d)
+        # the generic half of the rays: bit-exact
+        assert np.array_equal(i_g[2 * k:], i_o[2 * k:]) and np.array_equal(bits(r_g[2 * k:]), bits(r_o[2 * k:]))
+        # corner / edge walkers: the hit distance is always the reference's; which of several triangles meeting in that
+        # point reports it (an EXACT tie in r, resolved by visiting order in the reference) may differ because the device
+        # layout skips cells the reference happens to walk through -- excepted by the spec, counted here
+        bad = i_g != i_o
+        assert np.array_equal(bits(r_g[:, 0]), bits(r_o[:, 0])), "a hit distance differs: not a tie"
+        assert not ((i_g == api.MISS_ID) ^ (i_o == ob.MISS)).any(), "hit/miss decision differs"
+        ties = int(bad.sum())
+        print("tiled_box n=%d: %d exact-tie id differences in %d adversarial rays" % (n, ties, 2 * k))
+        assert ties < 0.06 * 2 * k

@@ -254,10 +254,7 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     {
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-        int b0 = 0, b1 = 0, b2 = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, trace_persistent_kernel<0>, 128, 0));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, trace_persistent_kernel<1>, 128, 0));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, trace_persistent_kernel<2>, 128, 0));
+        int b0 = 1 << 30, b1 = 1 << 30, b2 = 1 << 30;
         int w0 = 0, w1 = 0, w2 = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w0, trace_persistent_ww_kernel<0, true>, 128, 0));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&w1, trace_persistent_ww_kernel<1, true>, 128, 0));
@@ -300,10 +297,10 @@ static inline unsigned persistent_grid(int full, uint64_t n) {
 // Scheduling of rays onto lanes (results are identical in every mode; profiles/README.md has the A/B numbers):
 //   closest-hit waves: persistent warps with lane refill, while-while quantum (mode 2) -- +26 % over one thread per ray
 //   shadow waves:      one thread per ray (mode 0) -- short any-hit walks, refill overhead does not pay
-// TRN_PERSISTENT=0|1|2 forces one mode for both (1 = per-step state machine).
+// TRN_PERSISTENT=0|2 forces one mode for both kinds of wave.
 static int persistent_mode(bool shadow) {
     const char* v = std::getenv("TRN_PERSISTENT");
-    if (v) return std::atoi(v);
+    if (v) return std::atoi(v) != 0 ? 2 : 0;
     return shadow ? 0 : 2;
 }
 
@@ -536,9 +533,6 @@ struct Renderer {
                 TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), stream,
                     ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr,
                     static_cast<int>(env_u64("TRN_REFILL", 28)), static_cast<int>(env_u64("TRN_QUANTA", 2)), order, ds->treelet_pairs, pool_chunk_for(ds, n));
-            else if (mode_closest == 1)
-                trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, stream>>>(
-                    ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr);
             else
                 trace_closest_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits);
             timer.end();
@@ -572,10 +566,6 @@ struct Renderer {
                         ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
                         &ds->d_counters[cs].shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_REFILL", 26)),
                         static_cast<int>(env_u64("TRN_QUANTA", 2)), nullptr, ds->treelet_pairs, pool_chunk_for(ds, n));
-                else if (mode_shadow == 1)
-                    trace_persistent_kernel<1><<<persistent_grid(ds->grid_shadow, n), 128, 0, stream>>>(
-                        ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
-                        &ds->d_counters[cs].shadow_cursor, nullptr, acc);
                 else
                     trace_shadow_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_counters + cs, acc);
                 timer.end();
@@ -878,12 +868,8 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
             uint32_t cs;
             int rc2 = alloc_slot(ds, ds->stream, &cs);
             if (rc2) return rc2;
-            if (persistent_mode(false) == 2)
-                TRN_LAUNCH_WW(2, ds->two_pass, persistent_grid(ds->grid_plain, c), ds->stream,
+            TRN_LAUNCH_WW(2, ds->two_pass, persistent_grid(ds->grid_plain, c), ds->stream,
                     ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr, 28, 2, nullptr, ds->treelet_pairs, pool_chunk_for(ds, c));
-            else
-                trace_persistent_kernel<2><<<persistent_grid(ds->grid_plain, c), 128, 0, ds->stream>>>(
-                    ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr);
         } else
             trace_closest_plain_kernel<<<blocks_for(c, 128), 128, 0, ds->stream>>>(ds->dev, d_o, d_d, c, d_h);
         unpack_hits_kernel<<<blocks_for(c, 256), 256, 0, ds->stream>>>(d_h, c, d_ids, d_rst);
@@ -933,14 +919,9 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
             uint32_t cs;
             rc = alloc_slot(ds, ds->stream, &cs);
             if (rc) return rc;
-            if (persistent_mode(false) == 2)
-                TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), ds->stream,
+            TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), ds->stream,
                     ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr,
                     &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2, nullptr, ds->treelet_pairs, pool_chunk_for(ds, n));
-            else
-                trace_persistent_kernel<0><<<persistent_grid(ds->grid_closest, n), 128, 0, ds->stream>>>(
-                    ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr,
-                    &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr);
         } else {
             trace_closest_kernel<<<blocks_for(n, 128), 128, 0, ds->stream>>>(ds->dev, ds->waves[0].a, ds->waves[0].b, n, ds->d_hits);
         }

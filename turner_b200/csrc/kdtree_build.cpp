@@ -284,6 +284,8 @@ inline BuildNode* skip_cuts(BuildNode* n) {
 
 // Sibling-pair device layout, cuts included (see kdtree_build.h).
 void flatten_pairs(BuildNode* root, KdTree& out) {
+    float scale = 0.f;
+    for (int c = 0; c < 6; ++c) scale = std::fmax(scale, std::fabs(out.box[c]));
     auto& nodes = out.pair_nodes;
     auto& refs = out.pair_leaf_refs;
     nodes.assign(2, 0);
@@ -302,7 +304,15 @@ void flatten_pairs(BuildNode* root, KdTree& out) {
             const uint32_t pair = static_cast<uint32_t>(nodes.size());
             nodes.push_back(0);
             nodes.push_back(0);
-            nodes[it.slot] = (static_cast<uint64_t>((pair << 2) | static_cast<uint32_t>(n->axis)) << 32) | float_bits(n->split);
+            float split = n->split;
+            if (n->cut) {
+                // A cut plane exists only in this layout (the reference walks on into the surviving child with the
+                // parent's interval). Move it a few ulp of the scene scale INTO the void, so that a ray whose interval
+                // ends or starts within rounding noise of the plane still visits the solid side.
+                const float shift = 4e-6f * std::fmax(std::fabs(split), scale);
+                split += n->left ? shift : -shift; // solid left: void is above the plane, and vice versa
+            }
+            nodes[it.slot] = (static_cast<uint64_t>((pair << 2) | static_cast<uint32_t>(n->axis)) << 32) | float_bits(split);
             children.push_back({n->left, pair});
             children.push_back({n->right, pair + 1});
         } else {

@@ -255,7 +255,11 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
     out.s = 0.f;
     out.t = 0.f;
     if (texit < tenter) return false;
-    if (tenter < 0.f) tenter = 0.f;
+    // Rays with an exact-zero direction component are traversed with the "fixed" direction of lib/kdtree.cpp:503-511 but
+    // tested with the real one: their interval is not the real ray's, and what the reference finds depends on every cell
+    // it happens to visit. They take the reference's schedule verbatim: negative tenter, solid side of every cut, no
+    // early exit, no per-cell hit range.
+    if (tenter < 0.f && !axis_parallel) tenter = 0.f;
 
     uint4 stack[kStackDepth]; // (node.x, node.y, tmin, tmax)
     int sp = 0;
@@ -270,25 +274,24 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
             const float o_ax = sel3(ax, ox, oy, oz);
             const float i_ax = sel3(ax, ix, iy, iz);
             const float t = (split - o_ax) * i_ax;
+            if (axis_parallel && (pair.y == 3u || pair.w == 3u)) { // cut node: the reference has no plane here
+                n = pair.y == 3u ? make_uint2(pair.z, pair.w) : make_uint2(pair.x, pair.y);
+                continue;
+            }
             // left is near unless fixed_ray.d[ax] <= 0 (lib/kdtree.cpp:549-553); sign(d) == sign(1/d), d != 0
             const bool flip = (__float_as_uint(i_ax) >> 31) != 0u;
             const uint2 near = flip ? make_uint2(pair.z, pair.w) : make_uint2(pair.x, pair.y);
             const uint2 far = flip ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
-            if (texit < t) {
-                n = near;
-            } else if (t < tenter) {
-                n = far;
-            } else if (far.y == 3u) { // far side is a cut-off void: nothing to come back for
-                n = near;
-                texit = t;
-            } else if (near.y == 3u) { // near side is a void: go straight to the far side
-                n = far;
-                tenter = t;
-            } else {
-                stack[sp++] = make_uint4(far.x, far.y, __float_as_uint(t), __float_as_uint(texit));
-                n = near;
-                texit = t;
-            }
+            // lib/kdtree.cpp:555-563 without divergent branches: near only | far only | both (far pushed); cut-off voids
+            // (count-0 leaves, y == 3) are neither entered nor pushed
+            const bool near_only = texit < t;
+            const bool far_only = !near_only && (t < tenter);
+            const bool both = !near_only && !far_only;
+            const bool go_far = far_only || (both && near.y == 3u);
+            if (both && near.y != 3u && far.y != 3u) stack[sp++] = make_uint4(far.x, far.y, __float_as_uint(t), __float_as_uint(texit));
+            n = go_far ? far : near;
+            tenter = (both && go_far) ? t : tenter;
+            texit = (both && !go_far) ? t : texit;
         }
 
         const uint32_t first = n.x, count = n.y >> 2;
@@ -330,13 +333,13 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
             if (ANY_HIT) return true;
         }
 
-        if (out.id != kMiss && out.r <= texit) break;
+        if (!axis_parallel && out.id != kMiss && out.r <= texit) break;
         if (sp == 0) break;
         const uint4 e = stack[--sp];
         n = make_uint2(e.x, e.y);
         tenter = __uint_as_float(e.z);
         texit = __uint_as_float(e.w);
-        if (ANY_HIT && tenter > tmax_any) break;
+        if (ANY_HIT && !axis_parallel && tenter > tmax_any) break;
     }
     return out.id != kMiss;
 }

@@ -29,215 +29,6 @@ constexpr uint32_t kPoolChunk = 64;   // rays a warp reserves per global atomic 
 // MODE 0: closest hit, rays from a RayWave (a,b); result -> hits[idx]
 // MODE 1: any-hit shadow rays from a ShadowWave (a,b,c); unoccluded -> acc[pixel] += c
 // MODE 2: closest hit, rays from plain (o,d) float arrays; result -> hits[idx]
-template <int MODE>
-__global__ void __launch_bounds__(128) trace_persistent_kernel(DevScene sc, const float4* __restrict__ ra,
-                                                               const float4* __restrict__ rb,
-                                                               const float4* __restrict__ rc, const float* __restrict__ po,
-                                                               const float* __restrict__ pd, uint32_t count_arg,
-                                                               const uint32_t* __restrict__ count_ptr,
-                                                               uint32_t* __restrict__ cursor, uint4* __restrict__ hits,
-                                                               float4* __restrict__ acc) {
-    constexpr bool ANY = MODE == 1;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const uint32_t count = count_ptr ? *count_ptr : count_arg;
-
-    uint4 stack[kStackDepth]; // (node.x, node.y, tmin, tmax), local memory
-    int sp = 0;
-
-    // lane state
-    float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0;
-    float tenter = 0, texit = 0, tmax_any = 0;
-    uint2 n = make_uint2(0u, 3u);     // current node word
-    uint32_t tri_i = 0, tri_end = 0;  // pending triangle tests of the current leaf: refs[tri_i .. tri_end)
-    uint32_t next_id = 0;             // refs[tri_i], fetched one step ahead
-    uint32_t best_id = kMiss, idx = 0;
-    float best_r = kFltMax, best_s = 0.f, best_t = 0.f;
-    bool busy = false;
-
-    bool exhausted = false;               // warp-uniform
-    uint32_t pool_next = 0, pool_end = 0; // warp-uniform
-
-    for (;;) {
-        // ------------------------------------------------------------------ refill
-        int nbusy = __popc(__ballot_sync(0xffffffffu, busy));
-        if (nbusy < kRefillBelow && !exhausted) {
-            if (pool_next == pool_end) {
-                uint32_t b = 0;
-                if (lane == 0) b = atomicAdd(cursor, kPoolChunk);
-                b = __shfl_sync(0xffffffffu, b, 0);
-                if (b >= count) {
-                    exhausted = true;
-                } else {
-                    pool_next = b;
-                    pool_end = min(b + kPoolChunk, count);
-                }
-            }
-            if (!exhausted) {
-                const unsigned need = __ballot_sync(0xffffffffu, !busy);
-                const uint32_t take = min(static_cast<uint32_t>(__popc(need)), pool_end - pool_next);
-                const uint32_t rank = __popc(need & lt_mask);
-                if (!busy && rank < take) {
-                    idx = pool_next + rank;
-                    if (MODE == 2) {
-                        ox = po[3 * idx]; oy = po[3 * idx + 1]; oz = po[3 * idx + 2];
-                        dx = pd[3 * idx]; dy = pd[3 * idx + 1]; dz = pd[3 * idx + 2];
-                    } else {
-                        const float4 a = __ldcs(&ra[idx]);
-                        const float4 b = __ldcs(&rb[idx]);
-                        ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
-                        if (ANY) tmax_any = b.z;
-                    }
-                    // fix_direction + intersect_ray_box, lib/kdtree.cpp:503-511, lib/intersection.h:105-128
-                    const float fdx = dx == 0.f ? kEpsDir : dx;
-                    const float fdy = dy == 0.f ? kEpsDir : dy;
-                    const float fdz = dz == 0.f ? kEpsDir : dz;
-                    ix = 1 / fdx;
-                    iy = 1 / fdy;
-                    iz = 1 / fdz;
-                    float tx1 = (sc.lo[0] - ox) * ix, tx2 = (sc.hi[0] - ox) * ix;
-                    float t0 = fminf(tx1, tx2), t1 = fmaxf(tx1, tx2);
-                    float ty1 = (sc.lo[1] - oy) * iy, ty2 = (sc.hi[1] - oy) * iy;
-                    t0 = fmaxf(t0, fminf(ty1, ty2));
-                    t1 = fminf(t1, fmaxf(ty1, ty2));
-                    float tz1 = (sc.lo[2] - oz) * iz, tz2 = (sc.hi[2] - oz) * iz;
-                    t0 = fmaxf(t0, fminf(tz1, tz2));
-                    t1 = fminf(t1, fmaxf(tz1, tz2));
-                    best_id = kMiss;
-                    best_r = kFltMax;
-                    best_s = 0.f;
-                    best_t = 0.f;
-                    if (t1 < t0) { // misses the scene box: done on the spot
-                        if (ANY) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx]));
-                        else __stcs(&hits[idx], make_uint4(kMiss, __float_as_uint(kFltMax), 0u, 0u));
-                    } else {
-                        tenter = t0 < 0.f ? 0.f : t0;
-                        texit = t1;
-                        sp = 0;
-                        n = __ldg(&sc.pnodes[0]);
-                        tri_i = tri_end = 0;
-                        if ((n.y & 3u) == 3u) { // the root is a leaf (kd height 0, e.g. cornell_box)
-                            tri_i = n.x;
-                            tri_end = n.x + (n.y >> 2);
-                            next_id = __ldg(&sc.prefs[tri_i]);
-                        }
-                        busy = true;
-                    }
-                }
-                pool_next += take;
-            }
-            nbusy = __popc(__ballot_sync(0xffffffffu, busy));
-        }
-        if (nbusy == 0) {
-            if (exhausted) break;
-            continue; // everything fetched so far missed the box: fetch again
-        }
-
-        // ------------------------------------------------------------------ steps
-#pragma unroll 1
-        for (int step = 0; step < kStepsPerCheck; ++step) {
-            if (!busy) continue;
-            bool leaf_done = false;
-            if (tri_i < tri_end) {
-                // ---- one triangle test (lib/intersection.h:40-49,63-89; strict '<' keeps the first-visited on ties)
-                const uint32_t id = next_id;
-                ++tri_i;
-                if (tri_i < tri_end) next_id = __ldg(&sc.prefs[tri_i]);
-                const float4* rec = sc.isect_hot + 2 * static_cast<size_t>(id);
-                const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
-                const float nx = q0.w, ny = q1.x, nz = q1.y;
-                const float denom = nx * dx + ny * dy + nz * dz;
-                bool accept = false;
-                float r = 0.f, s = 0.f, t = 0.f;
-                if (denom != 0.f) {
-                    const float nom = nx * (q0.x - ox) + ny * (q0.y - oy) + nz * (q0.z - oz);
-                    r = nom / denom;
-                    const bool axis_parallel = dx == 0.f || dy == 0.f || dz == 0.f; // see traverse_pairs<>
-                    if (r >= 0.f && (ANY ? (r <= tmax_any) : (r < best_r)) &&
-                        (axis_parallel || (r >= tenter - kCellSlack * (fabsf(tenter) + 1.f) &&
-                                           r <= texit + kCellSlack * (fabsf(texit) + 1.f)))) {
-                        const float4* rec2 = sc.isect_cold + 2 * static_cast<size_t>(id);
-                        const float4 q2 = __ldg(rec2), q3 = __ldg(rec2 + 1);
-                        const float wx = (ox + r * dx) - q0.x, wy = (oy + r * dy) - q0.y, wz = (oz + r * dz) - q0.z;
-                        const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
-                        const float wv = wx * vx + wy * vy + wz * vz;
-                        const float wu = wx * ux + wy * uy + wz * uz;
-                        s = (q3.x * wv - q3.y * wu) / q3.w;
-                        if (!(s < 0.f)) {
-                            t = (q3.x * wu - q3.z * wv) / q3.w;
-                            accept = !(t < 0.f || 1.f < s + t);
-                        }
-                    }
-                }
-                if (accept) {
-                    best_id = id;
-                    best_r = r;
-                    best_s = s;
-                    best_t = t;
-                    if (ANY) {
-                        busy = false; // occluded: nothing to add
-                        continue;
-                    }
-                }
-                leaf_done = tri_i == tri_end;
-            } else {
-                // ---- one inner-node step (lib/kdtree.cpp:540-564) on the sibling-pair layout
-                const int ax = static_cast<int>(n.y & 3u);
-                const float split = __uint_as_float(n.x);
-                const uint4 pair = __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
-                const float o_ax = sel3(ax, ox, oy, oz);
-                const float i_ax = sel3(ax, ix, iy, iz);
-                const float t = (split - o_ax) * i_ax;
-                const bool flip = (__float_as_uint(i_ax) >> 31) != 0u;
-                const uint2 near = flip ? make_uint2(pair.z, pair.w) : make_uint2(pair.x, pair.y);
-                const uint2 far = flip ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
-                if (texit < t) {
-                    n = near;
-                } else if (t < tenter) {
-                    n = far;
-                } else if (far.y == 3u) {
-                    n = near;
-                    texit = t;
-                } else if (near.y == 3u) {
-                    n = far;
-                    tenter = t;
-                } else {
-                    stack[sp++] = make_uint4(far.x, far.y, __float_as_uint(t), __float_as_uint(texit));
-                    n = near;
-                    texit = t;
-                }
-                if ((n.y & 3u) == 3u) {
-                    tri_i = n.x;
-                    tri_end = n.x + (n.y >> 2);
-                    if (tri_i < tri_end) next_id = __ldg(&sc.prefs[tri_i]);
-                    else leaf_done = true; // walked into a cut-off void
-                }
-            }
-            if (leaf_done) {
-                // end of a leaf: stop if the best hit lies in this cell, else continue with the nearest pending cell
-                bool finished = (best_id != kMiss && best_r <= texit) || sp == 0;
-                if (!finished) {
-                    const uint4 e = stack[--sp];
-                    n = make_uint2(e.x, e.y);
-                    tenter = __uint_as_float(e.z);
-                    texit = __uint_as_float(e.w);
-                    if (ANY && tenter > tmax_any) finished = true;
-                    else if ((n.y & 3u) == 3u) {
-                        tri_i = n.x;
-                        tri_end = n.x + (n.y >> 2);
-                        next_id = __ldg(&sc.prefs[tri_i]); // pushed nodes are never voids
-                    }
-                }
-                if (finished) {
-                    busy = false;
-                    if (ANY) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx])); // reached the end unoccluded
-                    else __stcs(&hits[idx], make_uint4(best_id, __float_as_uint(best_r), __float_as_uint(best_s), __float_as_uint(best_t)));
-                }
-            }
-        }
-    }
-}
-
 
 // Barycentric part of intersect_ray_triangle (lib/intersection.h:70-86) for a triangle whose plane distance r already
 // passed 0 <= r; re-checks r < best (strict: the first-visited triangle keeps a tie). Returns true only in ANY mode
@@ -305,7 +96,7 @@ __global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_ker
     uint2 n = make_uint2(0u, 3u);
     uint32_t best_id = kMiss, idx = 0;
     float best_r = kFltMax, best_s = 0.f, best_t = 0.f;
-    bool busy = false;
+    bool busy = false, axis_parallel = false;
     bool exhausted = false;
     uint32_t pool_next = 0, pool_end = 0;
 
@@ -361,7 +152,8 @@ __global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_ker
                         if (ANY) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx]));
                         else __stcs(&hits[idx], make_uint4(kMiss, __float_as_uint(kFltMax), 0u, 0u));
                     } else {
-                        tenter = t0 < 0.f ? 0.f : t0;
+                        axis_parallel = dx == 0.f || dy == 0.f || dz == 0.f; // reference schedule verbatim, see traverse_pairs<>
+                        tenter = (t0 < 0.f && !axis_parallel) ? 0.f : t0;
                         texit = t1;
                         sp = 0;
                         n = __ldg(&sc.pnodes[0]);
@@ -393,6 +185,10 @@ __global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_ker
                 const float o_ax = sel3(ax, ox, oy, oz);
                 const float i_ax = sel3(ax, ix, iy, iz);
                 const float t = (split - o_ax) * i_ax;
+                if (axis_parallel && (pair.y == 3u || pair.w == 3u)) { // cut node: the reference has no plane here
+                    n = pair.y == 3u ? make_uint2(pair.z, pair.w) : make_uint2(pair.x, pair.y);
+                    continue;
+                }
                 const bool flip = (__float_as_uint(i_ax) >> 31) != 0u;
                 const uint2 near = flip ? make_uint2(pair.z, pair.w) : make_uint2(pair.x, pair.y);
                 const uint2 far = flip ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
@@ -409,7 +205,6 @@ __global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_ker
             }
             const uint32_t first = n.x, cnt = n.y >> 2;
             bool occluded = false;
-            const bool axis_parallel = dx == 0.f || dy == 0.f || dz == 0.f; // see traverse_pairs<>
             const float r_lo = axis_parallel ? -kFltMax : tenter - kCellSlack * (fabsf(tenter) + 1.f);
             const float r_hi = axis_parallel ? kFltMax : texit + kCellSlack * (fabsf(texit) + 1.f);
             // Two passes over the leaf so that the lanes of the warp stay together: first the plane test of every
@@ -461,13 +256,13 @@ __global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_ker
                 if (!(r >= r_lo && r <= r_hi)) continue;
                 if (test_candidate<ANY>(sc, id, r, ox, oy, oz, dx, dy, dz, best_id, best_r, best_s, best_t)) occluded = true;
             }
-            bool finished = occluded || (best_id != kMiss && best_r <= texit) || sp == 0;
+            bool finished = occluded || (!axis_parallel && best_id != kMiss && best_r <= texit) || sp == 0;
             if (!finished) {
                 const uint4 e = stack[--sp];
                 n = make_uint2(e.x, e.y);
                 tenter = __uint_as_float(e.z);
                 texit = __uint_as_float(e.w);
-                if (ANY && tenter > tmax_any) finished = true;
+                if (ANY && !axis_parallel && tenter > tmax_any) finished = true;
             }
             if (finished) {
                 busy = false;

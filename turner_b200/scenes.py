@@ -163,3 +163,29 @@ def random_rays(scene, n, seed=0, inside=False):
 
 def math_pi():
     return math.pi
+
+
+def tiled_box(n=8, size=1.0):
+    """closed axis-aligned box whose six walls are n x n quads (12 n^2 triangles): every triangle is planar in one axis
+    and its edges coincide with candidate split planes -- the adversarial case for anything that reasons about cells"""
+    t = np.linspace(0.0, size, n + 1)
+    V = []
+    for ax in range(3):
+        for side in (0.0, size):
+            for i in range(n):
+                for j in range(n):
+                    q = []
+                    for (a, b) in ((t[i], t[j]), (t[i + 1], t[j]), (t[i + 1], t[j + 1]), (t[i], t[j + 1])):
+                        p = [0.0, 0.0, 0.0]
+                        p[ax] = side
+                        p[(ax + 1) % 3] = a
+                        p[(ax + 2) % 3] = b
+                        q.append(p)
+                    V.append(q[0] + q[1] + q[2])
+                    V.append(q[0] + q[2] + q[3])
+    V = np.asarray(V, np.float32)
+    N = np.zeros_like(V)
+    D = np.tile(np.asarray([0.7, 0.7, 0.7, 1.0], np.float32), (V.shape[0], 1))
+    return {"name": "tiled_box_%d" % n, "vertices": V, "normals": N, "diffuse": D,
+            "camera": look_at_camera((size / 2, size / 2, size * 0.9), (size / 2, size / 2, 0)),
+            "light": {"pos": [size / 2, size * 0.9, size / 2], "color": [1.0, 1.0, 1.0, 1.0]}}
