@@ -332,6 +332,12 @@ def main():
                           * tot["shadow"] / max(tot["ms_shadow"], 1e-9) / 1e6},
         "fp32_tri_test_rate_gflops": 37.0 * (cnt["tri"] / max(cnt["q"], 1)) * tot["trace_queries"] / max(tot["ms_trace"], 1e-9) / 1e6,
     }
+    # FP32 intersection-test rate against the FP32 FMA peak (148 SMs x 128 lanes x 2 flop x SM clock under load); the
+    # tests run WITHOUT FMA contraction (bit-exactness), so 50 % is the ceiling of this ratio
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    roofline["fp32_peak_gflops"] = 148 * 128 * 2 * sm_mhz / 1e3
+    roofline["fp32_frac"] = roofline["fp32_tri_test_rate_gflops"] / roofline["fp32_peak_gflops"]
+    roofline["fp32_clock_mhz"] = sm_mhz
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

@@ -54,4 +54,7 @@ FLAGS="-std=c++14 -O2 -DNDEBUG -ffp-contract=off -fPIC -shared -pthread -w -s -n
 $CXX $FLAGS "$TMP/lib/kdtree.cpp" "$TMP/pathtracer.cpp" "$HERE/ref_driver.cpp" -l:libstdc++.so.6 -o "$OUT/libturner_ref_pathtracer.so"
 $CXX $FLAGS "$TMP/lib/kdtree.cpp" "$TMP/raycaster.cpp" "$HERE/ref_driver.cpp" -l:libstdc++.so.6 -o "$OUT/libturner_ref_raycaster.so"
 $CXX $FLAGS "$TMP/lib/kdtree.cpp" "$TMP/raytracer.cpp" "$HERE/ref_driver.cpp" -l:libstdc++.so.6 -o "$OUT/libturner_ref_raytracer.so"
+# the as-shipped flags (CMakeLists.txt:3-7: no -O, asserts on), for comparability with README.md:22-36's 129 k rays/s
+FLAGS_SHIPPED="-std=c++14 -fPIC -shared -pthread -w -s -nostdlib++ -I$HERE/ref_shims -I$TMP"
+$CXX $FLAGS_SHIPPED "$TMP/lib/kdtree.cpp" "$TMP/pathtracer.cpp" "$HERE/ref_driver.cpp" -l:libstdc++.so.6 -o "$OUT/libturner_ref_pathtracer_shipped.so"
 echo "built $OUT/libturner_ref_pathtracer.so $OUT/libturner_ref_raycaster.so"

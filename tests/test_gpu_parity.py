@@ -391,3 +391,26 @@ def test_adversarial_axis_aligned_tiles(api, ob, scenes):
         ties = int(bad.sum())
         print("tiled_box n=%d: %d exact-tie id differences in %d adversarial rays" % (n, ties, 2 * k))
         assert ties < 0.06 * 2 * k
+
+
+def test_ragged_image_shapes_and_degenerate_splits(api, ob, scenes):
+    # odd widths, non-square aspect (height = int(width / aspect), main.cpp:178-179), 1-pixel images, empty sample sets
+    sc = scenes.fixture("colored_cube")
+    p = api.Scene.from_dict(sc)
+    o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+    for W, aspect, pps in [(101, 16 / 9, 3), (7, 0.6, 2), (1, 1.0, 5), (33, 3.0, 1)]:
+        cam, cfg = api.make_config(sc, W, max_depth=2, mc_samples=2, pixel_samples=pps, aspect=aspect, seed=2, bg=(0.3, 0.3, 0.3, 1))
+        ocfg = ob.make_cfg(sc, W, 2, 2, pps, aspect=aspect, rng_mode=1, seed=2, bg=(0.3, 0.3, 0.3, 1))
+        assert (cfg.height, cfg.width) == (ocfg.height, ocfg.width) and cfg.height == int(np.float32(W) / np.float32(aspect))
+        img, st = p.render(cam, cfg)
+        ref, _, ost = o.render(ocfg)
+        assert img.shape == ref.shape and st.prim_rays == ost.num_prim_rays == W * cfg.height * pps
+        assert np.allclose(img, ref, rtol=2e-4, atol=2e-4)
+        ids, _ = p.primary_hits(cam, cfg)
+        dirs = ob.primary_dirs(ocfg).reshape(-1, 3)
+        oi, _ = o.intersect(np.tile(np.array(list(ocfg.cam_pos), np.float32), (dirs.shape[0], 1)), dirs, 0)
+        assert np.array_equal(ids.reshape(-1), oi)
+    # a rank whose first sample index lies beyond pixel_samples renders nothing (8 GPUs, 5 samples)
+    cam, cfg = api.make_config(sc, 16, pixel_samples=5, sample_begin=6, sample_stride=8)
+    img, st = p.render(cam, cfg)
+    assert st.rays == 0 and st.prim_rays == 0 and not img.any()
