@@ -49,54 +49,95 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    """SM clock + throttle reasons DURING the timed region. Polls NVML (what nvidia-smi reads: clocks.sm, clocks.max.sm,
+    clocks_event_reasons.*) every 5 ms from a thread -- the timed region of a short run is ~100 ms, below nvidia-smi's
+    own start-up time; falls back to the `nvidia-smi -lms` line of B200_PROFILING.md when pynvml is unavailable."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
         self.index = index
+        self.samples = []  # (t, sm_mhz, reasons_bitmask)
+        self.stop_flag = False
+        self.thread = None
         self.proc = None
-        self.lines = []
+        self.max_mhz = None
+        self.source = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES-free boxes: LOCAL_RANK == NVML index on the driver's single-node runs
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        while not self.stop_flag:
+            try:
+                mhz = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                why = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), mhz, why))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                mhz, mx = float(f[0]), float(f[1])
             except ValueError:
                 continue
-            for k, nm in enumerate(names):
-                if f[3 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            self.max_mhz = mx
+            why = 0
+            for bit, col in ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6)):
+                if f[col].lower().startswith("active"):
+                    why |= bit
+            self.samples.append((time.perf_counter(), mhz, why))
+
+    def stop(self, t0=None, t1=None):
+        """summary over the samples taken in [t0, t1] (perf_counter stamps of the timed region)"""
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        if self.thread:
+            self.thread.join(timeout=2)
+        inside = [s for s in self.samples if t0 is None or (t0 <= s[0] <= t1)]
+        window = "timed region"
+        if not inside and self.samples:  # region shorter than one sampling period: nearest samples (GPU under load: warm-up precedes)
+            mid = 0.5 * ((t0 or 0) + (t1 or 0))
+            inside = sorted(self.samples, key=lambda s: abs(s[0] - mid))[:3]
+            window = "nearest samples"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no clock samples (%s)" % self.source], "samples": 0}
+        mask = 0
+        for s_ in inside:
+            mask |= s_[2]
+        return {"sm_mhz": float(np.median([s_[1] for s_ in inside])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(v for k, v in self.REASONS.items() if mask & k), "samples": len(inside),
+                "source": self.source, "window": window}
 
 
 def alg_bytes(inner, leaf_nodes, tri_tests, queries):
@@ -202,6 +243,9 @@ def main():
         cfg.sample_stride = pps  # exactly one sample index per step
         return scene.render_device(cam, cfg, accum.data_ptr(), stream.cuda_stream, device=local_rank, want_stats=stats)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # polls through warm-up and the timed region; only samples inside the region are reported
     # ---- warm-up (untimed): scene upload, wave buffers, jitter table, clocks
     for i in range(max(args.warmup, 3)):
         step(i)
@@ -209,15 +253,13 @@ def main():
 
     # ---- timed region: exactly K steps + the final reduce, barrier + synchronize on both sides
     api.set_profiling(True)  # one CUDA-event pair per kernel launch on the launching stream (roofline leg)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     accum.zero_()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    t_region0 = time.perf_counter()
     tot = dict(rays=0, shadow=0, launches=0, ms_trace=0.0, ms_shadow=0.0, ms_shade=0.0, ms_other=0.0, trace_launches=0,
                trace_queries=0, shadow_launches=0)
     for i in range(args.steps):
@@ -236,8 +278,9 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    t_region1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
     api.set_profiling(False)
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     r = torch.tensor([tot["rays"]], device="cuda", dtype=torch.int64)
