@@ -70,6 +70,7 @@ struct DeviceScene {
     void* d_prefs = nullptr;
     void* d_isect_hot = nullptr;
     void* d_isect_cold = nullptr;
+    void* d_tri_box = nullptr;
     void* d_shade = nullptr;
     void* d_mirror = nullptr;
     uint32_t* d_child_slot = nullptr; // raytracer: child-ray slot of every shadow query
@@ -110,6 +111,7 @@ struct DeviceScene {
         cudaFree(d_prefs);
         cudaFree(d_isect_hot);
         cudaFree(d_isect_cold);
+        cudaFree(d_tri_box);
         cudaFree(d_shade);
         cudaFree(d_mirror);
         cudaFree(d_child_slot);
@@ -219,6 +221,18 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
         }
         CUDA_TRY(up(&ds->d_isect_hot, hot.data(), hot.size() * sizeof(float)));
         CUDA_TRY(up(&ds->d_isect_cold, cold.data(), cold.size() * sizeof(float)));
+        float scale = 0.f;
+        for (int c = 0; c < 6; ++c) scale = std::max(scale, std::fabs(sc->tree.box[c]));
+        const float grow = 1e-4f * scale;
+        std::vector<float> tb(nt * 8, 0.f);
+        for (size_t i = 0; i < nt; ++i) {
+            const float* v = &sc->tris.verts[i * 9];
+            for (int c = 0; c < 3; ++c) {
+                tb[i * 8 + c] = std::min(v[c], std::min(v[3 + c], v[6 + c])) - grow;
+                tb[i * 8 + 4 + c] = std::max(v[c], std::max(v[3 + c], v[6 + c])) + grow;
+            }
+        }
+        CUDA_TRY(up(&ds->d_tri_box, tb.data(), tb.size() * sizeof(float)));
     }
     CUDA_TRY(up(&ds->d_shade, sc->tris.shade.data(), sc->tris.shade.size() * sizeof(float)));
     CUDA_TRY(up(&ds->d_mirror, sc->tris.mirror.data(), sc->tris.mirror.size() * sizeof(float)));
@@ -228,6 +242,7 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     ds->dev.prefs = static_cast<const uint32_t*>(ds->d_prefs);
     ds->dev.isect_hot = static_cast<const float4*>(ds->d_isect_hot);
     ds->dev.isect_cold = static_cast<const float4*>(ds->d_isect_cold);
+    ds->dev.tri_box = static_cast<const float4*>(ds->d_tri_box);
     ds->dev.shade = static_cast<const float4*>(ds->d_shade);
     ds->dev.mirror = static_cast<const float4*>(ds->d_mirror);
     for (int c = 0; c < 3; ++c) {

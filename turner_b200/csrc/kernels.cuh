@@ -29,6 +29,9 @@ struct DevScene {
     // edge words), cold = 2 x float4: u.z v.xyz | uv vv uu denom (only for candidates that pass 0 <= r < best)
     const float4* isect_hot;
     const float4* isect_cold;
+    // bounding box of each triangle, grown by 1e-4 x scene scale: 2 x float4 (lo.xyz -, hi.xyz -). Used by the one-pass
+    // leaf schedule (big leaves): a plane hit outside the box cannot pass the barycentric test.
+    const float4* tri_box;
     const float4* shade;       // 4 x float4 per triangle: n0.xyz n1.x | n1.yz n2.xy | n2.z reflectivity - - | rgba
     const float4* mirror;      // reflective rgba per triangle (raytracer integrator only)
     float lo[3], hi[3];        // KDTree::box()
@@ -316,6 +319,11 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
             if (!(r >= 0.f)) continue;
             if (ANY_HIT ? !(r <= tmax_any) : !(r < out.r)) continue;
             if (!(r >= r_lo && r <= r_hi)) continue;
+            if (count > 8u) { // big leaf (a scene that is one leaf): most surviving plane hits lie far outside their triangle
+                const float4 blo = __ldg(sc.tri_box + 2 * static_cast<size_t>(id)), bhi = __ldg(sc.tri_box + 2 * static_cast<size_t>(id) + 1);
+                const float hx = ox + r * dx, hy = oy + r * dy, hz = oz + r * dz;
+                if (hx < blo.x || hy < blo.y || hz < blo.z || hx > bhi.x || hy > bhi.y || hz > bhi.z) continue;
+            }
             const float4* rec2 = sc.isect_cold + 2 * static_cast<size_t>(id);
             const float4 q2 = __ldg(rec2), q3 = __ldg(rec2 + 1);
             const float wx = (ox + r * dx) - q0.x, wy = (oy + r * dy) - q0.y, wz = (oz + r * dz) - q0.z; // :70-71
