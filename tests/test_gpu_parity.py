@@ -414,3 +414,40 @@ def test_ragged_image_shapes_and_degenerate_splits(api, ob, scenes):
     cam, cfg = api.make_config(sc, 16, pixel_samples=5, sample_begin=6, sample_stride=8)
     img, st = p.render(cam, cfg)
     assert st.rays == 0 and st.prim_rays == 0 and not img.any()
+
+
+def test_config1_full_size_readme_run(api, ob, cornell):
+    # BASELINE config 1 at full size: cornell_box -w 320 --max-depth 3 -m 1 --pixel-samples 8 (README.md:22-36)
+    sc, p, o = cornell
+    img, ref, st, ost = _compare_counter_mode(api, ob, sc, p, o, 320, 3, 1, 8, seed=1)
+    assert st.prim_rays == 819200
+    # README: 2 632 399 rays with the reference's stream; with other hemisphere samples the count moves by < 0.1 %
+    assert abs(int(st.rays) - 2632399) < 2632
+
+
+def test_config3_full_size_furnace(api, scenes):
+    # BASELINE config 3 at full size: furnace_test -w 1024 --max-depth 8 --pixel-samples 64 (-m 8 default), white
+    # environment. Energy conservation on the linear buffer: the disc well inside the silhouette averages rho = 0.18
+    # with alpha 1, no pixel exceeds max(background, rho + 6 sigma).
+    sc = scenes.fixture("furnace_test")
+    p = api.Scene.from_dict(sc)
+    W, pps, m, D = 1024, 64, 8, 8
+    cam, cfg = api.make_config(sc, W, max_depth=D, mc_samples=m, pixel_samples=pps, bg=(1, 1, 1, 1))
+    img, st = p.render(cam, cfg)
+    mean = img / pps
+    # coverage from a cheap low-resolution pass with the same camera
+    cam_l, cfg_l = api.make_config(sc, 128, pixel_samples=4)
+    ids, _ = p.primary_hits(cam_l, cfg_l)
+    cov = (ids != api.MISS_ID).all(-1)
+    ys, xs = np.nonzero(cov)
+    cy, cx = ys.mean() * 8 + 4, xs.mean() * 8 + 4
+    rad = 0.5 * min(ys.max() - ys.min(), xs.max() - xs.min()) * 8
+    yy, xx = np.mgrid[0:cfg.height, 0:W]
+    inner = (yy - cy) ** 2 + (xx - cx) ** 2 < (0.8 * rad) ** 2
+    assert inner.sum() > 20000, int(inner.sum())
+    assert abs(mean[inner][:, :3].mean() - 0.18) < 5e-4, mean[inner][:, :3].mean()
+    assert abs(mean[inner][:, 3].mean() - 1.0) < 2e-3
+    sd = 0.36 * np.sqrt(1 / 12) / np.sqrt(pps * m)
+    assert mean[inner][:, :3].max() < 0.18 + 6 * sd
+    assert mean[..., :3].max() <= 1.0 + 1e-5
+    assert st.prim_rays == W * cfg.height * pps
