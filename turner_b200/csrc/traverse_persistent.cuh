@@ -215,29 +215,40 @@ __global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_ker
             float c0_r = 0.f, c1_r = 0.f;
             int ncand = 0;
             const uint32_t cnt_two_pass = TWO_PASS ? cnt : 0u;
-            for (uint32_t i = 0; i < cnt_two_pass; ++i) {
-                const uint32_t id = __ldg(&sc.prefs[first + i]);
-                const float4* rec = sc.isect_hot + 2 * static_cast<size_t>(id);
-                const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
-                const float nx = q0.w, ny = q1.x, nz = q1.y;
-                const float denom = nx * dx + ny * dy + nz * dz;
-                const float nom = nx * (q0.x - ox) + ny * (q0.y - oy) + nz * (q0.z - oz);
-                const float r = nom / denom;
-                const bool cand = denom != 0.f && r >= 0.f && (ANY ? (r <= tmax_any) : (r < best_r)) && r >= r_lo && r <= r_hi;
-                if (cand) {
-                    if (ncand == 2) { // rare: drain the two recorded survivors first (keeps visiting order)
-                        if (test_candidate<ANY>(sc, c0_id, c0_r, ox, oy, oz, dx, dy, dz, best_id, best_r, best_s, best_t)) occluded = true;
-                        if (!occluded && test_candidate<ANY>(sc, c1_id, c1_r, ox, oy, oz, dx, dy, dz, best_id, best_r, best_s, best_t)) occluded = true;
-                        ncand = 0;
+            // two triangles per trip: both ids, then both records are requested before either is used, so a leaf costs
+            // one id latency + one record latency per PAIR of triangles instead of per triangle
+            for (uint32_t i = 0; i < cnt_two_pass; i += 2) {
+                const bool two = i + 1 < cnt_two_pass;
+                const uint32_t ida = __ldg(&sc.prefs[first + i]);
+                const uint32_t idb = two ? __ldg(&sc.prefs[first + i + 1]) : ida;
+                const float4* reca = sc.isect_hot + 2 * static_cast<size_t>(ida);
+                const float4* recb = sc.isect_hot + 2 * static_cast<size_t>(idb);
+                const float4 a0 = __ldg(reca), a1 = __ldg(reca + 1), b0 = __ldg(recb), b1 = __ldg(recb + 1);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float4 q0 = h ? b0 : a0, q1 = h ? b1 : a1;
+                    const uint32_t id = h ? idb : ida;
+                    const float nx = q0.w, ny = q1.x, nz = q1.y;
+                    const float denom = nx * dx + ny * dy + nz * dz;
+                    const float nom = nx * (q0.x - ox) + ny * (q0.y - oy) + nz * (q0.z - oz);
+                    const float r = nom / denom;
+                    const bool cand = (h == 0 || two) && denom != 0.f && r >= 0.f && (ANY ? (r <= tmax_any) : (r < best_r)) &&
+                                      r >= r_lo && r <= r_hi;
+                    if (cand) {
+                        if (ncand == 2) { // rare: drain the two recorded survivors first (keeps visiting order)
+                            if (test_candidate<ANY>(sc, c0_id, c0_r, ox, oy, oz, dx, dy, dz, best_id, best_r, best_s, best_t)) occluded = true;
+                            if (!occluded && test_candidate<ANY>(sc, c1_id, c1_r, ox, oy, oz, dx, dy, dz, best_id, best_r, best_s, best_t)) occluded = true;
+                            ncand = 0;
+                        }
+                        if (ncand == 0) {
+                            c0_id = id;
+                            c0_r = r;
+                        } else {
+                            c1_id = id;
+                            c1_r = r;
+                        }
+                        ++ncand;
                     }
-                    if (ncand == 0) {
-                        c0_id = id;
-                        c0_r = r;
-                    } else {
-                        c1_id = id;
-                        c1_r = r;
-                    }
-                    ++ncand;
                 }
             }
             if (ncand > 0 && !occluded && test_candidate<ANY>(sc, c0_id, c0_r, ox, oy, oz, dx, dy, dz, best_id, best_r, best_s, best_t)) occluded = true;
