@@ -451,3 +451,33 @@ def test_config3_full_size_furnace(api, scenes):
     assert mean[inner][:, :3].max() < 0.18 + 6 * sd
     assert mean[..., :3].max() <= 1.0 + 1e-5
     assert st.prim_rays == W * cfg.height * pps
+
+
+def test_against_reference_generated_golden_fixtures(api, scenes):
+    # tests/golden/reference_outputs.npz holds outputs of the reference's own code (tools/make_golden.py)
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs.npz"))
+    bgs = {"cornell_box": (0, 0, 0, 1), "colored_cube": (0.1, 0.2, 0.3, 1), "furnace_test": (1, 1, 1, 1)}
+    for name, bg in bgs.items():
+        sc = scenes.fixture(name)
+        p = api.Scene.from_dict(sc)
+        assert np.array_equal(p.nodes(), gold[name + "/nodes"])
+        cam, cfg = api.make_config(sc, 48, pixel_samples=1, integrator=api.RAYCASTER, bg=bg, max_visibility=2.0)
+        ids, rst = p.primary_hits(cam, cfg)
+        assert np.array_equal(ids.reshape(-1), gold[name + "/prim_ids"])
+        assert np.array_equal(bits(rst.reshape(-1, 3)), bits(gold[name + "/prim_rst"]))
+        img, st = p.render(cam, cfg)
+        assert np.array_equal(bits(img), bits(gold[name + "/rc_sum"]))
+        assert [st.rays, st.prim_rays] == gold[name + "/rc_rays"].tolist()
+        assert api.write_p3(api.tonemap(img, 1)) == gold[name + "/rc_p3"].tobytes().decode()
+        if sc["light"]:
+            cam, cfg = api.make_config(sc, 48, max_depth=4, pixel_samples=2, integrator=api.RAYTRACER, bg=bg, shadow_intensity=0.5)
+            img, st = p.render(cam, cfg)
+            assert [st.rays, st.prim_rays] == gold[name + "/rt_rays"].tolist()
+            assert np.all(np.abs(img - gold[name + "/rt_sum"]) <= 2e-5 * (1 + np.abs(gold[name + "/rt_sum"])))
+        # path tracer vs the reference's own radiance: same primaries, other hemisphere samples -> statistical agreement
+        cam, cfg = api.make_config(sc, 24, max_depth=3, mc_samples=2, pixel_samples=2, bg=bg)
+        img, st = p.render(cam, cfg)
+        ref = gold[name + "/pt_sum"]
+        assert st.prim_rays == int(gold[name + "/pt_rays"][1])
+        assert abs(img.mean() - ref.mean()) < 0.08 * max(ref.mean(), 1e-3)
