@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -36,8 +37,8 @@
 namespace trn {
 
 thread_local std::string g_last_error;
-static int g_profiling = 0;
-static int g_counting = 0;
+static std::atomic<int> g_profiling{0};
+static std::atomic<int> g_counting{0};
 
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
@@ -461,7 +462,7 @@ struct KernelTimer {
     cudaStream_t stream;
     bool on;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
-    explicit KernelTimer(cudaStream_t s) : stream(s), on(g_profiling != 0) {}
+    explicit KernelTimer(cudaStream_t s) : stream(s), on(g_profiling.load() != 0) {}
     void begin(int kind) {
         if (!on) return;
         cudaEvent_t a, b;
@@ -508,7 +509,7 @@ struct Renderer {
     KernelTimer timer;
     uint64_t rays = 0, prim = 0, shadow = 0, launches = 0;
     uint64_t trace_launches = 0, trace_queries = 0, shadow_launches = 0;
-    bool counting = g_counting != 0;
+    bool counting = g_counting.load() != 0;
     int mode_closest = persistent_mode(false), mode_shadow = persistent_mode(true);
     bool sort_rays = env_u64("TRN_SORT", 0) != 0 && ds->two_pass; // experiment: (octant, Morton) order for secondary waves; measured no gain (profiles/README.md)
     uint64_t cap;
@@ -688,7 +689,15 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
     rc = ensure_jitter(ds, cfg->width, cfg->pixel_samples);
     if (rc) return rc;
     cudaStream_t stream = use_user_stream ? user_stream : ds->stream;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    struct EventPair {
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair() {
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+        }
+    } ev;
+    cudaEvent_t& e0 = ev.a;
+    cudaEvent_t& e1 = ev.b;
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         CUDA_TRY(cudaEventCreate(&e0));
@@ -702,8 +711,6 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
         cudaEventSynchronize(e1);
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
         stats->ms_render = ms;
         stats->rays = r.rays;
         stats->prim_rays = r.prim;

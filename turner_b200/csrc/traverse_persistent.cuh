@@ -1,30 +1,23 @@
-// Persistent-warp kd traversal with lane refill -- EXPERIMENTAL variant, selected with TRN_PERSISTENT=1.
-// Measured on B200 (profiles/README.md): lane utilisation doubles (5.6 -> 11.1 of 32 on secondary rays) but the state
-// machine executes ~55 % more thread-instructions, so the net is +11 % on the closest-hit kernel of the 1M-triangle
-// mesh and a loss on shadow rays and on cornell_box; the one-thread-per-ray kernels stay the default.
+// Persistent-warp kd traversal with lane refill -- the production closest-hit kernel (shadow waves keep the
+// one-thread-per-ray kernel of kernels.cuh; A/B numbers in profiles/README.md).
 //
-// Why: ncu on the one-thread-per-ray kernels (profiles/r1_*_simple_*.txt) shows the issue slots 60-70 % busy
-// but only 5-12 of 32 lanes active per instruction. Ray cost is heavy-tailed (a miss leaves at once, a grazing
-// ray visits hundreds of leaves), so a warp of 32 fixed rays idles most of its lanes waiting for the slowest.
+// Why: ncu on the one-thread-per-ray kernel (profiles/r1_prof_trace_v2.txt) shows the issue slots 60-70 % busy but only
+// 5-12 of 32 lanes active per instruction. Ray cost is heavy-tailed (a miss leaves at once, a grazing ray visits
+// hundreds of leaves), so a warp of 32 fixed rays idles most of its lanes waiting for the slowest.
 //
-// Here a warp is a long-lived worker and a lane is a slot holding one ray:
-//   * every lane runs a small state machine -- one step is EITHER one inner-node step OR one triangle test --
-//     so lanes never wait for each other's loops, only the two step bodies alternate;
-//   * every kStepsPerCheck steps the warp counts its busy lanes; when fewer than kRefillBelow are busy the idle
-//     lanes take fresh rays from a per-warp pool (one atomicAdd per kPoolChunk rays on the work cursor);
-//   * grid = resident CTAs per SM x number of SMs (multiple of 148 on B200), no tail of half-empty CTAs.
-// The triangle id of the NEXT test is fetched one step ahead, so a step waits for one memory latency, not two.
+// Here a warp is a long-lived worker and a lane is a slot holding one ray (its traversal stack lives in local memory):
+//   * one scheduling quantum of a lane = walk down to the next leaf, test its triangles, pop ("while-while");
+//   * after every two quanta the warp counts its busy lanes; when fewer than 28 are busy the idle lanes take fresh
+//     rays from a per-warp pool that is replenished with one atomicAdd per 32 rays on the wave's work cursor
+//     (bigger chunks leave a static, unbalanced tail; smaller ones make the cursor a hot spot);
+//   * grid = resident CTAs per SM x number of SMs (9 x 148 on B200): no tail of half-empty CTAs.
 //
-// Per-ray arithmetic, visiting order and tie rule are exactly those of traverse_pairs<> in kernels.cuh (the
-// bit-exact contract); only the scheduling of rays onto lanes differs.
+// Per-ray arithmetic, visiting order and tie rule are exactly those of traverse_pairs<> in kernels.cuh (the bit-exact
+// contract); only the scheduling of rays onto lanes differs.
 #pragma once
 #include "kernels.cuh"
 
 namespace trn {
-
-constexpr int kRefillBelow = 26;      // refill when fewer lanes than this are busy
-constexpr int kStepsPerCheck = 6;     // state-machine steps between two busy-lane counts
-constexpr uint32_t kPoolChunk = 64;   // rays a warp reserves per global atomic (small: the tail must stay balanced)
 
 // MODE 0: closest hit, rays from a RayWave (a,b); result -> hits[idx]
 // MODE 1: any-hit shadow rays from a ShadowWave (a,b,c); unoccluded -> acc[pixel] += c
