@@ -1,0 +1,500 @@
+// CPU emulation of one warp of trace_pooled_kernel<0> (traverse_pooled.cuh), lane by lane in lockstep, with the same
+// control flow, queues and arithmetic (fmaf for the pre-filter, unfused fp32 for the exact part). Development tool:
+// finds logic errors (hangs, lost hits) and checks the pre-filter's conservativeness against the plain per-ray
+// traversal on the benchmark mesh without spending GPU time.
+//
+//   g++ -O2 -std=c++17 -ffp-contract=off -fopenmp tools/pooled_emul.cpp turner_b200/csrc/kdtree_build.o -o /tmp/sim/pooled_emul
+//   /tmp/sim/pooled_emul /tmp/sim/mesh1m.bin [rows]
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "../turner_b200/csrc/kdtree_build.h"
+
+using namespace trn;
+
+static const float kFltMax = 3.402823466e+38f, kCellSlack = 1e-4f;
+static const uint32_t kMiss = 0x40000000u;
+static const int kPqChunks = 128, kPqChunkTris = 4, kPqMaxAppend = 16, kPqSurv = 32 + 32 * 4;
+
+struct Ray {
+    float o[3], d[3];
+};
+struct Hit {
+    uint32_t id = kMiss;
+    float r = kFltMax, s = 0, t = 0;
+};
+struct Scene {
+    HostTriangles tris;
+    KdTree tree;
+    std::vector<float> planes;
+};
+static inline uint32_t fbits(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+static inline float bfloat(uint32_t u) {
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+// plain per-ray traversal (= traverse_pairs<false> for rays without zero direction components)
+static void trace_plain(const Scene& sc, const Ray& ray, Hit& out) {
+    const float ox = ray.o[0], oy = ray.o[1], oz = ray.o[2], dx = ray.d[0], dy = ray.d[1], dz = ray.d[2];
+    const float ix = 1 / dx, iy = 1 / dy, iz = 1 / dz;
+    const float* box = sc.tree.box;
+    float tx1 = (box[0] - ox) * ix, tx2 = (box[3] - ox) * ix;
+    float tenter = std::fmin(tx1, tx2), texit = std::fmax(tx1, tx2);
+    float ty1 = (box[1] - oy) * iy, ty2 = (box[4] - oy) * iy;
+    tenter = std::fmax(tenter, std::fmin(ty1, ty2));
+    texit = std::fmin(texit, std::fmax(ty1, ty2));
+    float tz1 = (box[2] - oz) * iz, tz2 = (box[5] - oz) * iz;
+    tenter = std::fmax(tenter, std::fmin(tz1, tz2));
+    texit = std::fmin(texit, std::fmax(tz1, tz2));
+    out = Hit();
+    if (texit < tenter) return;
+    if (tenter < 0.f) tenter = 0.f;
+    struct E {
+        uint32_t x, y;
+        float a, b;
+    } stack[64];
+    int sp = 0;
+    const uint64_t* pn = sc.tree.pair_nodes.data();
+    uint32_t nx_ = uint32_t(pn[0]), ny_ = uint32_t(pn[0] >> 32);
+    for (;;) {
+        while ((ny_ & 3u) != 3u) {
+            const int ax = int(ny_ & 3u);
+            const float split = bfloat(nx_);
+            const uint32_t ci = ny_ >> 2;
+            const uint32_t px = uint32_t(pn[ci]), py = uint32_t(pn[ci] >> 32), pz = uint32_t(pn[ci + 1]), pw = uint32_t(pn[ci + 1] >> 32);
+            const float o_ax = ax == 0 ? ox : (ax == 1 ? oy : oz), i_ax = ax == 0 ? ix : (ax == 1 ? iy : iz);
+            const float t = (split - o_ax) * i_ax;
+            const bool flip = std::signbit(i_ax);
+            const uint32_t nearx = flip ? pz : px, neary = flip ? pw : py, farx = flip ? px : pz, fary = flip ? py : pw;
+            const bool near_only = texit < t, far_only = !near_only && (t < tenter), both = !near_only && !far_only;
+            const bool go_far = far_only || (both && neary == 3u);
+            if (both && neary != 3u && fary != 3u) stack[sp++] = E{farx, fary, t, texit};
+            nx_ = go_far ? farx : nearx;
+            ny_ = go_far ? fary : neary;
+            const float te = (both && go_far) ? t : tenter, tx = (both && !go_far) ? t : texit;
+            tenter = te;
+            texit = tx;
+        }
+        const uint32_t first = nx_, cnt = ny_ >> 2;
+        const float r_lo = tenter - kCellSlack * (std::fabs(tenter) + 1.f), r_hi = texit + kCellSlack * (std::fabs(texit) + 1.f);
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t id = sc.tree.pair_leaf_refs[first + i];
+            const float* q = &sc.tris.isect[size_t(id) * 16];
+            const float nx = q[3], ny = q[4], nz = q[5];
+            const float denom = nx * dx + ny * dy + nz * dz;
+            if (denom == 0.f) continue;
+            const float nom = nx * (q[0] - ox) + ny * (q[1] - oy) + nz * (q[2] - oz);
+            const float r = nom / denom;
+            if (!(r >= 0.f) || !(r < out.r) || !(r >= r_lo && r <= r_hi)) continue;
+            const float wx = (ox + r * dx) - q[0], wy = (oy + r * dy) - q[1], wz = (oz + r * dz) - q[2];
+            const float wv = wx * q[9] + wy * q[10] + wz * q[11];
+            const float wu = wx * q[6] + wy * q[7] + wz * q[8];
+            const float s = (q[12] * wv - q[13] * wu) / q[15];
+            if (s < 0.f) continue;
+            const float t = (q[12] * wu - q[14] * wv) / q[15];
+            if (t < 0.f || 1.f < s + t) continue;
+            out.id = id;
+            out.r = r;
+            out.s = s;
+            out.t = t;
+        }
+        if (out.id != kMiss && out.r <= texit) break;
+        if (sp == 0) break;
+        const E e = stack[--sp];
+        nx_ = e.x;
+        ny_ = e.y;
+        tenter = e.a;
+        texit = e.b;
+    }
+}
+
+struct U4 {
+    uint32_t x, y, z, w;
+};
+struct F4 {
+    float x, y, z, w;
+};
+
+// one emulated warp over rays[begin, end); returns false on a detected hang
+static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin, size_t end, std::vector<Hit>& hits, int refill_below,
+                     int walk_iters, uint64_t* stat) {
+    F4 s_ray[64];
+    U4 s_chunk[kPqChunks];
+    uint32_t s_surv[kPqSurv][2];
+    uint32_t s_nchunk = 0, s_nvalid = kPqChunks, s_nsurv = 0;
+    float scale = 0.f;
+    for (int c = 0; c < 6; ++c) scale = std::fmax(scale, std::fabs(sc.tree.box[c]));
+    const uint64_t* pn = sc.tree.pair_nodes.data();
+    struct LaneS {
+        U4 stack[64];
+        int sp = 0;
+        float ox, oy, oz, ix, iy, iz, tenter, texit, last_texit;
+        uint32_t nx, ny;
+        uint32_t best_id, best_seq, idx, leaf_off;
+        float best_r, best_s, best_t;
+        bool busy = false, walking = false;
+    };
+    std::vector<LaneS> L(32);
+    size_t next = begin;
+    uint64_t cycles = 0;
+    for (;;) {
+        if (++cycles > 50000000ull) return false;
+        int nbusy = 0;
+        for (auto& l : L) nbusy += l.busy;
+        if (nbusy < refill_below && next < end) {
+            for (int lane = 0; lane < 32 && next < end; ++lane) {
+                LaneS& l = L[lane];
+                if (l.busy) continue;
+                l.idx = uint32_t(next++);
+                const Ray& ry = rays[l.idx];
+                const float dx = ry.d[0], dy = ry.d[1], dz = ry.d[2];
+                l.ox = ry.o[0];
+                l.oy = ry.o[1];
+                l.oz = ry.o[2];
+                if (dx == 0.f || dy == 0.f || dz == 0.f) {
+                    std::fprintf(stderr, "axis-parallel ray skipped\n");
+                    continue;
+                }
+                l.ix = 1 / dx;
+                l.iy = 1 / dy;
+                l.iz = 1 / dz;
+                const float* box = sc.tree.box;
+                float tx1 = (box[0] - l.ox) * l.ix, tx2 = (box[3] - l.ox) * l.ix;
+                float t0 = std::fmin(tx1, tx2), t1 = std::fmax(tx1, tx2);
+                float ty1 = (box[1] - l.oy) * l.iy, ty2 = (box[4] - l.oy) * l.iy;
+                t0 = std::fmax(t0, std::fmin(ty1, ty2));
+                t1 = std::fmin(t1, std::fmax(ty1, ty2));
+                float tz1 = (box[2] - l.oz) * l.iz, tz2 = (box[5] - l.oz) * l.iz;
+                t0 = std::fmax(t0, std::fmin(tz1, tz2));
+                t1 = std::fmin(t1, std::fmax(tz1, tz2));
+                if (t1 < t0) {
+                    hits[l.idx] = Hit();
+                    continue;
+                }
+                l.tenter = t0 < 0.f ? 0.f : t0;
+                l.texit = t1;
+                l.sp = 0;
+                l.nx = uint32_t(pn[0]);
+                l.ny = uint32_t(pn[0] >> 32);
+                l.best_id = kMiss;
+                l.best_r = kFltMax;
+                l.best_s = l.best_t = 0.f;
+                l.best_seq = 0;
+                l.last_texit = -kFltMax;
+                l.leaf_off = 0;
+                l.busy = l.walking = true;
+                const float E = 1.9073486e-6f * (3.f * scale + (std::fabs(l.ox) + std::fabs(l.oy) + std::fabs(l.oz)));
+                const float F = 9.5367432e-7f * (std::fabs(dx) + std::fabs(dy) + std::fabs(dz));
+                s_ray[2 * lane] = F4{l.ox, l.oy, l.oz, E};
+                s_ray[2 * lane + 1] = F4{dx, dy, dz, F};
+            }
+            nbusy = 0;
+            for (auto& l : L) nbusy += l.busy;
+        }
+        if (nbusy == 0) {
+            if (next >= end) break;
+            continue;
+        }
+        // WALK
+        bool blocked[32] = {false};
+        for (int it = 0; it < walk_iters; ++it) {
+            bool any = false;
+            for (int lane = 0; lane < 32; ++lane) any |= L[lane].busy && L[lane].walking && !blocked[lane];
+            if (!any) break;
+            stat[0]++;
+            for (int lane = 0; lane < 32; ++lane) {
+                LaneS& l = L[lane];
+                if (!(l.busy && l.walking && !blocked[lane])) continue;
+                stat[1]++;
+                if ((l.ny & 3u) != 3u) {
+                    const uint32_t ax = l.ny & 3u;
+                    const float split = bfloat(l.nx);
+                    const uint32_t ci = l.ny >> 2;
+                    const uint32_t px = uint32_t(pn[ci]), py = uint32_t(pn[ci] >> 32), pz = uint32_t(pn[ci + 1]), pw = uint32_t(pn[ci + 1] >> 32);
+                    float o_ax = l.oz, i_ax = l.iz;
+                    if (ax == 0u) { o_ax = l.ox; i_ax = l.ix; }
+                    if (ax == 1u) { o_ax = l.oy; i_ax = l.iy; }
+                    const float t = (split - o_ax) * i_ax;
+                    const bool flip = (fbits(i_ax) >> 31) != 0u;
+                    const uint32_t nearx = flip ? pz : px, neary = flip ? pw : py, farx = flip ? px : pz, fary = flip ? py : pw;
+                    const bool near_only = l.texit < t, far_only = !near_only && (t < l.tenter), both = !near_only && !far_only;
+                    const bool go_far = far_only || (both && neary == 3u);
+                    if (both && neary != 3u && fary != 3u) l.stack[l.sp++] = U4{farx, fary, fbits(t), fbits(l.texit)};
+                    l.nx = go_far ? farx : nearx;
+                    l.ny = go_far ? fary : neary;
+                    const float te = (both && go_far) ? t : l.tenter, tx = (both && !go_far) ? t : l.texit;
+                    l.tenter = te;
+                    l.texit = tx;
+                } else {
+                    const uint32_t cnt = l.ny >> 2;
+                    const uint32_t rem = cnt - l.leaf_off;
+                    const uint32_t ch = std::min<uint32_t>((rem + kPqChunkTris - 1) / kPqChunkTris, kPqMaxAppend);
+                    bool leaf_done = true;
+                    if (ch > 0) {
+                        const uint32_t slot = s_nchunk;
+                        s_nchunk += ch;
+                        if (slot + ch <= uint32_t(kPqChunks)) {
+                            float lo = l.tenter - kCellSlack * (std::fabs(l.tenter) + 1.f);
+                            float hi = l.texit + kCellSlack * (std::fabs(l.texit) + 1.f);
+                            lo = std::fmax(lo, 0.f);
+                            hi = std::fmin(hi, l.best_r);
+                            const uint32_t first = l.nx + l.leaf_off;
+                            for (uint32_t k = 0; k < ch; ++k) {
+                                const uint32_t c = std::min<uint32_t>(kPqChunkTris, rem - k * kPqChunkTris);
+                                s_chunk[slot + k] = U4{first + k * kPqChunkTris, c | (uint32_t(lane) << 8), fbits(lo), fbits(hi)};
+                            }
+                            l.leaf_off += ch * kPqChunkTris;
+                            leaf_done = l.leaf_off >= cnt;
+                        } else {
+                            s_nvalid = std::min(s_nvalid, slot);
+                            blocked[lane] = true;
+                            leaf_done = false;
+                        }
+                    }
+                    if (leaf_done) {
+                        l.leaf_off = 0;
+                        l.last_texit = l.texit;
+                        if (l.sp == 0) l.walking = false;
+                        else {
+                            const U4 e = l.stack[--l.sp];
+                            l.nx = e.x;
+                            l.ny = e.y;
+                            l.tenter = bfloat(e.z);
+                            l.texit = bfloat(e.w);
+                            if (l.tenter > l.best_r) l.walking = false;
+                        }
+                    }
+                }
+            }
+        }
+        // TEST / EXACT
+        const uint32_t nch = std::min(s_nchunk, s_nvalid);
+        uint32_t base = 0;
+        for (;;) {
+            const uint32_t ns = s_nsurv;
+            if (ns >= 32u || (base >= nch && ns > 0u)) {
+                const uint32_t take = std::min(32u, ns), sbase = ns - take;
+                stat[4]++;
+                stat[5] += take;
+                struct P {
+                    bool pass;
+                    uint32_t id, owner, seq;
+                    float r, s, t;
+                } res[32];
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    P& p = res[lane];
+                    p.pass = false;
+                    if (lane >= take) continue;
+                    p.id = s_surv[sbase + lane][0];
+                    p.owner = s_surv[sbase + lane][1] & 31u;
+                    p.seq = s_surv[sbase + lane][1] >> 5;
+                    const float lim = L[p.owner].best_r;
+                    const F4 ro = s_ray[2 * p.owner], rd = s_ray[2 * p.owner + 1];
+                    const float* q = &sc.tris.isect[size_t(p.id) * 16];
+                    const float nx = q[3], ny = q[4], nz = q[5];
+                    const float denom = nx * rd.x + ny * rd.y + nz * rd.z;
+                    const float nom = nx * (q[0] - ro.x) + ny * (q[1] - ro.y) + nz * (q[2] - ro.z);
+                    p.r = nom / denom;
+                    if (denom != 0.f && p.r >= 0.f && p.r <= lim) {
+                        const float wx = (ro.x + p.r * rd.x) - q[0], wy = (ro.y + p.r * rd.y) - q[1], wz = (ro.z + p.r * rd.z) - q[2];
+                        const float wv = wx * q[9] + wy * q[10] + wz * q[11];
+                        const float wu = wx * q[6] + wy * q[7] + wz * q[8];
+                        p.s = (q[12] * wv - q[13] * wu) / q[15];
+                        if (!(p.s < 0.f)) {
+                            p.t = (q[12] * wu - q[14] * wv) / q[15];
+                            p.pass = !(p.t < 0.f || 1.f < p.s + p.t);
+                        }
+                    }
+                }
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    const P& p = res[lane];
+                    if (!p.pass) continue;
+                    LaneS& o = L[p.owner];
+                    if (p.r < o.best_r || (p.r == o.best_r && p.seq < o.best_seq)) {
+                        o.best_id = p.id;
+                        o.best_r = p.r;
+                        o.best_s = p.s;
+                        o.best_t = p.t;
+                        o.best_seq = p.seq;
+                    }
+                }
+                s_nsurv = sbase;
+            } else if (base < nch) {
+                stat[2]++;
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    const uint32_t g = base + lane;
+                    if (g >= nch) continue;
+                    stat[3]++;
+                    const U4 d = s_chunk[g];
+                    const uint32_t first = d.x, cnt = d.y & 0xffu, owner = d.y >> 8;
+                    const float lo = bfloat(d.z), hi = bfloat(d.w);
+                    const F4 ro = s_ray[2 * owner], rd = s_ray[2 * owner + 1];
+                    const float E = ro.w, F = rd.w;
+                    const float c1 = std::fmaf(-lo, F, -E), c2 = std::fmaf(hi, F, E);
+                    for (uint32_t i = 0; i < cnt; ++i) {
+                        const uint32_t id = sc.tree.pair_leaf_refs[first + i];
+                        const float* p = &sc.planes[size_t(id) * 4];
+                        const float a = std::fmaf(p[0], rd.x, std::fmaf(p[1], rd.y, p[2] * rd.z));
+                        const float b = std::fmaf(-p[0], ro.x, std::fmaf(-p[1], ro.y, std::fmaf(-p[2], ro.z, p[3])));
+                        const float A = std::fabs(a);
+                        const float B = bfloat(fbits(b) ^ (fbits(a) & 0x80000000u));
+                        const bool keep = A <= F || (B >= std::fmaf(lo, A, c1) && B <= std::fmaf(hi, A, c2));
+                        stat[6]++;
+                        if (keep) {
+                            if (s_nsurv >= uint32_t(kPqSurv)) {
+                                std::fprintf(stderr, "survivor queue overflow\n");
+                                return false;
+                            }
+                            s_surv[s_nsurv][0] = id;
+                            s_surv[s_nsurv][1] = owner | ((g * 8u + i + 1u) << 5);
+                            ++s_nsurv;
+                        }
+                    }
+                }
+                base += 32u;
+            } else {
+                break;
+            }
+        }
+        s_nchunk = 0;
+        s_nvalid = kPqChunks;
+        for (int lane = 0; lane < 32; ++lane) {
+            LaneS& l = L[lane];
+            if (!l.busy) continue;
+            l.best_seq = 0;
+            const bool finished = !l.walking || (l.best_id != kMiss && (l.best_r <= l.last_texit || l.best_r < l.tenter));
+            if (finished) {
+                l.busy = false;
+                Hit h;
+                h.id = l.best_id;
+                h.r = l.best_r;
+                h.s = l.best_s;
+                h.t = l.best_t;
+                hits[l.idx] = h;
+            }
+        }
+    }
+    return true;
+}
+
+int main(int argc, char** argv) {
+    const char* path = argc > 1 ? argv[1] : "/tmp/sim/mesh1m.bin";
+    const int rows = argc > 2 ? std::atoi(argv[2]) : 16;
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return 1;
+    uint32_t n = 0;
+    if (std::fread(&n, 4, 1, f) != 1) return 1;
+    std::vector<float> V(size_t(n) * 9), N(size_t(n) * 9), D(size_t(n) * 4, 0.7f);
+    if (std::fread(V.data(), 4, V.size(), f) != V.size() || std::fread(N.data(), 4, N.size(), f) != N.size()) return 1;
+    std::fclose(f);
+    Scene sc;
+    precompute_triangles(V.data(), N.data(), D.data(), n, sc.tris);
+    build_kdtree(sc.tris, sc.tree, 0);
+    sc.planes.resize(size_t(n) * 4);
+    for (size_t i = 0; i < n; ++i) {
+        const float* q = &sc.tris.isect[i * 16];
+        sc.planes[i * 4] = q[3];
+        sc.planes[i * 4 + 1] = q[4];
+        sc.planes[i * 4 + 2] = q[5];
+        sc.planes[i * 4 + 3] = float(double(q[3]) * q[0] + double(q[4]) * q[1] + double(q[5]) * q[2]);
+    }
+    std::printf("triangles %u, pair nodes %zu\n", n, sc.tree.pair_nodes.size());
+    const float R[9] = {0.9438583850860596f, -0.07586748898029327f, 0.3215206563472748f, 0.0f, 0.9732714891433716f, 0.2296576052904129f,
+                        -0.33035042881965637f, -0.21676425635814667f, 0.9186304211616516f};
+    const float P[3] = {1.4881685972213745f, 1.0629775524139404f, 4.251910209655762f};
+    const float delta = std::tan(0.4287780225276947f);
+    const int W = 1920, H = 1920;
+    std::vector<Ray> wave;
+    const int y0 = H / 2 - rows / 2 - 200;
+    for (int y = y0; y < y0 + rows; ++y)
+        for (int x = 0; x < W; ++x) {
+            const float px = x + 0.5f, py = y + 0.5f;
+            const float vx = -delta * (1 - 2 * px / W), vy = delta * (1 - 2 * py / H), vz = -1.f;
+            Ray r;
+            for (int c = 0; c < 3; ++c) {
+                r.o[c] = P[c];
+                r.d[c] = R[3 * c] * vx + R[3 * c + 1] * vy + R[3 * c + 2] * vz;
+            }
+            wave.push_back(r);
+        }
+    std::mt19937_64 rng(1);
+    std::uniform_real_distribution<float> U(0.f, 1.f);
+    const int m = 4;
+    for (int depth = 0; depth < 3; ++depth) {
+        std::vector<Hit> ref(wave.size()), got(wave.size());
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < long(wave.size()); ++i) trace_plain(sc, wave[i], ref[i]);
+        const size_t per = 4096;
+        const long nw = long((wave.size() + per - 1) / per);
+        uint64_t stat[8] = {0};
+        bool ok = true;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (long w = 0; w < nw; ++w) {
+            uint64_t st[8] = {0};
+            const bool r = warp_run(sc, wave, size_t(w) * per, std::min(wave.size(), size_t(w + 1) * per), got, 24, 12, st);
+#pragma omp critical
+            {
+                ok &= r;
+                for (int k = 0; k < 8; ++k) stat[k] += st[k];
+            }
+        }
+        size_t id_diff = 0, bit_diff = 0, hits = 0;
+        for (size_t i = 0; i < wave.size(); ++i) {
+            hits += ref[i].id != kMiss;
+            if (ref[i].id != got[i].id) ++id_diff;
+            else if (ref[i].id != kMiss && (fbits(ref[i].r) != fbits(got[i].r) || fbits(ref[i].s) != fbits(got[i].s) || fbits(ref[i].t) != fbits(got[i].t))) ++bit_diff;
+        }
+        const double nr = double(wave.size());
+        std::printf("depth %d: %zu rays, %zu hits, completed %d, id differences %zu, (r,s,t) bit differences %zu\n", depth, wave.size(), hits,
+                    int(ok), id_diff, bit_diff);
+        std::printf("   per ray: walk iterations %.2f (lanes %.1f)  test rounds %.3f (chunks/round %.1f)  exact rounds %.3f (survivors/round %.1f)  "
+                    "tests %.1f survivors %.2f\n",
+                    stat[0] / nr, double(stat[1]) / std::max<uint64_t>(1, stat[0]), stat[2] / nr, double(stat[3]) / std::max<uint64_t>(1, stat[2]),
+                    stat[4] / nr, double(stat[5]) / std::max<uint64_t>(1, stat[4]), stat[6] / nr, stat[5] / nr);
+        std::vector<Ray> next;
+        for (size_t base = 0; base < wave.size(); base += 32) {
+            std::vector<size_t> hl;
+            for (size_t i = base; i < std::min(wave.size(), base + 32); ++i)
+                if (ref[i].id != kMiss) hl.push_back(i);
+            const size_t nh = hl.size(), cbase = next.size();
+            next.resize(cbase + nh * m);
+            for (size_t rank = 0; rank < nh; ++rank) {
+                const size_t i = hl[rank];
+                const float* q = &sc.tris.isect[size_t(ref[i].id) * 16];
+                float nrm[3] = {q[3], q[4], q[5]}, p2[3];
+                for (int c = 0; c < 3; ++c) p2[c] = (wave[i].o[c] + ref[i].r * wave[i].d[c]) + 0.0001f * nrm[c];
+                float a[3] = {std::fabs(nrm[0]) < 0.9f ? 1.f : 0.f, std::fabs(nrm[0]) < 0.9f ? 0.f : 1.f, 0.f};
+                float t1[3] = {nrm[1] * a[2] - nrm[2] * a[1], nrm[2] * a[0] - nrm[0] * a[2], nrm[0] * a[1] - nrm[1] * a[0]};
+                const float l1 = std::sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+                for (int c = 0; c < 3; ++c) t1[c] /= l1;
+                float t2[3] = {nrm[1] * t1[2] - nrm[2] * t1[1], nrm[2] * t1[0] - nrm[0] * t1[2], nrm[0] * t1[1] - nrm[1] * t1[0]};
+                for (int k = 0; k < m; ++k) {
+                    const float u1 = U(rng), u2 = U(rng);
+                    const float z = u1, rr = std::sqrt(std::max(0.f, 1.f - z * z)), phi = 6.2831853f * u2;
+                    const float lx = rr * std::cos(phi), ly = rr * std::sin(phi);
+                    Ray ch;
+                    for (int c = 0; c < 3; ++c) {
+                        ch.o[c] = p2[c];
+                        ch.d[c] = t1[c] * lx + t2[c] * ly + nrm[c] * z;
+                    }
+                    next[cbase + k * nh + rank] = ch;
+                }
+            }
+        }
+        wave.swap(next);
+        if (wave.empty()) break;
+    }
+    return 0;
+}

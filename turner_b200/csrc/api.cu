@@ -8,6 +8,7 @@
 #include "kdtree_build.h"
 #include "kernels.cuh"
 #include "traverse_persistent.cuh"
+#include "traverse_pooled.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
@@ -72,6 +73,7 @@ struct DeviceScene {
     void* d_isect_hot = nullptr;
     void* d_isect_cold = nullptr;
     void* d_tri_box = nullptr;
+    void* d_planes = nullptr; // float4 per triangle: unit normal, n.v0 -- the pre-filter record of the pooled kernels
     void* d_shade = nullptr;
     void* d_mirror = nullptr;
     uint32_t* d_child_slot = nullptr; // raytracer: child-ray slot of every shadow query
@@ -92,6 +94,7 @@ struct DeviceScene {
     uint32_t treelet_pairs = 0; // node pairs of the top treelet present in pnodes (<= kTreeletNodes / 2)
     bool two_pass = true; // leaf evaluation schedule of the persistent kernels (small leaves: two-pass)
     int grid_closest = 0, grid_shadow = 0, grid_plain = 0; // persistent grids: resident CTAs per SM x SMs
+    int grid_pooled[3] = {0, 0, 0};                        // same for trace_pooled_kernel<MODE>
     unsigned long long* d_hitcount = nullptr;
     unsigned long long* d_visits = nullptr; // [6]: closest inner/leaf/tri, shadow inner/leaf/tri
     float2* d_jitter = nullptr;
@@ -113,6 +116,7 @@ struct DeviceScene {
         cudaFree(d_isect_hot);
         cudaFree(d_isect_cold);
         cudaFree(d_tri_box);
+        cudaFree(d_planes);
         cudaFree(d_shade);
         cudaFree(d_mirror);
         cudaFree(d_child_slot);
@@ -234,6 +238,16 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
             }
         }
         CUDA_TRY(up(&ds->d_tri_box, tb.data(), tb.size() * sizeof(float)));
+        // plane records of the pooled kernels' pre-filter: (n, dp), dp = n.v0 accumulated in double and rounded once
+        std::vector<float> pl(nt * 4);
+        for (size_t i = 0; i < nt; ++i) {
+            const float* q = &sc->tris.isect[i * 16]; // v0.xyz n.xyz ...
+            pl[i * 4] = q[3];
+            pl[i * 4 + 1] = q[4];
+            pl[i * 4 + 2] = q[5];
+            pl[i * 4 + 3] = static_cast<float>(static_cast<double>(q[3]) * q[0] + static_cast<double>(q[4]) * q[1] + static_cast<double>(q[5]) * q[2]);
+        }
+        CUDA_TRY(up(&ds->d_planes, pl.data(), pl.size() * sizeof(float)));
     }
     CUDA_TRY(up(&ds->d_shade, sc->tris.shade.data(), sc->tris.shade.size() * sizeof(float)));
     CUDA_TRY(up(&ds->d_mirror, sc->tris.mirror.data(), sc->tris.mirror.size() * sizeof(float)));
@@ -278,6 +292,13 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
         b0 = std::min(b0, w0);
         b1 = std::min(b1, w1);
         b2 = std::min(b2, w2);
+        int p0 = 0, p1 = 0, p2 = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p0, trace_pooled_kernel<0>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p1, trace_pooled_kernel<1>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, trace_pooled_kernel<2>, 128, 0));
+        ds->grid_pooled[0] = std::max(1, p0) * prop.multiProcessorCount;
+        ds->grid_pooled[1] = std::max(1, p1) * prop.multiProcessorCount;
+        ds->grid_pooled[2] = std::max(1, p2) * prop.multiProcessorCount;
         ds->grid_closest = std::max(1, b0) * prop.multiProcessorCount;
         ds->grid_shadow = std::max(1, b1) * prop.multiProcessorCount;
         ds->grid_plain = std::max(1, b2) * prop.multiProcessorCount;
@@ -308,17 +329,14 @@ static inline unsigned persistent_grid(int full, uint64_t n) {
     return static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(static_cast<uint64_t>(full), need)));
 }
 
-// production = one-thread-per-ray traversal kernels; TRN_PERSISTENT=1 selects the persistent-warp variant with lane
-// refill (traverse_persistent.cuh; same results, measured slower on both bench workloads -- profiles/README.md)
 // Scheduling of rays onto lanes (results are identical in every mode; profiles/README.md has the A/B numbers):
-//   closest-hit waves: persistent warps with lane refill, while-while quantum (mode 2) -- +26 % over one thread per ray
-//   shadow waves:      one thread per ray (mode 0) -- short any-hit walks, refill overhead does not pay
-// TRN_PERSISTENT=0|2 forces one mode for both kinds of wave.
-static int persistent_mode(bool shadow) {
-    const char* v = std::getenv("TRN_PERSISTENT");
-    if (v) return std::atoi(v) != 0 ? 2 : 0;
-    return shadow ? 0 : 2;
-}
+//   3  pooled kernel (traverse_pooled.cuh): speculative walk + warp-pooled triangle tests -- production for trees with
+//      small leaves, closest-hit and shadow waves alike
+//   2  persistent warps with lane refill, while-while quantum (traverse_persistent.cuh) -- closest-hit waves of scenes
+//      that are a few big leaves (cornell_box)
+//   0  one thread per ray (kernels.cuh) -- shadow waves of those scenes
+// TRN_PERSISTENT=0|2|3 forces one mode for both kinds of wave.
+static int persistent_mode(const struct DeviceScene* ds, bool shadow);
 
 static inline uint32_t pool_chunk_for(const DeviceScene* ds, uint64_t n) {
     (void)ds;
@@ -332,6 +350,64 @@ static uint64_t env_u64(const char* name, uint64_t dflt) {
     const char* v = std::getenv(name);
     if (!v || !*v) return dflt;
     return std::strtoull(v, nullptr, 10);
+}
+
+static inline unsigned blocks_for(uint64_t n, unsigned bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
+
+static int persistent_mode(const DeviceScene* ds, bool shadow) {
+    const char* v = std::getenv("TRN_PERSISTENT");
+    if (v && *v) {
+        const int m = std::atoi(v);
+        return m == 3 ? 3 : (m != 0 ? 2 : 0);
+    }
+    if (ds->two_pass) return 3;
+    return shadow ? 0 : 2;
+}
+
+// closest-hit traversal of n rays (wave arrays ra/rb, or plain o/d arrays) into hits, in the given scheduling mode
+static void launch_closest(DeviceScene* ds, int mode, cudaStream_t stream, const float4* ra, const float4* rb, const float* po,
+                           const float* pd, uint32_t n, uint32_t* cursor, uint4* hits, const uint32_t* order = nullptr) {
+    const bool plain = po != nullptr;
+    if (mode == 3) {
+        const int refill = static_cast<int>(env_u64("TRN_PQ_REFILL", 24)), iters = static_cast<int>(env_u64("TRN_PQ_WALK", 12));
+        if (plain)
+            trace_pooled_kernel<2><<<persistent_grid(ds->grid_pooled[2], n), 128, 0, stream>>>(
+                ds->dev, static_cast<const float4*>(ds->d_planes), nullptr, nullptr, nullptr, po, pd, n, nullptr, cursor, hits, nullptr,
+                refill, iters, pool_chunk_for(ds, n));
+        else
+            trace_pooled_kernel<0><<<persistent_grid(ds->grid_pooled[0], n), 128, 0, stream>>>(
+                ds->dev, static_cast<const float4*>(ds->d_planes), ra, rb, nullptr, nullptr, nullptr, n, nullptr, cursor, hits, nullptr,
+                refill, iters, pool_chunk_for(ds, n));
+    } else if (mode == 2) {
+        const int refill = static_cast<int>(env_u64("TRN_REFILL", 28)), quanta = static_cast<int>(env_u64("TRN_QUANTA", 2));
+        if (plain)
+            TRN_LAUNCH_WW(2, ds->two_pass, persistent_grid(ds->grid_plain, n), stream, ds->dev, nullptr, nullptr, nullptr, po, pd, n,
+                          nullptr, cursor, hits, nullptr, refill, quanta, nullptr, ds->treelet_pairs, pool_chunk_for(ds, n));
+        else
+            TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), stream, ds->dev, ra, rb, nullptr, nullptr, nullptr, n,
+                          nullptr, cursor, hits, nullptr, refill, quanta, order, ds->treelet_pairs, pool_chunk_for(ds, n));
+    } else if (plain) {
+        trace_closest_plain_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, po, pd, n, hits);
+    } else {
+        trace_closest_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ra, rb, n, hits);
+    }
+}
+
+// any-hit traversal of the shadow wave built by shade_bounce_kernel (count in counters->shadow_count, at most n_max)
+static void launch_shadow(DeviceScene* ds, int mode, cudaStream_t stream, uint32_t n_max, WaveCounters* counters, float4* acc) {
+    if (mode == 3) {
+        trace_pooled_kernel<1><<<persistent_grid(ds->grid_pooled[1], n_max), 128, 0, stream>>>(
+            ds->dev, static_cast<const float4*>(ds->d_planes), ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0,
+            &counters->shadow_count, &counters->shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_PQ_REFILL", 24)),
+            static_cast<int>(env_u64("TRN_PQ_WALK", 12)), pool_chunk_for(ds, n_max));
+    } else if (mode == 2) {
+        TRN_LAUNCH_WW(1, ds->two_pass, persistent_grid(ds->grid_shadow, n_max), stream, ds->dev, ds->shadow.a, ds->shadow.b,
+                      ds->shadow.c, nullptr, nullptr, 0, &counters->shadow_count, &counters->shadow_cursor, nullptr, acc,
+                      static_cast<int>(env_u64("TRN_REFILL", 26)), static_cast<int>(env_u64("TRN_QUANTA", 2)), nullptr,
+                      ds->treelet_pairs, pool_chunk_for(ds, n_max));
+    } else {
+        trace_shadow_kernel<<<blocks_for(n_max, 128), 128, 0, stream>>>(ds->dev, ds->shadow, counters, acc);
+    }
 }
 
 // wave buffers: `levels` ray waves of `cap` rays + one shadow wave + one hit buffer
@@ -493,7 +569,6 @@ struct KernelTimer {
     }
 };
 
-static inline unsigned blocks_for(uint64_t n, unsigned bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
 
 // The wavefront over one device: primaries in batches; per batch a depth-first walk over waves.
 // A wave at depth d is processed in chunks small enough that its children (<= m per ray) fit the next
@@ -510,12 +585,13 @@ struct Renderer {
     uint64_t rays = 0, prim = 0, shadow = 0, launches = 0;
     uint64_t trace_launches = 0, trace_queries = 0, shadow_launches = 0;
     bool counting = g_counting.load() != 0;
-    int mode_closest = persistent_mode(false), mode_shadow = persistent_mode(true);
+    int mode_closest, mode_shadow;
     bool sort_rays = env_u64("TRN_SORT", 0) != 0 && ds->two_pass; // experiment: (octant, Morton) order for secondary waves; measured no gain (profiles/README.md)
     uint64_t cap;
 
     Renderer(DeviceScene* d, const FrameParams& f, int integ, float4* a, cudaStream_t s)
-        : ds(d), fp(f), integrator(integ), acc(a), stream(s), timer(s), cap(d->wave_cap) {}
+        : ds(d), fp(f), integrator(integ), acc(a), stream(s), timer(s), mode_closest(persistent_mode(d, false)),
+          mode_shadow(persistent_mode(d, true)), cap(d->wave_cap) {}
 
     int next_slot(uint32_t* out) { return alloc_slot(ds, stream, out); }
 
@@ -545,12 +621,8 @@ struct Renderer {
             timer.begin(0);
             if (counting)
                 trace_closest_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits, ds->d_visits);
-            else if (mode_closest == 2)
-                TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), stream,
-                    ds->dev, w.a, w.b, nullptr, nullptr, nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr,
-                    static_cast<int>(env_u64("TRN_REFILL", 28)), static_cast<int>(env_u64("TRN_QUANTA", 2)), order, ds->treelet_pairs, pool_chunk_for(ds, n));
             else
-                trace_closest_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits);
+                launch_closest(ds, mode_closest, stream, w.a, w.b, nullptr, nullptr, n, &ds->d_counters[cs].trace_cursor, ds->d_hits, order);
             timer.end();
             ++launches;
             ++trace_launches;
@@ -577,13 +649,8 @@ struct Renderer {
                 if (counting)
                     trace_shadow_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_counters + cs, acc,
                                                                                        ds->d_visits + 3);
-                else if (mode_shadow == 2)
-                    TRN_LAUNCH_WW(1, ds->two_pass, persistent_grid(ds->grid_shadow, n), stream,
-                        ds->dev, ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0, &ds->d_counters[cs].shadow_count,
-                        &ds->d_counters[cs].shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_REFILL", 26)),
-                        static_cast<int>(env_u64("TRN_QUANTA", 2)), nullptr, ds->treelet_pairs, pool_chunk_for(ds, n));
                 else
-                    trace_shadow_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_counters + cs, acc);
+                    launch_shadow(ds, mode_shadow, stream, n, ds->d_counters + cs, acc);
                 timer.end();
                 ++launches;
                 ++shadow_launches;
@@ -605,11 +672,7 @@ struct Renderer {
         int rc = next_slot(&cs);
         if (rc) return rc;
         timer.begin(0);
-        if (mode_closest == 2)
-            TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), stream, ds->dev, wave.a, wave.b, nullptr, nullptr,
-                          nullptr, n, nullptr, &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2, nullptr, ds->treelet_pairs, pool_chunk_for(ds, n));
-        else
-            trace_closest_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, wave.a, wave.b, n, ds->d_hits);
+        launch_closest(ds, mode_closest, stream, wave.a, wave.b, nullptr, nullptr, n, &ds->d_counters[cs].trace_cursor, ds->d_hits);
         timer.end();
         ++launches;
         ++trace_launches;
@@ -886,14 +949,12 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
         CUDA_TRY(cudaMemcpyAsync(d_d, dirs + 3 * off, size_t(c) * 12, cudaMemcpyHostToDevice, ds->stream));
         if (counts3)
             trace_closest_plain_count_kernel<<<blocks_for(c, 128), 128, 0, ds->stream>>>(ds->dev, d_o, d_d, c, d_h, ds->d_visits);
-        else if (persistent_mode(false) != 0) {
+        else {
             uint32_t cs;
             int rc2 = alloc_slot(ds, ds->stream, &cs);
             if (rc2) return rc2;
-            TRN_LAUNCH_WW(2, ds->two_pass, persistent_grid(ds->grid_plain, c), ds->stream,
-                    ds->dev, nullptr, nullptr, nullptr, d_o, d_d, c, nullptr, &ds->d_counters[cs].trace_cursor, d_h, nullptr, 28, 2, nullptr, ds->treelet_pairs, pool_chunk_for(ds, c));
-        } else
-            trace_closest_plain_kernel<<<blocks_for(c, 128), 128, 0, ds->stream>>>(ds->dev, d_o, d_d, c, d_h);
+            launch_closest(ds, persistent_mode(ds, false), ds->stream, nullptr, nullptr, d_o, d_d, c, &ds->d_counters[cs].trace_cursor, d_h);
+        }
         unpack_hits_kernel<<<blocks_for(c, 256), 256, 0, ds->stream>>>(d_h, c, d_ids, d_rst);
         CUDA_TRY(cudaMemcpyAsync(ids + off, d_ids, size_t(c) * 4, cudaMemcpyDeviceToHost, ds->stream));
         CUDA_TRY(cudaMemcpyAsync(rst + 3 * off, d_rst, size_t(c) * 12, cudaMemcpyDeviceToHost, ds->stream));
@@ -937,15 +998,12 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
     for (uint64_t first = 0; first < total; first += cap) {
         const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(cap, total - first));
         raygen_kernel<<<blocks_for(n, 256), 256, 0, ds->stream>>>(fp, ds->d_jitter, first, n, ds->waves[0]);
-        if (persistent_mode(false) != 0) {
+        {
             uint32_t cs;
             rc = alloc_slot(ds, ds->stream, &cs);
             if (rc) return rc;
-            TRN_LAUNCH_WW(0, ds->two_pass, persistent_grid(ds->grid_closest, n), ds->stream,
-                    ds->dev, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, nullptr, n, nullptr,
-                    &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, 28, 2, nullptr, ds->treelet_pairs, pool_chunk_for(ds, n));
-        } else {
-            trace_closest_kernel<<<blocks_for(n, 128), 128, 0, ds->stream>>>(ds->dev, ds->waves[0].a, ds->waves[0].b, n, ds->d_hits);
+            launch_closest(ds, persistent_mode(ds, false), ds->stream, ds->waves[0].a, ds->waves[0].b, nullptr, nullptr, n,
+                           &ds->d_counters[cs].trace_cursor, ds->d_hits);
         }
         unpack_hits_kernel<<<blocks_for(n, 256), 256, 0, ds->stream>>>(ds->d_hits, n, d_ids, d_rst);
         CUDA_TRY(cudaMemcpyAsync(ids + first, d_ids, size_t(n) * 4, cudaMemcpyDeviceToHost, ds->stream));
