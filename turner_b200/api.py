@@ -99,7 +99,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no fallback path)" % LIB_PATH)
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(os.environ.get("TRN_LIB", LIB_PATH))  # TRN_LIB: A/B builds during kernel development
         L.trn_last_error.restype = C.c_char_p
         L.trn_device_count.restype = C.c_int32
         L.trn_scene_create.argtypes = [_f32p, _f32p, _f32p, C.c_uint32, C.POINTER(C.c_void_p)]

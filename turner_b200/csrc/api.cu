@@ -373,11 +373,11 @@ static void launch_closest(DeviceScene* ds, int mode, cudaStream_t stream, const
         if (plain)
             trace_pooled_kernel<2><<<persistent_grid(ds->grid_pooled[2], n), 128, 0, stream>>>(
                 ds->dev, static_cast<const float4*>(ds->d_planes), nullptr, nullptr, nullptr, po, pd, n, nullptr, cursor, hits, nullptr,
-                refill, iters, pool_chunk_for(ds, n));
+                refill, iters, pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 8)));
         else
             trace_pooled_kernel<0><<<persistent_grid(ds->grid_pooled[0], n), 128, 0, stream>>>(
                 ds->dev, static_cast<const float4*>(ds->d_planes), ra, rb, nullptr, nullptr, nullptr, n, nullptr, cursor, hits, nullptr,
-                refill, iters, pool_chunk_for(ds, n));
+                refill, iters, pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 8)));
     } else if (mode == 2) {
         const int refill = static_cast<int>(env_u64("TRN_REFILL", 28)), quanta = static_cast<int>(env_u64("TRN_QUANTA", 2));
         if (plain)
@@ -399,7 +399,7 @@ static void launch_shadow(DeviceScene* ds, int mode, cudaStream_t stream, uint32
         trace_pooled_kernel<1><<<persistent_grid(ds->grid_pooled[1], n_max), 128, 0, stream>>>(
             ds->dev, static_cast<const float4*>(ds->d_planes), ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0,
             &counters->shadow_count, &counters->shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_PQ_REFILL", 24)),
-            static_cast<int>(env_u64("TRN_PQ_WALK", 12)), pool_chunk_for(ds, n_max));
+            static_cast<int>(env_u64("TRN_PQ_WALK", 12)), pool_chunk_for(ds, n_max), static_cast<int>(env_u64("TRN_PQ_GATE", 8)));
     } else if (mode == 2) {
         TRN_LAUNCH_WW(1, ds->two_pass, persistent_grid(ds->grid_shadow, n_max), stream, ds->dev, ds->shadow.a, ds->shadow.b,
                       ds->shadow.c, nullptr, nullptr, 0, &counters->shadow_count, &counters->shadow_cursor, nullptr, acc,
@@ -526,6 +526,7 @@ static FrameParams make_frame(const trn_camera* cam, const trn_render_config* cf
     fp.max_depth = cfg->max_depth;
     std::memcpy(fp.bg, cfg->bg_rgba, sizeof fp.bg);
     fp.has_light = cfg->num_lights;
+    fp.child_major = static_cast<int32_t>(env_u64("TRN_CHILD_MAJOR", 0));
     std::memcpy(fp.light_pos, cfg->light.pos, sizeof fp.light_pos);
     std::memcpy(fp.light_rgba, cfg->light.rgba, sizeof fp.light_rgba);
     fp.max_visibility = cfg->max_visibility;

@@ -73,6 +73,7 @@ struct FrameParams {
     float max_visibility;
     float shadow_intensity;
     uint64_t seed;
+    int32_t child_major; // next-wave layout inside a warp's block: 1 = the m children of a hit adjacent, 0 = k-major
 };
 
 // -------------------------------------------------------------------------- RNG
@@ -639,7 +640,10 @@ __global__ void __launch_bounds__(256) shade_bounce_kernel(DevScene sc, FramePar
         const float dy = m10 * lx + m11 * ly + m12 * lz;
         const float dz = m20 * lx + m21 * ly + m22 * lz;
         const float wgt = (2.f * u1) / fm; // pathtracer.cpp:84,88,100-101: rho * 2 * (cos / m)
-        const uint32_t slot = cbase + static_cast<uint32_t>(k) * nh + rank;
+        // k-major: every store of the loop is one contiguous run; child-major: the m rays that share an origin sit in
+        // adjacent lanes of the next wave, so their walks down the tree touch the same lines (profiles/README.md)
+        const uint32_t slot = fp.child_major ? cbase + rank * static_cast<uint32_t>(m) + static_cast<uint32_t>(k)
+                                             : cbase + static_cast<uint32_t>(k) * nh + rank;
         __stcs(&next.a[slot], make_float4(p2x, p2y, p2z, dx));
         __stcs(&next.b[slot], make_float4(dy, dz, __uint_as_float(rel), __uint_as_float(child)));
         __stcs(&next.T[slot], make_float4(T.x * (rho.x * wgt), T.y * (rho.y * wgt), T.z * (rho.z * wgt), T.w * (rho.w * wgt)));

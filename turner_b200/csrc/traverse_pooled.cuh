@@ -28,22 +28,26 @@
 
 namespace trn {
 
-#ifndef TRN_PQ_CHUNKS
-#define TRN_PQ_CHUNKS 128 // chunk descriptors per warp queue
+#ifndef TRN_PQ_LEAVES
+#define TRN_PQ_LEAVES 64 // leaf descriptors per warp queue
 #endif
 #ifndef TRN_PQ_MINBLOCKS
 #define TRN_PQ_MINBLOCKS 8
 #endif
-constexpr int kPqChunks = TRN_PQ_CHUNKS;
-constexpr int kPqChunkTris = 4;                  // triangle references per chunk
-constexpr int kPqMaxAppend = 16;                 // chunks a lane may queue per walk iteration (bigger leaves: instalments)
+constexpr int kPqLeaves = TRN_PQ_LEAVES;
+constexpr int kPqChunkTris = 4;                  // triangle references a lane tests per TEST round
 constexpr int kPqSurv = 32 + 32 * kPqChunkTris; // survivors: < 32 left over + one TEST round
 
 struct PooledWarpSmem {
-    float4 ray[64];          // [2*lane] = o.xyz, E   [2*lane+1] = d.xyz, F   (E, F: error bounds of the pre-filter)
-    uint4 chunk[kPqChunks];  // first ref, count | owner << 8, lo bits, hi bits (parameter range of the cell)
+    float4 ray_o[32];        // o.xyz, E   (E, F: error bounds of the pre-filter)
+    float4 ray_d[32];        // d.xyz, F
+    uint4 leaf[kPqLeaves];   // first ref, count | owner << 24, lo bits, hi bits (parameter range of the cell)
     uint2 surv[kPqSurv];     // triangle id, owner | seq << 5
-    uint32_t nchunk, nvalid, nsurv, pad;
+    uint4 best[32];          // per lane: best hit so far (id, r, s, t) -- cold state kept out of the registers
+    uint32_t ray_idx[32];    // per lane: index of its ray in the wave
+    float walk_o[3][32];     // per lane: origin and reciprocal direction by axis -- the WALK step reads the split axis'
+    float walk_i[3][32];     // component with one conflict-free LDS instead of holding six registers + selects
+    uint32_t nleaf, pad[3];
 };
 
 // exact-zero direction component: the reference's schedule verbatim (see traverse_pairs<>)
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
     DevScene sc, const float4* __restrict__ planes, const float4* __restrict__ ra, const float4* __restrict__ rb,
     const float4* __restrict__ rc, const float* __restrict__ po, const float* __restrict__ pd, uint32_t count_arg,
     const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor, uint4* __restrict__ hits, float4* __restrict__ acc,
-    int refill_below, int walk_iters, uint32_t pool_chunk) {
+    int refill_below, int walk_iters, uint32_t pool_chunk, int leaf_gate) {
     constexpr bool ANY = MODE == 1;
     constexpr unsigned kFull = 0xffffffffu;
     __shared__ PooledWarpSmem smem[4];
@@ -69,11 +73,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t count = count_ptr ? *count_ptr : count_arg;
-    if (lane == 0) {
-        sm.nchunk = 0;
-        sm.nvalid = kPqChunks;
-        sm.nsurv = 0;
-    }
+    if (lane == 0) sm.nleaf = 0;
     __syncwarp();
     float scale = 0.f; // largest |coordinate| of the scene box
 #pragma unroll
@@ -81,11 +81,10 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
 
     uint4 stack[kStackDepth];
     int sp = 0;
-    float ox = 0, oy = 0, oz = 0, ix = 0, iy = 0, iz = 0;
     float tenter = 0, texit = 0, tmax_any = 0, last_texit = -kFltMax;
     uint2 n = make_uint2(0u, 3u);
-    uint32_t best_id = kMiss, best_seq = 0, idx = 0, leaf_off = 0;
-    float best_r = kFltMax, best_s = 0.f, best_t = 0.f;
+    uint32_t best_seq = 0;
+    float best_r = kFltMax; // mirrors sm.best[lane].y (kFltMax while there is no hit)
     bool busy = false, walking = false, occluded = false, exhausted = false;
     uint32_t pool_next = 0, pool_end = 0;
 
@@ -109,8 +108,8 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                 const uint32_t take = min(static_cast<uint32_t>(__popc(need)), pool_end - pool_next);
                 const uint32_t rank = __popc(need & lt_mask);
                 if (!busy && rank < take) {
-                    idx = pool_next + rank;
-                    float dx, dy, dz;
+                    const uint32_t idx = pool_next + rank;
+                    float ox, oy, oz, dx, dy, dz;
                     if (MODE == 2) {
                         ox = po[3 * idx]; oy = po[3 * idx + 1]; oz = po[3 * idx + 2];
                         dx = pd[3 * idx]; dy = pd[3 * idx + 1]; dz = pd[3 * idx + 2];
@@ -128,9 +127,8 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                         hit = trace_axis_parallel<ANY>(sc, ox, oy, oz, dx, dy, dz, tmax_any, h);
                         done = true;
                     } else {
-                        ix = 1 / dx; // fix_direction (lib/kdtree.cpp:503-511) changes nothing: no component is zero
-                        iy = 1 / dy;
-                        iz = 1 / dz;
+                        // fix_direction (lib/kdtree.cpp:503-511) changes nothing: no component is zero
+                        const float ix = 1 / dx, iy = 1 / dy, iz = 1 / dz;
                         // intersect_ray_box, lib/intersection.h:105-128
                         float tx1 = (sc.lo[0] - ox) * ix, tx2 = (sc.hi[0] - ox) * ix;
                         float t0 = fminf(tx1, tx2), t1 = fmaxf(tx1, tx2);
@@ -147,13 +145,11 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                             texit = t1;
                             sp = 0;
                             n = __ldg(&sc.pnodes[0]);
-                            best_id = kMiss;
                             best_r = kFltMax;
-                            best_s = 0.f;
-                            best_t = 0.f;
                             best_seq = 0;
+                            sm.best[lane] = make_uint4(kMiss, __float_as_uint(kFltMax), 0u, 0u);
+                            sm.ray_idx[lane] = idx;
                             last_texit = -kFltMax;
-                            leaf_off = 0;
                             occluded = false;
                             busy = true;
                             walking = !(ANY && tenter > tmax_any);
@@ -163,8 +159,10 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                             // n.d within 6 u |d|_1. E and F carry a safety factor of ~3.
                             const float E = 1.9073486e-6f * (3.f * scale + (fabsf(ox) + fabsf(oy) + fabsf(oz)));
                             const float F = 9.5367432e-7f * (fabsf(dx) + fabsf(dy) + fabsf(dz));
-                            sm.ray[2 * lane] = make_float4(ox, oy, oz, E);
-                            sm.ray[2 * lane + 1] = make_float4(dx, dy, dz, F);
+                            sm.ray_o[lane] = make_float4(ox, oy, oz, E);
+                            sm.ray_d[lane] = make_float4(dx, dy, dz, F);
+                            sm.walk_o[0][lane] = ox; sm.walk_o[1][lane] = oy; sm.walk_o[2][lane] = oz;
+                            sm.walk_i[0][lane] = ix; sm.walk_i[1][lane] = iy; sm.walk_i[2][lane] = iz;
                         }
                     }
                     if (done) {
@@ -186,61 +184,41 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
         __syncwarp();
 
         // ------------------------------------------------------------------ WALK
+        // Every iteration the lanes at inner nodes take one step. The lanes that have reached a leaf queue it and pop --
+        // but that block is only issued when at least leaf_gate lanes wait at a leaf (or no lane can step): it is as
+        // long as the step itself and would otherwise run for 4 of 32 lanes in nearly every iteration.
         bool blocked = false;
+        int it = 0;
 #pragma unroll 1
-        for (int it = 0; it < walk_iters; ++it) {
+        for (;;) {
             const bool can = busy && walking && !blocked;
-            if (!__any_sync(kFull, can)) break;
-            if (can) {
-                if ((n.y & 3u) != 3u) {
-                    // one inner-node step, lib/kdtree.cpp:540-563 on the sibling-pair layout (see traverse_pairs<>)
-                    const uint32_t ax = n.y & 3u;
-                    const float split = __uint_as_float(n.x);
-                    const uint4 pair = __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
-                    float o_ax = oz, i_ax = iz;
-                    if (ax == 0u) { o_ax = ox; i_ax = ix; }
-                    if (ax == 1u) { o_ax = oy; i_ax = iy; }
-                    const float t = (split - o_ax) * i_ax;
-                    const bool flip = (__float_as_uint(i_ax) >> 31) != 0u;
-                    const uint2 near = flip ? make_uint2(pair.z, pair.w) : make_uint2(pair.x, pair.y);
-                    const uint2 far = flip ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
-                    const bool near_only = texit < t;
-                    const bool far_only = !near_only && (t < tenter);
-                    const bool both = !near_only && !far_only;
-                    const bool go_far = far_only || (both && near.y == 3u);
-                    if (both && near.y != 3u && far.y != 3u) stack[sp++] = make_uint4(far.x, far.y, __float_as_uint(t), __float_as_uint(texit));
-                    n = go_far ? far : near;
-                    tenter = (both && go_far) ? t : tenter;
-                    texit = (both && !go_far) ? t : texit;
-                } else {
-                    // leaf: queue its triangle references as chunks; the parameter range of the cell (plus slack) travels
-                    // with them. A count-0 leaf (cut-off void) can only be the root of an empty tree.
-                    const uint32_t cnt = n.y >> 2;
-                    const uint32_t rem = cnt - leaf_off;
-                    const uint32_t ch = min((rem + kPqChunkTris - 1) / kPqChunkTris, static_cast<uint32_t>(kPqMaxAppend));
-                    bool leaf_done = true;
-                    if (ch > 0) {
-                        const uint32_t slot = atomicAdd(&sm.nchunk, ch);
-                        if (slot + ch <= kPqChunks) {
+            const bool at_leaf = can && (n.y & 3u) == 3u;
+            const unsigned lm = __ballot_sync(kFull, at_leaf);
+            const unsigned im = __ballot_sync(kFull, can && !at_leaf);
+            const bool last = it >= walk_iters || im == 0u;
+            if (lm != 0u && (last || __popc(lm) >= leaf_gate)) {
+                // leaf: queue it (one descriptor: reference range, owner, parameter range of the cell plus slack) and pop
+                // at once. One atomic reserves the slots of all lanes. A count-0 leaf (cut-off void) can only be the
+                // root of an empty tree.
+                const uint32_t cnt = n.y >> 2;
+                const unsigned want = __ballot_sync(kFull, at_leaf && cnt > 0u);
+                uint32_t slot0 = 0;
+                if (want != 0u && lane == static_cast<unsigned>(__ffs(want) - 1)) slot0 = atomicAdd(&sm.nleaf, static_cast<uint32_t>(__popc(want)));
+                slot0 = __shfl_sync(kFull, slot0, want ? __ffs(want) - 1 : 0);
+                if (at_leaf) {
+                    if (cnt > 0u) {
+                        const uint32_t slot = slot0 + __popc(want & lt_mask);
+                        if (slot < static_cast<uint32_t>(kPqLeaves)) {
                             float lo = tenter - kCellSlack * (fabsf(tenter) + 1.f);
                             float hi = texit + kCellSlack * (fabsf(texit) + 1.f);
                             lo = fmaxf(lo, 0.f);
                             hi = ANY ? fminf(hi, tmax_any) : fminf(hi, best_r);
-                            const uint32_t first = n.x + leaf_off;
-                            for (uint32_t k = 0; k < ch; ++k) {
-                                const uint32_t c = min(static_cast<uint32_t>(kPqChunkTris), rem - k * kPqChunkTris);
-                                sm.chunk[slot + k] = make_uint4(first + k * kPqChunkTris, c | (lane << 8), __float_as_uint(lo), __float_as_uint(hi));
-                            }
-                            leaf_off += ch * kPqChunkTris;
-                            leaf_done = leaf_off >= cnt;
+                            sm.leaf[slot] = make_uint4(n.x, cnt | (lane << 24), __float_as_uint(lo), __float_as_uint(hi));
                         } else {
-                            atomicMin(&sm.nvalid, slot); // queue full: everything from this slot on is unwritten
-                            blocked = true;
-                            leaf_done = false;
+                            blocked = true; // queue full: retry in the next cycle
                         }
                     }
-                    if (leaf_done) {
-                        leaf_off = 0;
+                    if (!blocked) {
                         last_texit = texit;
                         if (sp == 0) {
                             walking = false;
@@ -255,16 +233,45 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                     }
                 }
             }
+            if (last) break;
+            ++it;
+            if (can && !at_leaf) {
+                // one inner-node step, lib/kdtree.cpp:540-563 on the sibling-pair layout (see traverse_pairs<>)
+                const uint32_t ax = n.y & 3u;
+                const float split = __uint_as_float(n.x);
+                const uint4 pair = __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
+                const float o_ax = sm.walk_o[ax][lane], i_ax = sm.walk_i[ax][lane];
+                const float t = (split - o_ax) * i_ax;
+                const bool flip = (__float_as_uint(i_ax) >> 31) != 0u;
+                const uint2 near = flip ? make_uint2(pair.z, pair.w) : make_uint2(pair.x, pair.y);
+                const uint2 far = flip ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
+                const bool near_only = texit < t;
+                const bool far_only = !near_only && (t < tenter);
+                const bool both = !near_only && !far_only;
+                const bool go_far = far_only || (both && near.y == 3u);
+                if (both && near.y != 3u && far.y != 3u) stack[sp++] = make_uint4(far.x, far.y, __float_as_uint(t), __float_as_uint(texit));
+                n = go_far ? far : near;
+                tenter = (both && go_far) ? t : tenter;
+                texit = (both && !go_far) ? t : texit;
+            }
         }
         __syncwarp();
 
         // ------------------------------------------------------------------ TEST (pre-filter) and EXACT rounds
-        const uint32_t nch = min(*reinterpret_cast<volatile uint32_t*>(&sm.nchunk), *reinterpret_cast<volatile uint32_t*>(&sm.nvalid));
-        uint32_t base = 0;
+        // The queued leaves are taken 32 at a time, one per lane; their triangle references are cut into chunks of 4
+        // and the chunks of the whole batch are dealt out 32 per round (a lane finds its chunk's leaf by a shuffle
+        // binary search over the running chunk totals), so that every lane tests 4 triangles per round whatever the
+        // leaf sizes are. Survivors go to the warp's survivor queue; whenever 32 are waiting (and at the end) they
+        // get the exact test, 32 at a time.
+        const uint32_t nleaf = min(*reinterpret_cast<volatile uint32_t*>(&sm.nleaf), static_cast<uint32_t>(kPqLeaves));
+        uint32_t ns = 0;        // survivors waiting (warp-uniform; only this loop appends)
+        uint32_t lb = 0;        // first leaf of the current batch
+        uint32_t base = 0, total = 0, P = 0; // chunk cursor / chunk count of the batch / inclusive chunk totals per lane
+        uint4 ld = make_uint4(0u, 0u, 0u, 0u);
+        bool have_batch = false;
         for (;;) {
-            const uint32_t ns = *reinterpret_cast<volatile uint32_t*>(&sm.nsurv);
-            __syncwarp();
-            if (ns >= 32u || (base >= nch && ns > 0u)) {
+            const bool more_tests = have_batch ? (base < total || lb + 32u < nleaf) : (lb < nleaf);
+            if (ns >= 32u || (!more_tests && ns > 0u)) {
                 // EXACT: the reference's operation sequence for up to 32 pooled survivors (taken from the tail)
                 const uint32_t take = min(32u, ns), sbase = ns - take;
                 bool pass = false;
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                 }
                 const float lim = __shfl_sync(kFull, ANY ? tmax_any : best_r, owner);
                 if (lane < take) {
-                    const float4 ro = sm.ray[2 * owner], rd = sm.ray[2 * owner + 1];
+                    const float4 ro = sm.ray_o[owner], rd = sm.ray_d[owner];
                     const float4* rec = sc.isect_hot + 2 * static_cast<size_t>(id);
                     const float4* rec2 = sc.isect_cold + 2 * static_cast<size_t>(id);
                     const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
@@ -286,8 +293,8 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                     const float denom = nx * rd.x + ny * rd.y + nz * rd.z; // intersect_ray_plane, lib/intersection.h:40-49
                     const float nom = nx * (q0.x - ro.x) + ny * (q0.y - ro.y) + nz * (q0.z - ro.z);
                     r = nom / denom;
-                    // r < 0 rejects (intersection.h:66); only a hit nearer than the owner's best (strictly: ties are
-                    // settled below), resp. within the light distance, matters
+                    // r < 0 rejects (intersection.h:66); only a hit not farther than the owner's best (ties are settled
+                    // below), resp. within the light distance, matters
                     if (denom != 0.f && r >= 0.f && r <= lim) {
                         const float4 q2 = __ldg(rec2), q3 = __ldg(rec2 + 1);
                         const float wx = (ro.x + r * rd.x) - q0.x, wy = (ro.y + r * rd.y) - q0.y, wz = (ro.z + r * rd.z) - q0.z; // :70-71
@@ -317,72 +324,113 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                         if (ANY) {
                             occluded = true;
                         } else if (r_ < best_r || (r_ == best_r && q_ < best_seq)) {
-                            best_id = id_;
                             best_r = r_;
-                            best_s = s_;
-                            best_t = t_;
                             best_seq = q_;
+                            sm.best[lane] = make_uint4(id_, __float_as_uint(r_), __float_as_uint(s_), __float_as_uint(t_));
                         }
                     }
                 }
-                if (lane == 0) sm.nsurv = sbase;
+                ns = sbase;
                 __syncwarp();
-            } else if (base < nch) {
+            } else if (more_tests) {
+                if (!have_batch || base >= total) {
+                    // next batch of up to 32 leaves: one descriptor per lane, inclusive scan of their chunk counts
+                    if (have_batch) lb += 32u;
+                    have_batch = true;
+                    ld = lb + lane < nleaf ? sm.leaf[lb + lane] : make_uint4(0u, 0u, 0u, 0u);
+                    P = ((ld.y & 0xffffffu) + kPqChunkTris - 1) / kPqChunkTris;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const uint32_t v = __shfl_up_sync(kFull, P, off);
+                        if (static_cast<int>(lane) >= off) P += v;
+                    }
+                    total = __shfl_sync(kFull, P, 31);
+                    base = 0;
+                    continue;
+                }
                 // TEST: one chunk per lane. Pre-filter: with a ~ n.d and b ~ n.(v0 - o) (FMA arithmetic, |a - denom| <= F,
                 // |b - nom| <= E for the reference's denom, nom), A = |a|, B = b * sign(a):
                 //   0 <= lo <= nom/denom <= hi   ==>   A <= F  or  (B + E >= lo (A - F)  and  B - E <= hi (A + F)).
                 // Triangles that fail cannot have their exact plane distance inside [lo, hi].
                 const uint32_t g = base + lane;
-                if (g < nch) {
-                    const uint4 d = sm.chunk[g];
-                    const uint32_t first = d.x, cnt = d.y & 0xffu, owner = d.y >> 8;
-                    const float lo = __uint_as_float(d.z), hi = __uint_as_float(d.w);
-                    const float4 ro = sm.ray[2 * owner], rd = sm.ray[2 * owner + 1];
+                // leaf of chunk g = number of lanes whose inclusive total is <= g
+                uint32_t j = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const uint32_t pj = __shfl_sync(kFull, P, (j + step - 1) & 31u);
+                    if (pj <= g) j += step;
+                }
+                j &= 31u; // g >= total (idle lane): any leaf, masked below
+                const uint32_t first = __shfl_sync(kFull, ld.x, j), cw = __shfl_sync(kFull, ld.y, j);
+                const float lo = __uint_as_float(__shfl_sync(kFull, ld.z, j)), hi = __uint_as_float(__shfl_sync(kFull, ld.w, j));
+                const uint32_t pend = __shfl_sync(kFull, P, j);
+                const uint32_t lcnt = cw & 0xffffffu, owner = cw >> 24;
+                const uint32_t sub = g - (pend - (lcnt + kPqChunkTris - 1) / kPqChunkTris); // chunk index inside the leaf
+                const uint32_t off0 = sub * kPqChunkTris;
+                const uint32_t cnt = g < total ? min(static_cast<uint32_t>(kPqChunkTris), lcnt - off0) : 0u;
+                uint32_t id0 = 0, id1 = 0, id2 = 0, id3 = 0, km = 0; // the chunk's triangle ids, bit k of km: triangle k survives
+                if (cnt > 0u) {
+                    const float4 ro = sm.ray_o[owner], rd = sm.ray_d[owner];
                     const float E = ro.w, F = rd.w;
                     const float c1 = fmaf(-lo, F, -E), c2 = fmaf(hi, F, E);
-                    for (uint32_t i = 0; i < cnt; i += 2) {
-                        const bool two = i + 1 < cnt;
-                        const uint32_t ida = __ldg(&sc.prefs[first + i]);
-                        const uint32_t idb = two ? __ldg(&sc.prefs[first + i + 1]) : ida;
-                        const float4 pa = __ldg(&planes[ida]), pb = __ldg(&planes[idb]);
+                    const uint32_t* refs = sc.prefs + first + off0;
+                    // all ids first, then all plane records: one id latency + one record latency per chunk
+                    id0 = __ldg(refs);
+                    id1 = cnt > 1u ? __ldg(refs + 1) : id0;
+                    id2 = cnt > 2u ? __ldg(refs + 2) : id0;
+                    id3 = cnt > 3u ? __ldg(refs + 3) : id0;
+                    const float4 p0 = __ldg(&planes[id0]), p1 = __ldg(&planes[id1]), p2 = __ldg(&planes[id2]), p3 = __ldg(&planes[id3]);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const float4 p = h ? pb : pa;
-                            const float a = fmaf(p.x, rd.x, fmaf(p.y, rd.y, p.z * rd.z));
-                            const float b = fmaf(-p.x, ro.x, fmaf(-p.y, ro.y, fmaf(-p.z, ro.z, p.w)));
-                            const float A = fabsf(a);
-                            const float B = __uint_as_float(__float_as_uint(b) ^ (__float_as_uint(a) & 0x80000000u));
-                            const bool keep = (h == 0 || two) && (A <= F || (B >= fmaf(lo, A, c1) && B <= fmaf(hi, A, c2)));
-                            if (keep) {
-                                const uint32_t sl = atomicAdd(&sm.nsurv, 1u);
-                                sm.surv[sl] = make_uint2(h ? idb : ida, owner | ((g * 8u + i + h + 1u) << 5));
-                            }
-                        }
+                    for (int k = 0; k < kPqChunkTris; ++k) {
+                        const float4 p = k == 0 ? p0 : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+                        const float a = fmaf(p.x, rd.x, fmaf(p.y, rd.y, p.z * rd.z));
+                        const float b = fmaf(-p.x, ro.x, fmaf(-p.y, ro.y, fmaf(-p.z, ro.z, p.w)));
+                        const float A = fabsf(a);
+                        const float B = __uint_as_float(__float_as_uint(b) ^ (__float_as_uint(a) & 0x80000000u));
+                        const bool keep = static_cast<uint32_t>(k) < cnt && (A <= F || (B >= fmaf(lo, A, c1) && B <= fmaf(hi, A, c2)));
+                        km |= keep ? (1u << k) : 0u;
                     }
                 }
+                const uint32_t nk = __popc(km);
+                // append the survivors of the round: exclusive scan of the per-lane counts, no atomics
+                uint32_t pos = nk;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t v = __shfl_up_sync(kFull, pos, off);
+                    if (static_cast<int>(lane) >= off) pos += v;
+                }
+                const uint32_t round_total = __shfl_sync(kFull, pos, 31);
+                pos = ns + pos - nk;
+                // seq = visiting order inside the cycle: (leaf slot in the queue, position in the leaf) + 1
+                const uint32_t seq0 = ((lb + j) << 20) + off0 + 1u;
+#pragma unroll
+                for (int k = 0; k < kPqChunkTris; ++k)
+                    if (km & (1u << k)) {
+                        const uint32_t id = k == 0 ? id0 : (k == 1 ? id1 : (k == 2 ? id2 : id3));
+                        sm.surv[pos + __popc(km & ((1u << k) - 1u))] = make_uint2(id, owner | ((seq0 + k) << 5));
+                    }
+                ns += round_total;
                 base += 32u;
                 __syncwarp();
             } else {
                 break;
             }
         }
-        if (lane == 0) {
-            sm.nchunk = 0;
-            sm.nvalid = kPqChunks;
-        }
+        if (lane == 0) sm.nleaf = 0;
 
         // ------------------------------------------------------------------ finished rays
         if (busy) {
             best_seq = 0;
             bool finished;
             if (ANY) finished = occluded || !walking;
-            else finished = !walking || (best_id != kMiss && (best_r <= last_texit || best_r < tenter));
+            else finished = !walking || (best_r < kFltMax && (best_r <= last_texit || best_r < tenter));
             if (finished) {
                 busy = false;
+                const uint32_t idx = sm.ray_idx[lane];
                 if (ANY) {
                     if (!occluded) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx]));
                 } else {
-                    __stcs(&hits[idx], make_uint4(best_id, __float_as_uint(best_r), __float_as_uint(best_s), __float_as_uint(best_t)));
+                    __stcs(&hits[idx], sm.best[lane]);
                 }
             }
         }
