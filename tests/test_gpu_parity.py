@@ -481,3 +481,44 @@ def test_against_reference_generated_golden_fixtures(api, scenes):
         ref = gold[name + "/pt_sum"]
         assert st.prim_rays == int(gold[name + "/pt_rays"][1])
         assert abs(img.mean() - ref.mean()) < 0.08 * max(ref.mean(), 1e-3)
+
+
+def test_all_scheduling_modes_bit_exact(api, ob, scenes, monkeypatch):
+    # The three lane schedules of the traversal (one thread per ray, persistent while-while warps, pooled walk/test/exact
+    # cycle with the division-free plane pre-filter) must return the same bits: ids and (r,s,t) against the reference's
+    # exhaustive schedule, on trees with small leaves, with big leaves (a 36-triangle single leaf: chunked by the pooled
+    # kernel), on axis-aligned tiles (exact ties) and with exact-zero direction components.
+    cases = [scenes.cubesphere(48), scenes.random_soup(5000, 2), scenes.fixture("cornell_box"), scenes.fixture("furnace_test"),
+             scenes.tiled_box(8), scenes.four_triangles()]
+    for sc in cases:
+        o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+        p = api.Scene.from_dict(sc)
+        for inside in (False, True):
+            ro, rd = scenes.random_rays(sc, 60000, seed=31, inside=inside)
+            rd[::17, 0] = 0
+            rd[::19, 2] = 0
+            i_o, r_o = o.intersect(ro, rd, 0)
+            for mode in ("0", "2", "3"):
+                monkeypatch.setenv("TRN_PERSISTENT", mode)
+                i_g, r_g = p.intersect(ro, rd)
+                assert np.array_equal(i_g, i_o), (sc["name"], inside, mode, int((i_g != i_o).sum()))
+                assert np.array_equal(bits(r_g), bits(r_o)), (sc["name"], inside, mode)
+    monkeypatch.delenv("TRN_PERSISTENT")
+
+
+def test_pooled_kernel_renders_like_the_others(api, scenes, monkeypatch):
+    # closest-hit + shadow waves through every schedule: same ray / shadow-ray counts, same image up to the fp32 order
+    # of the accumulation atomics
+    for sc, width in ((scenes.cubesphere(48), 256), (scenes.fixture("cornell_box"), 128)):
+        p = api.Scene.from_dict(sc)
+        cam, cfg = api.make_config(sc, width, max_depth=3, mc_samples=4, pixel_samples=4, seed=5)
+        out = {}
+        for mode in ("0", "2", "3"):
+            monkeypatch.setenv("TRN_PERSISTENT", mode)
+            img, st = p.render(cam, cfg)
+            out[mode] = (img.copy(), st.rays, st.shadow_rays)
+        for mode in ("2", "3"):
+            assert out[mode][1:] == out["0"][1:], (sc["name"], mode)
+            d = np.abs(out[mode][0] - out["0"][0])
+            assert (d <= 2e-4 * (1 + np.abs(out["0"][0]))).all(), (sc["name"], mode, float(d.max()))
+    monkeypatch.delenv("TRN_PERSISTENT")

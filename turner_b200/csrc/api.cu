@@ -93,6 +93,7 @@ struct DeviceScene {
     uint32_t ring_pos = 0;
     uint32_t treelet_pairs = 0; // node pairs of the top treelet present in pnodes (<= kTreeletNodes / 2)
     bool two_pass = true; // leaf evaluation schedule of the persistent kernels (small leaves: two-pass)
+    bool pooled = true;   // pooled kernel for both kinds of wave (a real tree: many leaves of moderate size)
     int grid_closest = 0, grid_shadow = 0, grid_plain = 0; // persistent grids: resident CTAs per SM x SMs
     int grid_pooled[3] = {0, 0, 0};                        // same for trace_pooled_kernel<MODE>
     unsigned long long* d_hitcount = nullptr;
@@ -272,7 +273,12 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
             if ((y & 3u) == 3u && (y >> 2) > 0) ++leaves;
         }
         ds->treelet_pairs = static_cast<uint32_t>(std::min<size_t>(sc->tree.pair_nodes.size(), KdTree::kTreeletNodes) / 2);
-        ds->two_pass = leaves > 0 && static_cast<double>(sc->tree.pair_leaf_refs.size()) / static_cast<double>(leaves) <= 6.0;
+        const double refs_per_leaf = leaves > 0 ? static_cast<double>(sc->tree.pair_leaf_refs.size()) / static_cast<double>(leaves) : 0.0;
+        ds->two_pass = leaves > 0 && refs_per_leaf <= 6.0;
+        // measured (profiles/README.md): the pooled kernel wins from a few thousand leaves up (5000-triangle soup +11 %,
+        // 110k-triangle mesh +6 %, 1M-triangle mesh +17 %), ties around 12k leaves and loses on trees that are a handful of
+        // big leaves (furnace_test 155 leaves: -4 %; cornell_box, one 36-triangle leaf: -44 %)
+        ds->pooled = leaves >= 1024 && refs_per_leaf <= 16.0;
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_sync, cudaEventDisableTiming));
@@ -360,7 +366,7 @@ static int persistent_mode(const DeviceScene* ds, bool shadow) {
         const int m = std::atoi(v);
         return m == 3 ? 3 : (m != 0 ? 2 : 0);
     }
-    if (ds->two_pass) return 3;
+    if (ds->pooled) return 3;
     return shadow ? 0 : 2;
 }
 
@@ -369,15 +375,15 @@ static void launch_closest(DeviceScene* ds, int mode, cudaStream_t stream, const
                            const float* pd, uint32_t n, uint32_t* cursor, uint4* hits, const uint32_t* order = nullptr) {
     const bool plain = po != nullptr;
     if (mode == 3) {
-        const int refill = static_cast<int>(env_u64("TRN_PQ_REFILL", 24)), iters = static_cast<int>(env_u64("TRN_PQ_WALK", 12));
+        const int refill = static_cast<int>(env_u64("TRN_PQ_REFILL", 28)), iters = static_cast<int>(env_u64("TRN_PQ_WALK", 12));
         if (plain)
             trace_pooled_kernel<2><<<persistent_grid(ds->grid_pooled[2], n), 128, 0, stream>>>(
                 ds->dev, static_cast<const float4*>(ds->d_planes), nullptr, nullptr, nullptr, po, pd, n, nullptr, cursor, hits, nullptr,
-                refill, iters, pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 8)));
+                refill, iters, pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 10)));
         else
             trace_pooled_kernel<0><<<persistent_grid(ds->grid_pooled[0], n), 128, 0, stream>>>(
                 ds->dev, static_cast<const float4*>(ds->d_planes), ra, rb, nullptr, nullptr, nullptr, n, nullptr, cursor, hits, nullptr,
-                refill, iters, pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 8)));
+                refill, iters, pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 10)));
     } else if (mode == 2) {
         const int refill = static_cast<int>(env_u64("TRN_REFILL", 28)), quanta = static_cast<int>(env_u64("TRN_QUANTA", 2));
         if (plain)
@@ -398,8 +404,8 @@ static void launch_shadow(DeviceScene* ds, int mode, cudaStream_t stream, uint32
     if (mode == 3) {
         trace_pooled_kernel<1><<<persistent_grid(ds->grid_pooled[1], n_max), 128, 0, stream>>>(
             ds->dev, static_cast<const float4*>(ds->d_planes), ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0,
-            &counters->shadow_count, &counters->shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_PQ_REFILL", 24)),
-            static_cast<int>(env_u64("TRN_PQ_WALK", 12)), pool_chunk_for(ds, n_max), static_cast<int>(env_u64("TRN_PQ_GATE", 8)));
+            &counters->shadow_count, &counters->shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_PQ_REFILL", 28)),
+            static_cast<int>(env_u64("TRN_PQ_WALK", 12)), pool_chunk_for(ds, n_max), static_cast<int>(env_u64("TRN_PQ_GATE", 10)));
     } else if (mode == 2) {
         TRN_LAUNCH_WW(1, ds->two_pass, persistent_grid(ds->grid_shadow, n_max), stream, ds->dev, ds->shadow.a, ds->shadow.b,
                       ds->shadow.c, nullptr, nullptr, 0, &counters->shadow_count, &counters->shadow_cursor, nullptr, acc,
@@ -526,7 +532,7 @@ static FrameParams make_frame(const trn_camera* cam, const trn_render_config* cf
     fp.max_depth = cfg->max_depth;
     std::memcpy(fp.bg, cfg->bg_rgba, sizeof fp.bg);
     fp.has_light = cfg->num_lights;
-    fp.child_major = static_cast<int32_t>(env_u64("TRN_CHILD_MAJOR", 0));
+    fp.child_major = static_cast<int32_t>(env_u64("TRN_CHILD_MAJOR", 1));
     std::memcpy(fp.light_pos, cfg->light.pos, sizeof fp.light_pos);
     std::memcpy(fp.light_rgba, cfg->light.rgba, sizeof fp.light_rgba);
     fp.max_visibility = cfg->max_visibility;
