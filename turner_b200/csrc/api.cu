@@ -273,7 +273,7 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
             if ((y & 3u) == 3u && (y >> 2) > 0) ++leaves;
         }
         ds->treelet_pairs = static_cast<uint32_t>(std::min<size_t>(sc->tree.pair_nodes.size(), KdTree::kTreeletNodes) / 2);
-        const double refs_per_leaf = leaves > 0 ? static_cast<double>(sc->tree.pair_leaf_refs.size()) / static_cast<double>(leaves) : 0.0;
+        const double refs_per_leaf = leaves > 0 ? static_cast<double>(sc->tree.num_pair_refs) / static_cast<double>(leaves) : 0.0;
         ds->two_pass = leaves > 0 && refs_per_leaf <= 6.0;
         // measured (profiles/README.md): the pooled kernel wins from a few thousand leaves up (5000-triangle soup +11 %,
         // 110k-triangle mesh +6 %, 1M-triangle mesh +17 %), ties around 12k leaves and loses on trees that are a handful of

@@ -295,6 +295,7 @@ void flatten_pairs(BuildNode* root, KdTree& out) {
         uint32_t slot;
     };
     out.num_cut_nodes = 0;
+    out.num_pair_refs = 0;
     auto emit = [&](const Item& it, std::vector<Item>& children) {
         BuildNode* n = it.node;
         if (!n) {
@@ -316,8 +317,12 @@ void flatten_pairs(BuildNode* root, KdTree& out) {
             children.push_back({n->left, pair});
             children.push_back({n->right, pair + 1});
         } else {
+            // every leaf's run starts at a multiple of 4 references (16 bytes), so that a kernel can fetch four ids with
+            // one vector load; the padding repeats the previous run's last id (a valid triangle, never counted)
+            while (refs.size() % 4 != 0) refs.push_back(refs.back());
             const uint32_t first = static_cast<uint32_t>(refs.size());
             refs.insert(refs.end(), n->ids.begin(), n->ids.end());
+            out.num_pair_refs += n->ids.size();
             nodes[it.slot] = (static_cast<uint64_t>((static_cast<uint32_t>(n->ids.size()) << 2) | 3u) << 32) | first;
         }
     };
@@ -337,6 +342,7 @@ void flatten_pairs(BuildNode* root, KdTree& out) {
         emit(it, kids);
         for (auto k = kids.rbegin(); k != kids.rend(); ++k) stack.push_back(*k);
     }
+    for (int k = 0; k < 4; ++k) refs.push_back(refs.empty() ? 0u : refs.back()); // a 4-wide read of the last chunk stays inside
 }
 
 // DFS layout of lib/kdtree.cpp:420-467 in the FlatNode encoding of lib/kdtree.h:62-154.

@@ -46,7 +46,8 @@ struct KdTree {
     // stage in shared memory as one contiguous block); below that each subtree is laid out depth-first.
     static constexpr uint32_t kTreeletNodes = 2048;
     std::vector<uint64_t> pair_nodes;      // low 32 bits = x, high 32 bits = y
-    std::vector<uint32_t> pair_leaf_refs;  // triangle ids, leaf after leaf
+    std::vector<uint32_t> pair_leaf_refs;  // triangle ids, leaf after leaf; every run starts at a multiple of 4 (padded)
+    uint64_t num_pair_refs = 0;            // references without the padding
     uint64_t num_cut_nodes = 0;
 };
 

@@ -368,18 +368,16 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                 const uint32_t sub = g - (pend - (lcnt + kPqChunkTris - 1) / kPqChunkTris); // chunk index inside the leaf
                 const uint32_t off0 = sub * kPqChunkTris;
                 const uint32_t cnt = g < total ? min(static_cast<uint32_t>(kPqChunkTris), lcnt - off0) : 0u;
-                uint32_t id0 = 0, id1 = 0, id2 = 0, id3 = 0, km = 0; // the chunk's triangle ids, bit k of km: triangle k survives
+                uint4 ids = make_uint4(0u, 0u, 0u, 0u); // the chunk's triangle ids
+                uint32_t km = 0;                         // bit k: triangle k survives the pre-filter
                 if (cnt > 0u) {
                     const float4 ro = sm.ray_o[owner], rd = sm.ray_d[owner];
                     const float E = ro.w, F = rd.w;
                     const float c1 = fmaf(-lo, F, -E), c2 = fmaf(hi, F, E);
-                    const uint32_t* refs = sc.prefs + first + off0;
-                    // all ids first, then all plane records: one id latency + one record latency per chunk
-                    id0 = __ldg(refs);
-                    id1 = cnt > 1u ? __ldg(refs + 1) : id0;
-                    id2 = cnt > 2u ? __ldg(refs + 2) : id0;
-                    id3 = cnt > 3u ? __ldg(refs + 3) : id0;
-                    const float4 p0 = __ldg(&planes[id0]), p1 = __ldg(&planes[id1]), p2 = __ldg(&planes[id2]), p3 = __ldg(&planes[id3]);
+                    // leaf runs start at multiples of 4 references and the array is padded (kdtree_build.cpp): one 16-byte
+                    // load brings the chunk's ids; ids beyond cnt are valid triangles whose result is masked
+                    ids = __ldg(reinterpret_cast<const uint4*>(sc.prefs + first + off0));
+                    const float4 p0 = __ldg(&planes[ids.x]), p1 = __ldg(&planes[ids.y]), p2 = __ldg(&planes[ids.z]), p3 = __ldg(&planes[ids.w]);
 #pragma unroll
                     for (int k = 0; k < kPqChunkTris; ++k) {
                         const float4 p = k == 0 ? p0 : (k == 1 ? p1 : (k == 2 ? p2 : p3));
@@ -387,28 +385,24 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                         const float b = fmaf(-p.x, ro.x, fmaf(-p.y, ro.y, fmaf(-p.z, ro.z, p.w)));
                         const float A = fabsf(a);
                         const float B = __uint_as_float(__float_as_uint(b) ^ (__float_as_uint(a) & 0x80000000u));
-                        const bool keep = static_cast<uint32_t>(k) < cnt && (A <= F || (B >= fmaf(lo, A, c1) && B <= fmaf(hi, A, c2)));
+                        // bitwise, not short-circuit: no branches in the round
+                        const bool keep = (static_cast<uint32_t>(k) < cnt) & ((A <= F) | ((B >= fmaf(lo, A, c1)) & (B <= fmaf(hi, A, c2))));
                         km |= keep ? (1u << k) : 0u;
                     }
                 }
-                const uint32_t nk = __popc(km);
-                // append the survivors of the round: exclusive scan of the per-lane counts, no atomics
-                uint32_t pos = nk;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const uint32_t v = __shfl_up_sync(kFull, pos, off);
-                    if (static_cast<int>(lane) >= off) pos += v;
-                }
-                const uint32_t round_total = __shfl_sync(kFull, pos, 31);
-                pos = ns + pos - nk;
-                // seq = visiting order inside the cycle: (leaf slot in the queue, position in the leaf) + 1
+                // append the survivors of the round, k-major (the order inside the queue is irrelevant: seq carries the
+                // visiting order): four ballots, no scan, no atomics
                 const uint32_t seq0 = ((lb + j) << 20) + off0 + 1u;
+                uint32_t round_total = 0;
 #pragma unroll
-                for (int k = 0; k < kPqChunkTris; ++k)
-                    if (km & (1u << k)) {
-                        const uint32_t id = k == 0 ? id0 : (k == 1 ? id1 : (k == 2 ? id2 : id3));
-                        sm.surv[pos + __popc(km & ((1u << k) - 1u))] = make_uint2(id, owner | ((seq0 + k) << 5));
+                for (int k = 0; k < kPqChunkTris; ++k) {
+                    const unsigned bk = __ballot_sync(kFull, (km >> k) & 1u);
+                    if ((km >> k) & 1u) {
+                        const uint32_t id = k == 0 ? ids.x : (k == 1 ? ids.y : (k == 2 ? ids.z : ids.w));
+                        sm.surv[ns + round_total + __popc(bk & lt_mask)] = make_uint2(id, owner | ((seq0 + k) << 5));
                     }
+                    round_total += __popc(bk);
+                }
                 ns += round_total;
                 base += 32u;
                 __syncwarp();
