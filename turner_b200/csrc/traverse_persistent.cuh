@@ -1,5 +1,6 @@
-// Persistent-warp kd traversal with lane refill -- the production closest-hit kernel (shadow waves keep the
-// one-thread-per-ray kernel of kernels.cuh; A/B numbers in profiles/README.md).
+// Persistent-warp kd traversal with lane refill -- the closest-hit kernel of trees that are a few big leaves (shadow
+// waves of those trees keep the one-thread-per-ray kernel of kernels.cuh). Trees with >= 1024 leaves run the pooled
+// kernel of traverse_pooled.cuh, which grew out of this one; A/B numbers in profiles/README.md.
 //
 // Why: ncu on the one-thread-per-ray kernel (profiles/r1_prof_trace_v2.txt) shows the issue slots 60-70 % busy but only
 // 5-12 of 32 lanes active per instruction. Ray cost is heavy-tailed (a miss leaves at once, a grazing ray visits

@@ -1,22 +1,25 @@
 // Pooled kd traversal -- persistent warps whose lanes WALK their own rays but whose triangle tests are pooled over the
-// warp. Production kernel for closest-hit and shadow waves (A/B numbers and the SIMT model behind the design:
-// profiles/README.md, tools/simt_sim.cpp).
+// warp. Production kernel for closest-hit and shadow waves of every tree with >= 1024 leaves (A/B numbers, the SIMT
+// model and the CPU warp emulation behind the design: profiles/README.md, tools/simt_sim.cpp, tools/pooled_emul.cpp).
 //
 // Why: the while-while kernel (traverse_persistent.cuh) issues 930 warp-instructions per secondary ray with 8.5 of 32
 // lanes active: the lanes of a warp need different numbers of inner steps to reach their next leaf (mean 3, max ~10),
-// their leaves hold different numbers of triangles (1..20), and the few plane hits that need the full ray/triangle
+// their leaves hold different numbers of triangles (1..40), and the few plane hits that need the full ray/triangle
 // test (6 % of the tests) are evaluated by 2-3 lanes while the rest wait. Here every warp runs a three-phase cycle:
 //
-//   WALK   a fixed number of warp-wide iterations; in each, a lane takes ONE inner-node step of its own ray or, at a
-//          leaf, appends the leaf to the warp's queue in shared memory as chunks of <= 4 triangle references and pops
-//          its stack at once. The walk is speculative: it does not wait for the leaf's outcome (98.6 % of the leaf
-//          visits of the benchmark's secondary rays do not end the ray). ~25 lanes active.
-//   TEST   the queued chunks of ALL rays are dealt out 32 at a time, one chunk per lane; the lane reads the owner ray
-//          from a table in shared memory and runs a division-free, conservative plane pre-filter on the chunk's
-//          triangles (16-byte plane records, FMA arithmetic with explicit error bounds). ~28 lanes active.
-//   EXACT  pre-filter survivors of all rays are pooled too and get, 32 at a time, the reference's exact operation
-//          sequence (lib/intersection.h:40-89: plane distance with IEEE division, barycentric part); accepted hits are
-//          handed to the owner lane in visiting order.
+//   WALK   up to walk_iters warp-wide iterations; in each, a lane at an inner node takes ONE step of its own ray. The
+//          lanes that have reached a leaf queue a 16-byte leaf descriptor in shared memory and pop their stack -- in a
+//          block that is only issued once leaf_gate lanes wait (or nobody can step). The walk is speculative: it does not
+//          wait for the leaf's outcome (98.6 % of the leaf visits of the benchmark's secondary rays do not end the ray).
+//   TEST   the queued leaves of ALL rays, 32 at a time (one descriptor per lane), are cut into chunks of 4 triangle
+//          references; the chunks are dealt out 32 per round, one per lane, by a shuffle binary search over the running
+//          chunk totals. The lane reads the owner ray from a table in shared memory, the chunk's ids with one 16-byte
+//          load (leaf runs are 16-byte aligned), four 16-byte plane records, and runs a division-free, conservative plane
+//          pre-filter (FMA arithmetic with explicit error bounds). Survivors are appended to the warp's survivor queue
+//          with four ballots -- no atomics.
+//   EXACT  whenever 32 survivors are waiting (and at the end of the cycle) they get, 32 at a time, the reference's exact
+//          operation sequence (lib/intersection.h:40-89: plane distance with IEEE division, barycentric part); accepted
+//          hits are handed to the owner lane, ordered by a visiting-order sequence number.
 //
 // Bit-exact contract (tests/test_gpu_parity.py): a triangle is accepted, and its (r, s, t) computed, ONLY by the exact
 // sequence in EXACT; the pre-filter can only discard triangles whose exact plane distance lies outside the current
