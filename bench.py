@@ -152,8 +152,10 @@ def cpu_reference_run(name, sc, nodes, box, steps=1, warmup=0):
     w = WORKLOADS[name]
     cores = os.cpu_count() or 1
     W = w["cpu_width"]
-    sample = ("same scene / max-depth %d / -m %d, width %d instead of %d, 1 of %d pixel samples per step "
-              "(Mrays/s does not depend on either)" % (w["max_depth"], w["mc_samples"], W, w["width"], w["pixel_samples"]))
+    # ~10 s of host work for one step of the mesh at 16 cores; a run of K steps keeps its total near 30 s
+    cpu_pps = max(1, min(16, 48 // max(1, steps + warmup)))
+    sample = ("same scene / max-depth %d / -m %d, width %d instead of %d, %d of %d pixel samples per step "
+              "(Mrays/s does not depend on either)" % (w["max_depth"], w["mc_samples"], W, w["width"], cpu_pps, w["pixel_samples"]))
     vals, rays_total, t_total = [], 0, 0.0
     if ob.ref_available():
         kind = "reference"
@@ -162,7 +164,7 @@ def cpu_reference_run(name, sc, nodes, box, steps=1, warmup=0):
         r = (ob.RefScene(sc["vertices"], sc["normals"], sc["diffuse"], nodes=nodes, box=box) if nodes is not None
              else ob.RefScene(sc["vertices"], sc["normals"], sc["diffuse"]))
         cam = ob.ref_camera(sc)
-        cfg = ob.ref_config(sc, W, w["max_depth"], w["mc_samples"], 1, num_threads=cores)
+        cfg = ob.ref_config(sc, W, w["max_depth"], w["mc_samples"], cpu_pps, num_threads=cores)
         for it in range(warmup + steps):
             _, _, _, st = r.render(cam, cfg)
             if it >= warmup:
@@ -172,7 +174,7 @@ def cpu_reference_run(name, sc, nodes, box, steps=1, warmup=0):
         kind = "port"
         o = (ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"], nodes=nodes, box=box) if nodes is not None
              else ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"]))
-        cfg = ob.make_cfg(sc, W, w["max_depth"], w["mc_samples"], 1, num_threads=cores)
+        cfg = ob.make_cfg(sc, W, w["max_depth"], w["mc_samples"], cpu_pps, num_threads=cores)
         for it in range(warmup + steps):
             _, _, st = o.render(cfg)
             if it >= warmup:
