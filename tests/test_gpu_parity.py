@@ -522,3 +522,35 @@ def test_pooled_kernel_renders_like_the_others(api, scenes, monkeypatch):
             d = np.abs(out[mode][0] - out["0"][0])
             assert (d <= 2e-4 * (1 + np.abs(out["0"][0]))).all(), (sc["name"], mode, float(d.max()))
     monkeypatch.delenv("TRN_PERSISTENT")
+
+
+def test_pooled_kernel_is_schedule_independent(api, ob, scenes, monkeypatch):
+    # The pooled kernel's result must not depend on how its cycle is scheduled: extreme walk lengths, leaf gates and
+    # refill thresholds (queue-full retries, one-lane warps, every leaf flushed at once) against the exhaustive reference
+    # schedule, bit for bit, on secondary-ray shaped input (rays leaving the surface) of a real tree.
+    sc = scenes.cubesphere(40)
+    o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+    p = api.Scene.from_dict(sc)
+    rng = np.random.RandomState(9)
+    V = sc["vertices"].reshape(-1, 3, 3)
+    n = 80000
+    idx = rng.randint(0, V.shape[0], n)
+    bary = rng.dirichlet([1, 1, 1], n)
+    pts = (V[idx] * bary[:, :, None]).sum(1)
+    nrm = pts / np.linalg.norm(pts, axis=1, keepdims=True)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d *= np.sign((d * nrm).sum(1, keepdims=True))
+    ro = np.ascontiguousarray(pts + 1e-4 * nrm, np.float32)
+    rd = np.ascontiguousarray(d, np.float32)
+    i_o, r_o = o.intersect(ro, rd, 0)
+    monkeypatch.setenv("TRN_PERSISTENT", "3")
+    for walk, gate, refill in ((1, 1, 28), (1, 32, 1), (64, 32, 32), (3, 5, 7), (12, 10, 28)):
+        monkeypatch.setenv("TRN_PQ_WALK", str(walk))
+        monkeypatch.setenv("TRN_PQ_GATE", str(gate))
+        monkeypatch.setenv("TRN_PQ_REFILL", str(refill))
+        i_g, r_g = p.intersect(ro, rd)
+        assert np.array_equal(i_g, i_o), (walk, gate, refill, int((i_g != i_o).sum()))
+        assert np.array_equal(bits(r_g), bits(r_o)), (walk, gate, refill)
+    for k in ("TRN_PERSISTENT", "TRN_PQ_WALK", "TRN_PQ_GATE", "TRN_PQ_REFILL"):
+        monkeypatch.delenv(k)
