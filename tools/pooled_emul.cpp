@@ -20,7 +20,7 @@ using namespace trn;
 
 static const float kFltMax = 3.402823466e+38f, kCellSlack = 1e-4f;
 static const uint32_t kMiss = 0x40000000u;
-static const int kPqChunks = 128, kPqChunkTris = 4, kPqMaxAppend = 16, kPqSurv = 32 + 32 * 4;
+static const int kPqLeaves = 64, kPqChunkTris = 4, kPqSurv = 32 + 32 * 4;
 
 struct Ray {
     float o[3], d[3];
@@ -129,11 +129,11 @@ struct F4 {
 
 // one emulated warp over rays[begin, end); returns false on a detected hang
 static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin, size_t end, std::vector<Hit>& hits, int refill_below,
-                     int walk_iters, uint64_t* stat) {
+                     int walk_iters, int leaf_gate, uint64_t* stat) {
     F4 s_ray[64];
-    U4 s_chunk[kPqChunks];
+    U4 s_leaf[kPqLeaves];
     uint32_t s_surv[kPqSurv][2];
-    uint32_t s_nchunk = 0, s_nvalid = kPqChunks, s_nsurv = 0;
+    uint32_t s_nleaf = 0, s_nsurv = 0;
     float scale = 0.f;
     for (int c = 0; c < 6; ++c) scale = std::fmax(scale, std::fabs(sc.tree.box[c]));
     const uint64_t* pn = sc.tree.pair_nodes.data();
@@ -142,7 +142,7 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
         int sp = 0;
         float ox, oy, oz, ix, iy, iz, tenter, texit, last_texit;
         uint32_t nx, ny;
-        uint32_t best_id, best_seq, idx, leaf_off;
+        uint32_t best_id, best_seq, idx;
         float best_r, best_s, best_t;
         bool busy = false, walking = false;
     };
@@ -193,8 +193,7 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
                 l.best_s = l.best_t = 0.f;
                 l.best_seq = 0;
                 l.last_texit = -kFltMax;
-                l.leaf_off = 0;
-                l.busy = l.walking = true;
+                                l.busy = l.walking = true;
                 const float E = 1.9073486e-6f * (3.f * scale + (std::fabs(l.ox) + std::fabs(l.oy) + std::fabs(l.oz)));
                 const float F = 9.5367432e-7f * (std::fabs(dx) + std::fabs(dy) + std::fabs(dz));
                 s_ray[2 * lane] = F4{l.ox, l.oy, l.oz, E};
@@ -207,64 +206,36 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
             if (next >= end) break;
             continue;
         }
-        // WALK
+        // WALK (gated leaf block, as in the kernel)
         bool blocked[32] = {false};
-        for (int it = 0; it < walk_iters; ++it) {
-            bool any = false;
-            for (int lane = 0; lane < 32; ++lane) any |= L[lane].busy && L[lane].walking && !blocked[lane];
-            if (!any) break;
-            stat[0]++;
+        for (int it = 0;; ) {
+            bool can[32], at_leaf[32];
+            int n_leaf = 0, n_inner = 0;
             for (int lane = 0; lane < 32; ++lane) {
-                LaneS& l = L[lane];
-                if (!(l.busy && l.walking && !blocked[lane])) continue;
-                stat[1]++;
-                if ((l.ny & 3u) != 3u) {
-                    const uint32_t ax = l.ny & 3u;
-                    const float split = bfloat(l.nx);
-                    const uint32_t ci = l.ny >> 2;
-                    const uint32_t px = uint32_t(pn[ci]), py = uint32_t(pn[ci] >> 32), pz = uint32_t(pn[ci + 1]), pw = uint32_t(pn[ci + 1] >> 32);
-                    float o_ax = l.oz, i_ax = l.iz;
-                    if (ax == 0u) { o_ax = l.ox; i_ax = l.ix; }
-                    if (ax == 1u) { o_ax = l.oy; i_ax = l.iy; }
-                    const float t = (split - o_ax) * i_ax;
-                    const bool flip = (fbits(i_ax) >> 31) != 0u;
-                    const uint32_t nearx = flip ? pz : px, neary = flip ? pw : py, farx = flip ? px : pz, fary = flip ? py : pw;
-                    const bool near_only = l.texit < t, far_only = !near_only && (t < l.tenter), both = !near_only && !far_only;
-                    const bool go_far = far_only || (both && neary == 3u);
-                    if (both && neary != 3u && fary != 3u) l.stack[l.sp++] = U4{farx, fary, fbits(t), fbits(l.texit)};
-                    l.nx = go_far ? farx : nearx;
-                    l.ny = go_far ? fary : neary;
-                    const float te = (both && go_far) ? t : l.tenter, tx = (both && !go_far) ? t : l.texit;
-                    l.tenter = te;
-                    l.texit = tx;
-                } else {
+                can[lane] = L[lane].busy && L[lane].walking && !blocked[lane];
+                at_leaf[lane] = can[lane] && (L[lane].ny & 3u) == 3u;
+                n_leaf += at_leaf[lane];
+                n_inner += can[lane] && !at_leaf[lane];
+            }
+            const bool last = it >= walk_iters || n_inner == 0;
+            if (n_leaf != 0 && (last || n_leaf >= leaf_gate)) {
+                for (int lane = 0; lane < 32; ++lane) {
+                    if (!at_leaf[lane]) continue;
+                    LaneS& l = L[lane];
                     const uint32_t cnt = l.ny >> 2;
-                    const uint32_t rem = cnt - l.leaf_off;
-                    const uint32_t ch = std::min<uint32_t>((rem + kPqChunkTris - 1) / kPqChunkTris, kPqMaxAppend);
-                    bool leaf_done = true;
-                    if (ch > 0) {
-                        const uint32_t slot = s_nchunk;
-                        s_nchunk += ch;
-                        if (slot + ch <= uint32_t(kPqChunks)) {
+                    if (cnt > 0u) {
+                        const uint32_t slot = s_nleaf++;
+                        if (slot < uint32_t(kPqLeaves)) {
                             float lo = l.tenter - kCellSlack * (std::fabs(l.tenter) + 1.f);
                             float hi = l.texit + kCellSlack * (std::fabs(l.texit) + 1.f);
                             lo = std::fmax(lo, 0.f);
                             hi = std::fmin(hi, l.best_r);
-                            const uint32_t first = l.nx + l.leaf_off;
-                            for (uint32_t k = 0; k < ch; ++k) {
-                                const uint32_t c = std::min<uint32_t>(kPqChunkTris, rem - k * kPqChunkTris);
-                                s_chunk[slot + k] = U4{first + k * kPqChunkTris, c | (uint32_t(lane) << 8), fbits(lo), fbits(hi)};
-                            }
-                            l.leaf_off += ch * kPqChunkTris;
-                            leaf_done = l.leaf_off >= cnt;
+                            s_leaf[slot] = U4{l.nx, cnt | (uint32_t(lane) << 24), fbits(lo), fbits(hi)};
                         } else {
-                            s_nvalid = std::min(s_nvalid, slot);
                             blocked[lane] = true;
-                            leaf_done = false;
                         }
                     }
-                    if (leaf_done) {
-                        l.leaf_off = 0;
+                    if (!blocked[lane]) {
                         l.last_texit = l.texit;
                         if (l.sp == 0) l.walking = false;
                         else {
@@ -278,98 +249,139 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
                     }
                 }
             }
+            if (last) break;
+            ++it;
+            stat[0]++;
+            for (int lane = 0; lane < 32; ++lane) {
+                if (!(can[lane] && !at_leaf[lane])) continue;
+                LaneS& l = L[lane];
+                stat[1]++;
+                const uint32_t ax = l.ny & 3u;
+                const float split = bfloat(l.nx);
+                const uint32_t ci = l.ny >> 2;
+                const uint32_t px = uint32_t(pn[ci]), py = uint32_t(pn[ci] >> 32), pz = uint32_t(pn[ci + 1]), pw = uint32_t(pn[ci + 1] >> 32);
+                float o_ax = l.oz, i_ax = l.iz;
+                if (ax == 0u) { o_ax = l.ox; i_ax = l.ix; }
+                if (ax == 1u) { o_ax = l.oy; i_ax = l.iy; }
+                const float t = (split - o_ax) * i_ax;
+                const bool flip = (fbits(i_ax) >> 31) != 0u;
+                const uint32_t nearx = flip ? pz : px, neary = flip ? pw : py, farx = flip ? px : pz, fary = flip ? py : pw;
+                const bool near_only = l.texit < t, far_only = !near_only && (t < l.tenter), both = !near_only && !far_only;
+                const bool go_far = far_only || (both && neary == 3u);
+                if (both && neary != 3u && fary != 3u) l.stack[l.sp++] = U4{farx, fary, fbits(t), fbits(l.texit)};
+                l.nx = go_far ? farx : nearx;
+                l.ny = go_far ? fary : neary;
+                const float te = (both && go_far) ? t : l.tenter, tx = (both && !go_far) ? t : l.texit;
+                l.tenter = te;
+                l.texit = tx;
+            }
         }
-        // TEST / EXACT
-        const uint32_t nch = std::min(s_nchunk, s_nvalid);
-        uint32_t base = 0;
-        for (;;) {
+        // TEST / EXACT: leaves 32 at a time, their chunks of 4 references dealt out 32 per round
+        const uint32_t nleaf = std::min<uint32_t>(s_nleaf, kPqLeaves);
+        auto exact_round = [&]() {
             const uint32_t ns = s_nsurv;
-            if (ns >= 32u || (base >= nch && ns > 0u)) {
-                const uint32_t take = std::min(32u, ns), sbase = ns - take;
-                stat[4]++;
-                stat[5] += take;
-                struct P {
-                    bool pass;
-                    uint32_t id, owner, seq;
-                    float r, s, t;
-                } res[32];
-                for (uint32_t lane = 0; lane < 32; ++lane) {
-                    P& p = res[lane];
-                    p.pass = false;
-                    if (lane >= take) continue;
-                    p.id = s_surv[sbase + lane][0];
-                    p.owner = s_surv[sbase + lane][1] & 31u;
-                    p.seq = s_surv[sbase + lane][1] >> 5;
-                    const float lim = L[p.owner].best_r;
-                    const F4 ro = s_ray[2 * p.owner], rd = s_ray[2 * p.owner + 1];
-                    const float* q = &sc.tris.isect[size_t(p.id) * 16];
-                    const float nx = q[3], ny = q[4], nz = q[5];
-                    const float denom = nx * rd.x + ny * rd.y + nz * rd.z;
-                    const float nom = nx * (q[0] - ro.x) + ny * (q[1] - ro.y) + nz * (q[2] - ro.z);
-                    p.r = nom / denom;
-                    if (denom != 0.f && p.r >= 0.f && p.r <= lim) {
-                        const float wx = (ro.x + p.r * rd.x) - q[0], wy = (ro.y + p.r * rd.y) - q[1], wz = (ro.z + p.r * rd.z) - q[2];
-                        const float wv = wx * q[9] + wy * q[10] + wz * q[11];
-                        const float wu = wx * q[6] + wy * q[7] + wz * q[8];
-                        p.s = (q[12] * wv - q[13] * wu) / q[15];
-                        if (!(p.s < 0.f)) {
-                            p.t = (q[12] * wu - q[14] * wv) / q[15];
-                            p.pass = !(p.t < 0.f || 1.f < p.s + p.t);
-                        }
+            const uint32_t take = std::min(32u, ns), sbase = ns - take;
+            stat[4]++;
+            stat[5] += take;
+            struct P {
+                bool pass;
+                uint32_t id, owner, seq;
+                float r, s, t;
+            } res[32];
+            for (uint32_t lane = 0; lane < 32; ++lane) {
+                P& p = res[lane];
+                p.pass = false;
+                if (lane >= take) continue;
+                p.id = s_surv[sbase + lane][0];
+                p.owner = s_surv[sbase + lane][1] & 31u;
+                p.seq = s_surv[sbase + lane][1] >> 5;
+                const float lim = L[p.owner].best_r;
+                const F4 ro = s_ray[2 * p.owner], rd = s_ray[2 * p.owner + 1];
+                const float* q = &sc.tris.isect[size_t(p.id) * 16];
+                const float nx = q[3], ny = q[4], nz = q[5];
+                const float denom = nx * rd.x + ny * rd.y + nz * rd.z;
+                const float nom = nx * (q[0] - ro.x) + ny * (q[1] - ro.y) + nz * (q[2] - ro.z);
+                p.r = nom / denom;
+                if (denom != 0.f && p.r >= 0.f && p.r <= lim) {
+                    const float wx = (ro.x + p.r * rd.x) - q[0], wy = (ro.y + p.r * rd.y) - q[1], wz = (ro.z + p.r * rd.z) - q[2];
+                    const float wv = wx * q[9] + wy * q[10] + wz * q[11];
+                    const float wu = wx * q[6] + wy * q[7] + wz * q[8];
+                    p.s = (q[12] * wv - q[13] * wu) / q[15];
+                    if (!(p.s < 0.f)) {
+                        p.t = (q[12] * wu - q[14] * wv) / q[15];
+                        p.pass = !(p.t < 0.f || 1.f < p.s + p.t);
                     }
                 }
-                for (uint32_t lane = 0; lane < 32; ++lane) {
-                    const P& p = res[lane];
-                    if (!p.pass) continue;
-                    LaneS& o = L[p.owner];
-                    if (p.r < o.best_r || (p.r == o.best_r && p.seq < o.best_seq)) {
-                        o.best_id = p.id;
-                        o.best_r = p.r;
-                        o.best_s = p.s;
-                        o.best_t = p.t;
-                        o.best_seq = p.seq;
-                    }
+            }
+            for (uint32_t lane = 0; lane < 32; ++lane) {
+                const P& p = res[lane];
+                if (!p.pass) continue;
+                LaneS& o = L[p.owner];
+                if (p.r < o.best_r || (p.r == o.best_r && p.seq < o.best_seq)) {
+                    o.best_id = p.id;
+                    o.best_r = p.r;
+                    o.best_s = p.s;
+                    o.best_t = p.t;
+                    o.best_seq = p.seq;
                 }
-                s_nsurv = sbase;
-            } else if (base < nch) {
+            }
+            s_nsurv = sbase;
+        };
+        for (uint32_t lb = 0; lb < nleaf; lb += 32) {
+            uint32_t P[32], total = 0; // inclusive chunk totals of the batch's leaves
+            for (uint32_t j = 0; j < 32; ++j) {
+                const uint32_t c = lb + j < nleaf ? (s_leaf[lb + j].y & 0xffffffu) : 0u;
+                total += (c + kPqChunkTris - 1) / kPqChunkTris;
+                P[j] = total;
+            }
+            for (uint32_t base = 0; base < total; base += 32) {
+                while (s_nsurv >= 32u) exact_round();
                 stat[2]++;
+                uint32_t km[32], owner_[32], seq0[32], ids[32][4];
                 for (uint32_t lane = 0; lane < 32; ++lane) {
+                    km[lane] = 0;
                     const uint32_t g = base + lane;
-                    if (g >= nch) continue;
+                    if (g >= total) continue;
                     stat[3]++;
-                    const U4 d = s_chunk[g];
-                    const uint32_t first = d.x, cnt = d.y & 0xffu, owner = d.y >> 8;
+                    uint32_t j = 0;
+                    while (P[j] <= g) ++j;
+                    const U4 d = s_leaf[lb + j];
+                    const uint32_t lcnt = d.y & 0xffffffu, owner = d.y >> 24;
+                    const uint32_t sub = g - (P[j] - (lcnt + kPqChunkTris - 1) / kPqChunkTris), off0 = sub * kPqChunkTris;
+                    const uint32_t cnt = std::min<uint32_t>(kPqChunkTris, lcnt - off0);
                     const float lo = bfloat(d.z), hi = bfloat(d.w);
                     const F4 ro = s_ray[2 * owner], rd = s_ray[2 * owner + 1];
                     const float E = ro.w, F = rd.w;
                     const float c1 = std::fmaf(-lo, F, -E), c2 = std::fmaf(hi, F, E);
-                    for (uint32_t i = 0; i < cnt; ++i) {
-                        const uint32_t id = sc.tree.pair_leaf_refs[first + i];
+                    owner_[lane] = owner;
+                    seq0[lane] = ((lb + j) << 20) + off0 + 1u;
+                    for (uint32_t k = 0; k < cnt; ++k) {
+                        const uint32_t id = sc.tree.pair_leaf_refs[d.x + off0 + k];
+                        ids[lane][k] = id;
                         const float* p = &sc.planes[size_t(id) * 4];
                         const float a = std::fmaf(p[0], rd.x, std::fmaf(p[1], rd.y, p[2] * rd.z));
                         const float b = std::fmaf(-p[0], ro.x, std::fmaf(-p[1], ro.y, std::fmaf(-p[2], ro.z, p[3])));
                         const float A = std::fabs(a);
                         const float B = bfloat(fbits(b) ^ (fbits(a) & 0x80000000u));
-                        const bool keep = A <= F || (B >= std::fmaf(lo, A, c1) && B <= std::fmaf(hi, A, c2));
                         stat[6]++;
-                        if (keep) {
+                        if (A <= F || (B >= std::fmaf(lo, A, c1) && B <= std::fmaf(hi, A, c2))) km[lane] |= 1u << k;
+                    }
+                }
+                for (uint32_t k = 0; k < uint32_t(kPqChunkTris); ++k) // k-major append, as the kernel's four ballots
+                    for (uint32_t lane = 0; lane < 32; ++lane)
+                        if (km[lane] & (1u << k)) {
                             if (s_nsurv >= uint32_t(kPqSurv)) {
                                 std::fprintf(stderr, "survivor queue overflow\n");
                                 return false;
                             }
-                            s_surv[s_nsurv][0] = id;
-                            s_surv[s_nsurv][1] = owner | ((g * 8u + i + 1u) << 5);
+                            s_surv[s_nsurv][0] = ids[lane][k];
+                            s_surv[s_nsurv][1] = owner_[lane] | ((seq0[lane] + k) << 5);
                             ++s_nsurv;
                         }
-                    }
-                }
-                base += 32u;
-            } else {
-                break;
             }
         }
-        s_nchunk = 0;
-        s_nvalid = kPqChunks;
+        while (s_nsurv > 0u) exact_round();
+        s_nleaf = 0;
         for (int lane = 0; lane < 32; ++lane) {
             LaneS& l = L[lane];
             if (!l.busy) continue;
@@ -443,7 +455,7 @@ int main(int argc, char** argv) {
 #pragma omp parallel for schedule(dynamic, 1)
         for (long w = 0; w < nw; ++w) {
             uint64_t st[8] = {0};
-            const bool r = warp_run(sc, wave, size_t(w) * per, std::min(wave.size(), size_t(w + 1) * per), got, 24, 12, st);
+            const bool r = warp_run(sc, wave, size_t(w) * per, std::min(wave.size(), size_t(w + 1) * per), got, 28, 12, 10, st);
 #pragma omp critical
             {
                 ok &= r;
