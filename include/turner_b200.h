@@ -202,6 +202,19 @@ int32_t trn_load_blend(const char* path, trn_loaded_scene* out);
 int32_t trn_load_soup(const char* path, trn_loaded_scene* out);
 void trn_loaded_scene_free(trn_loaded_scene* s);
 
+/* ---- kdtree.cache (main.cpp:142-167): the reference stores its KDTree (triangles with their precomputed fields, the
+ * scene box, the FlatNode array) through cereal's PortableBinary archive and, when ./kdtree.cache exists, loads it INSTEAD
+ * of the scene's triangles -- whatever scene was asked for. Here the file is explicit and checked:
+ *   trn_scene_save_cache  writes the same byte layout (1 flag byte; u64 triangle count; 48 f32 per triangle in the order
+ *                         of Triangle::serialize, lib/triangle.h:89-92 -- ambient is written as 0, it is not part of the
+ *                         scene arrays and no tracer reads it, emissive = diffuse as main.cpp:43 loads it; 6 f32 box;
+ *                         u64 node count; 8-byte FlatNodes, lib/kdtree.h:62-154).
+ *   trn_scene_load_cache  reads such a file (written by this library or by the reference), rebuilds the tree from the
+ *                         cached triangles and REFUSES the file (TRN_ERR_INVALID) when the cached node array or box is not
+ *                         what these triangles produce: a stale or foreign cache cannot be rendered silently. */
+int32_t trn_scene_save_cache(const trn_scene* scene, const char* path);
+int32_t trn_scene_load_cache(const char* path, trn_scene** out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -251,6 +251,10 @@ def ref_lib(kind="pathtracer"):
         L.ref_scene_create_prebuilt.restype = C.c_void_p
         L.ref_scene_create_prebuilt.argtypes = [_f32p, _f32p, _f32p, C.c_uint32, _u64p, C.c_uint64, _f32p]
         L.ref_scene_destroy.argtypes = [C.c_void_p]
+        L.ref_cache_write.restype = C.c_int
+        L.ref_cache_write.argtypes = [C.c_void_p, C.c_char_p]
+        L.ref_cache_read.restype = C.c_void_p
+        L.ref_cache_read.argtypes = [C.c_char_p]
         L.ref_scene_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                      _f32p]
         L.ref_scene_nodes.argtypes = [C.c_void_p, _u64p]
@@ -327,6 +331,25 @@ class RefScene:
         if getattr(self, "h", None):
             self.L.ref_scene_destroy(self.h)
             self.h = None
+
+    @classmethod
+    def from_cache(cls, path, kind="pathtracer"):
+        """main.cpp:147-152: KDTree loaded from a kdtree.cache through the reference's serialize()"""
+        self = cls.__new__(cls)
+        self.L = ref_lib(kind)
+        self.h = self.L.ref_cache_read(os.fsencode(path))
+        if not self.h:
+            raise RuntimeError("the reference's KDTree::serialize() could not read %s" % path)
+        nn, hh, nt = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        b = np.zeros(6, np.float32)
+        self.L.ref_scene_info(self.h, C.byref(nn), C.byref(hh), C.byref(nt), b)
+        self.num_nodes, self.height, self.num_tris, self.box = nn.value, hh.value, nt.value, b
+        return self
+
+    def write_cache(self, path):
+        """main.cpp:158-165: the reference's KDTree::serialize() into a PortableBinary archive"""
+        if self.L.ref_cache_write(self.h, os.fsencode(path)) != 0:
+            raise RuntimeError("cannot write %s" % path)
 
     def nodes(self):
         out = np.zeros(self.num_nodes, np.uint64)

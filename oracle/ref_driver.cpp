@@ -28,6 +28,8 @@
 #include <sstream>
 #include <string>
 #include <thread>
+#include <fstream>
+#include <cereal/archives/portable_binary.hpp>
 #include <vector>
 
 // The reference TUs define USAGE; keep the linker happy if they are absent.
@@ -155,6 +157,32 @@ void* ref_scene_create_prebuilt(const float* verts, const float* normals, const 
     g.nodes->resize(num_nodes);
     static_assert(sizeof(detail::FlatNode) == 8, "FlatNode is 8 bytes");
     std::memcpy(static_cast<void*>(g.nodes->data()), nodes, num_nodes * 8);
+    return s;
+}
+
+// kdtree.cache, as main.cpp:158-165 writes it and main.cpp:147-152 reads it: the reference's KDTree::serialize() through
+// a PortableBinary archive (oracle/ref_shims/cereal/archives/portable_binary.hpp restates cereal's byte layer).
+int ref_cache_write(void* h, const char* path) {
+    auto* s = static_cast<RefScene*>(h);
+    std::ofstream output_file;
+    output_file.open(path, std::ios::out | std::ios::binary);
+    if (!output_file.is_open()) return -1;
+    cereal::PortableBinaryOutputArchive oarchive(output_file);
+    oarchive(s->tree);
+    return output_file.good() ? 0 : -1;
+}
+
+void* ref_cache_read(const char* path) {
+    std::ifstream kdtree_cache(path, std::ios::in | std::ios::binary);
+    if (!kdtree_cache.is_open()) return nullptr;
+    auto* s = new RefScene;
+    try {
+        cereal::PortableBinaryInputArchive iarchive(kdtree_cache);
+        iarchive(s->tree);
+    } catch (const std::exception&) {
+        delete s;
+        return nullptr;
+    }
     return s;
 }
 

@@ -129,3 +129,33 @@ def test_raytracer_end_to_end_matches_oracle(api, ob, scenes, soup):
     px = np.array(r.stdout.split("\n255\n", 1)[1].split(), dtype=np.int64)
     want = np.array(ob.write_p3(ob.tonemap(ref, 1)).split("\n255\n", 1)[1].split(), dtype=np.int64)
     assert (np.abs(px - want) <= 1).all() and (px == want).mean() > 0.999
+
+
+def test_kdtree_cache_flag(api, scenes, soup, tmp_path):
+    # main.cpp:142-167 through the CLI: first run builds and writes the named cache, later runs load it; a cache whose
+    # tree does not belong to its triangles is refused (the reference would render it). The scene set-up
+    # happens before the device is touched, so this runs without a GPU too (the run then stops with exit code 3).
+    cache = str(tmp_path / "kdtree.cache")
+    r = run(PT, soup, "-w", "16", "--kdtree-cache", cache)
+    assert r.returncode in (0, 3) and os.path.exists(cache), r.stderr
+    first = open(cache, "rb").read()
+    p = api.Scene.load_cache(cache)
+    assert p.num_triangles == 36 and p.height == 0
+    r = run(PT, soup, "-w", "16", "--kdtree-cache=" + cache)
+    assert r.returncode in (0, 3) and "Triangles      : 36" in r.stderr or r.returncode == 3
+    assert open(cache, "rb").read() == first  # loaded, not rewritten
+    stale = bytearray(first)
+    stale[9:13] = np.float32(42.0).tobytes()
+    open(cache, "wb").write(stale)
+    r = run(PT, soup, "-w", "16", "--kdtree-cache", cache)
+    assert r.returncode == 2 and "stale or foreign" in r.stderr
+
+
+@pytest.mark.gpu
+def test_render_from_kdtree_cache_is_identical(api, soup, tmp_path):
+    cache = str(tmp_path / "kdtree.cache")
+    a = run(RC, soup, "-w", "64", "--kdtree-cache", cache)
+    b = run(RC, soup, "-w", "64", "--kdtree-cache", cache)
+    c = run(RC, soup, "-w", "64")
+    assert a.returncode == b.returncode == c.returncode == 0, a.stderr
+    assert a.stdout == b.stdout == c.stdout

@@ -78,7 +78,7 @@ class LoadedScene(C.Structure):
 EXPORTS = [
     "trn_last_error", "trn_device_count", "trn_scene_create", "trn_scene_create_ex", "trn_scene_destroy", "trn_scene_get_info",
     "trn_scene_get_nodes", "trn_intersect", "trn_primary_hits", "trn_render", "trn_render_device", "trn_render_multi",
-    "trn_set_profiling", "trn_set_counting", "trn_intersect_counted", "trn_camera_setup", "trn_tonemap", "trn_write_p3", "trn_load_blend", "trn_load_soup", "trn_loaded_scene_free",
+    "trn_set_profiling", "trn_set_counting", "trn_intersect_counted", "trn_camera_setup", "trn_tonemap", "trn_write_p3", "trn_load_blend", "trn_load_soup", "trn_loaded_scene_free", "trn_scene_save_cache", "trn_scene_load_cache",
 ]
 
 _lib = None
@@ -106,6 +106,8 @@ def lib():
         L.trn_scene_create_ex.argtypes = [_f32p, _f32p, _f32p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
         L.trn_scene_create_ex.restype = C.c_int32
         L.trn_scene_destroy.argtypes = [C.c_void_p]
+        L.trn_scene_save_cache.argtypes = [C.c_void_p, C.c_char_p]
+        L.trn_scene_load_cache.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.trn_scene_get_info.argtypes = [C.c_void_p, C.POINTER(SceneInfo)]
         L.trn_scene_get_nodes.argtypes = [C.c_void_p, _u64p]
         L.trn_intersect.argtypes = [C.c_void_p, C.c_int32, _f32p, _f32p, C.c_uint64, _u32p, _f32p]
@@ -204,6 +206,20 @@ class Scene:
     @classmethod
     def from_dict(cls, scene):
         return cls(scene["vertices"], scene["normals"], scene["diffuse"], scene.get("reflective"), scene.get("reflectivity"))
+
+    @classmethod
+    def load_cache(cls, path):
+        """a kdtree.cache (main.cpp:147-152) written by this library or by the reference; refused when stale"""
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        _check(lib().trn_scene_load_cache(os.fsencode(path), C.byref(self.h)))
+        self.info = SceneInfo()
+        _check(lib().trn_scene_get_info(self.h, C.byref(self.info)))
+        return self
+
+    def save_cache(self, path):
+        """write the tree in the reference's kdtree.cache layout (main.cpp:158-165)"""
+        _check(lib().trn_scene_save_cache(self.h, os.fsencode(path)))
 
     def close(self):
         if getattr(self, "h", None):

@@ -1154,3 +1154,104 @@ int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_d
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------------ kdtree.cache (main.cpp:142-167)
+namespace {
+struct CacheWriter {
+    FILE* f;
+    bool ok = true;
+    void raw(const void* p, size_t n) { ok = ok && std::fwrite(p, 1, n, f) == n; }
+    void f32(const float* p, size_t n) { raw(p, n * sizeof(float)); }
+    void u64(uint64_t v) { raw(&v, 8); }
+};
+struct CacheReader {
+    FILE* f;
+    bool ok = true;
+    void raw(void* p, size_t n) { ok = ok && std::fread(p, 1, n, f) == n; }
+    uint64_t u64() {
+        uint64_t v = 0;
+        raw(&v, 8);
+        return v;
+    }
+};
+} // namespace
+
+int32_t trn_scene_save_cache(const trn_scene* scene, const char* path) {
+    if (!scene || !path) return trn::fail(TRN_ERR_INVALID, "null argument");
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return trn::fail(TRN_ERR_IO, std::string("cannot write ") + path);
+    CacheWriter w{f};
+    const uint8_t little = 1; // cereal::PortableBinaryOutputArchive: endianness flag of the writer
+    w.raw(&little, 1);
+    const trn::HostTriangles& t = scene->tris;
+    w.u64(t.count);
+    const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (uint32_t i = 0; i < t.count; ++i) { // Triangle::serialize, lib/triangle.h:89-92
+        const float* is = &t.isect[size_t(i) * 16]; // v0 n u v | uv vv uu denom
+        const float* sh = &t.shade[size_t(i) * 16]; // n0 n1 n2 reflectivity - - rgba
+        w.f32(&t.verts[size_t(i) * 9], 9);          // vertices
+        w.f32(sh, 9);                               // normals
+        w.f32(zero4, 4);                            // ambient (not carried, never read by a tracer)
+        w.f32(sh + 12, 4);                          // diffuse
+        w.f32(sh + 12, 4);                          // emissive: main.cpp:43 loads it from the DIFFUSE key
+        w.f32(&t.mirror[size_t(i) * 4], 4);         // reflective
+        w.f32(sh + 9, 1);                           // reflectivity
+        w.f32(is + 6, 3);                           // u
+        w.f32(is + 9, 3);                           // v
+        w.f32(is + 3, 3);                           // normal
+        w.f32(is + 12, 4);                          // uv vv uu denom
+    }
+    w.f32(scene->tree.box, 6);
+    w.u64(scene->tree.nodes.size());
+    w.raw(scene->tree.nodes.data(), scene->tree.nodes.size() * 8);
+    const bool ok = w.ok && std::fclose(f) == 0;
+    return ok ? TRN_OK : trn::fail(TRN_ERR_IO, std::string("short write to ") + path);
+}
+
+int32_t trn_scene_load_cache(const char* path, trn_scene** out) {
+    if (!path || !out) return trn::fail(TRN_ERR_INVALID, "null argument");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return trn::fail(TRN_ERR_IO, std::string("cannot read ") + path);
+    CacheReader r{f};
+    uint8_t little = 0;
+    r.raw(&little, 1);
+    const uint64_t n = r.u64();
+    if (!r.ok || little != 1 || n == 0 || n >= TRN_MISS_ID) {
+        std::fclose(f);
+        return trn::fail(TRN_ERR_INVALID, std::string(path) + ": not a little-endian kdtree.cache");
+    }
+    std::vector<float> verts(n * 9), normals(n * 9), diffuse(n * 4), reflective(n * 4), reflectivity(n);
+    float rec[48];
+    for (uint64_t i = 0; i < n && r.ok; ++i) {
+        r.raw(rec, sizeof rec);
+        std::memcpy(&verts[i * 9], rec, 9 * sizeof(float));
+        std::memcpy(&normals[i * 9], rec + 9, 9 * sizeof(float));
+        std::memcpy(&diffuse[i * 4], rec + 22, 4 * sizeof(float));
+        std::memcpy(&reflective[i * 4], rec + 30, 4 * sizeof(float));
+        reflectivity[i] = rec[34];
+    }
+    float box[6];
+    r.raw(box, sizeof box);
+    const uint64_t num_nodes = r.u64();
+    std::vector<uint64_t> nodes;
+    if (r.ok && num_nodes < (1ull << 32)) {
+        nodes.resize(num_nodes);
+        r.raw(nodes.data(), num_nodes * 8);
+    } else {
+        r.ok = false;
+    }
+    std::fclose(f);
+    if (!r.ok) return trn::fail(TRN_ERR_INVALID, std::string(path) + ": truncated kdtree.cache");
+    trn_scene* sc = nullptr;
+    const int32_t rc = trn_scene_create_ex(verts.data(), normals.data(), diffuse.data(), reflective.data(), reflectivity.data(),
+                                           static_cast<uint32_t>(n), &sc);
+    if (rc != TRN_OK) return rc;
+    // the reference would now traverse whatever the file holds (main.cpp:147-152); here the cached tree must be the tree
+    // of the cached triangles
+    if (sc->tree.nodes != nodes || std::memcmp(sc->tree.box, box, sizeof box) != 0) {
+        trn_scene_destroy(sc);
+        return trn::fail(TRN_ERR_INVALID, std::string(path) + ": cached kd-tree does not belong to the cached triangles (stale or foreign kdtree.cache)");
+    }
+    *out = sc;
+    return TRN_OK;
+}

@@ -49,6 +49,8 @@ std::string usage_text() {
          "  --seed=<int>                      Run seed of the hemisphere streams [default: 1].\n"
          "  --dump-linear=<file>              Also write the linear RGBA sums (raw float32).\n"
          "  --dump-hits=<file>                Also write primary-hit triangle ids (raw uint32).\n"
+         "  --kdtree-cache=<file>             Load the triangles + kd-tree from this kdtree.cache if it exists (refused\n"
+         "                                    when stale), else build them and write it [default: none].\n"
          "  -h --help                         Show this text.\n\n";
     if (kPathtracer) {
         u << "Pathtracer options:\n"
@@ -78,7 +80,7 @@ struct Options {
     bool verbose = false;
     long gpus = 1;
     unsigned long long seed = 1;
-    std::string dump_linear, dump_hits;
+    std::string dump_linear, dump_hits, kdtree_cache;
     // TracerConfig defaults (config.h:106-117); the pathtracer USAGE overrides -m to 8 (pathtracer.h:24)
     long max_depth = 3;
     float max_visibility = 2;
@@ -108,6 +110,7 @@ const OptSpec kSpecs[] = {
     {nullptr, "--exposure", true, 7},    {"-v", "--verbose", false, 7},
     {nullptr, "--gpus", true, 7},        {nullptr, "--seed", true, 7},
     {nullptr, "--dump-linear", true, 7}, {nullptr, "--dump-hits", true, 7},
+    {nullptr, "--kdtree-cache", true, 7},
     {"-h", "--help", false, 7},          {"-d", "--max-depth", true, 1 | 4},
     {"-p", "--pixel-samples", true, 1},  {"-m", "--monte-carlo-samples", true, 1},
     {nullptr, "--max-visibility", true, 2}, {nullptr, "--shadow", true, 4},
@@ -136,6 +139,7 @@ void apply(Options& o, const OptSpec& s, const std::string& v) {
         else if (n == "--seed") o.seed = std::stoull(v);
         else if (n == "--dump-linear") o.dump_linear = v;
         else if (n == "--dump-hits") o.dump_hits = v;
+        else if (n == "--kdtree-cache") o.kdtree_cache = v;
         else if (n == "--max-depth") o.max_depth = std::stol(v);
         else if (n == "--pixel-samples") o.pixel_samples = std::stol(v);
         else if (n == "--monte-carlo-samples") o.mc_samples = std::stol(v);
@@ -308,9 +312,28 @@ int main(int argc, char const* argv[]) {
     setenv("TRN_BUILD_THREADS", std::to_string(o.threads).c_str(), 0);
     trn_scene* scene = nullptr;
     const auto t_kd = std::chrono::steady_clock::now();
-    if (trn_scene_create_ex(ls.verts, ls.normals, ls.diffuse, ls.reflective, ls.reflectivity, ls.num_triangles, &scene) != TRN_OK) {
-        std::cerr << trn_last_error() << std::endl;
-        return 2;
+    // main.cpp:142-167 reads ./kdtree.cache whenever it exists, whatever scene was asked for; here the file is named
+    // explicitly, and a cache whose tree does not belong to its triangles is refused (trn_scene_load_cache)
+    bool from_cache = false;
+    if (!o.kdtree_cache.empty()) {
+        if (FILE* probe = std::fopen(o.kdtree_cache.c_str(), "rb")) {
+            std::fclose(probe);
+            if (trn_scene_load_cache(o.kdtree_cache.c_str(), &scene) != TRN_OK) {
+                std::cerr << trn_last_error() << std::endl;
+                return 2;
+            }
+            from_cache = true;
+        }
+    }
+    if (!from_cache) {
+        if (trn_scene_create_ex(ls.verts, ls.normals, ls.diffuse, ls.reflective, ls.reflectivity, ls.num_triangles, &scene) != TRN_OK) {
+            std::cerr << trn_last_error() << std::endl;
+            return 2;
+        }
+        if (!o.kdtree_cache.empty() && trn_scene_save_cache(scene, o.kdtree_cache.c_str()) != TRN_OK) {
+            std::cerr << trn_last_error() << std::endl;
+            return 2;
+        }
     }
     std::cerr << "KDTree runtime: " << ms_since(t_kd) << std::endl; // main.cpp:168
     trn_scene_info info;
