@@ -254,7 +254,6 @@ def main():
     torch.cuda.synchronize()
 
     # ---- timed region: exactly K steps + the final reduce, barrier + synchronize on both sides
-    api.set_profiling(True)  # one CUDA-event pair per kernel launch on the launching stream (roofline leg)
     accum.zero_()
     if world > 1:
         dist.barrier()
@@ -270,8 +269,6 @@ def main():
         tot["rays"] += st.rays
         tot["shadow"] += st.shadow_rays
         tot["launches"] += st.launches
-        for k in ("ms_trace", "ms_shadow", "ms_shade", "ms_other"):
-            tot[k] += getattr(st, k)
         tot["trace_launches"] += st.trace_launches
         tot["trace_queries"] += st.trace_queries
         tot["shadow_launches"] += st.shadow_launches
@@ -283,7 +280,24 @@ def main():
     t_region1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
+    # ---- per-kernel durations for the roofline leg: the same K steps once more with one CUDA-event pair per kernel launch
+    # on the launching stream. Untimed for `value`: while every launch carries its own events the shadow waves are not
+    # overlapped with the next closest-hit wave (two streams), so the spans add up to the step and the shares can be
+    # compared with the serialised ncu launch list in profiles/.
+    api.set_profiling(True)
+    scratch = torch.zeros_like(accum)
+    ms_profiled = 0.0
+    for i in range(args.steps):
+        cfg.sample_begin = ((args.warmup + i) * world + rank) % pps
+        cfg.sample_stride = pps
+        st = scene.render_device(cam, cfg, scratch.data_ptr(), stream.cuda_stream, device=local_rank, want_stats=True)
+        flush.zero_()
+        for k in ("ms_trace", "ms_shadow", "ms_shade", "ms_other"):
+            tot[k] += getattr(st, k)
+        ms_profiled += st.ms_render
+    torch.cuda.synchronize()
     api.set_profiling(False)
+    del scratch
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     r = torch.tensor([tot["rays"]], device="cuda", dtype=torch.int64)
     if world > 1:
@@ -374,7 +388,8 @@ def main():
                              "tri_tests": cnt["a_tri"] / max(cnt["q"], 1),
                              "note": "visits of the production kernel on the device layout (empty-space cuts kept)"},
         "launches": tot["trace_launches"], "avg_launch_ms": tot["ms_trace"] / max(tot["trace_launches"], 1),
-        "share_of_step": tot["ms_trace"] / ms,
+        "share_of_step": tot["ms_trace"] / max(ms_profiled, 1e-9),
+        "profiled_pass_ms_per_step": ms_profiled / max(args.steps, 1),
         "kernel_ms": {k: tot[k] for k in ("ms_trace", "ms_shadow", "ms_shade", "ms_other")},
         "shadow_per_query": {"ref": [cnt["s_inner"] / max(cnt["s_q"], 1), cnt["s_leaf"] / max(cnt["s_q"], 1), cnt["s_tri"] / max(cnt["s_q"], 1)],
                              "actual": [cnt["sa_inner"] / max(cnt["s_q"], 1), cnt["sa_leaf"] / max(cnt["s_q"], 1), cnt["sa_tri"] / max(cnt["s_q"], 1)]},

@@ -554,3 +554,26 @@ def test_pooled_kernel_is_schedule_independent(api, ob, scenes, monkeypatch):
         assert np.array_equal(bits(r_g), bits(r_o)), (walk, gate, refill)
     for k in ("TRN_PERSISTENT", "TRN_PQ_WALK", "TRN_PQ_GATE", "TRN_PQ_REFILL"):
         monkeypatch.delenv(k)
+
+
+def test_shadow_waves_on_the_second_stream_change_nothing(api, scenes, monkeypatch):
+    # shadow waves overlapped with the next closest-hit wave (two streams, two shadow buffers) vs strictly serial launches:
+    # same counts, same image up to the fp32 order of the accumulation atomics; also with waves chunked small enough that
+    # both shadow buffers are reused many times per frame
+    sc = scenes.cubesphere(32)
+    p = api.Scene.from_dict(sc)
+    cam, cfg = api.make_config(sc, 192, max_depth=3, mc_samples=4, pixel_samples=2, seed=3)
+    out = {}
+    for cap in ("16777216", "8192"):
+        monkeypatch.setenv("TRN_WAVE_CAP", cap)
+        for ov in ("0", "1"):
+            monkeypatch.setenv("TRN_SHADOW_OVERLAP", ov)
+            img, st = p.render(cam, cfg)
+            out[(cap, ov)] = (img.copy(), st.rays, st.shadow_rays)
+    base = out[("16777216", "0")]
+    for k, v in out.items():
+        assert v[1:] == base[1:], k
+        d = np.abs(v[0] - base[0])
+        assert (d <= 2e-4 * (1 + np.abs(base[0]))).all(), (k, float(d.max()))
+    monkeypatch.delenv("TRN_WAVE_CAP")
+    monkeypatch.delenv("TRN_SHADOW_OVERLAP")

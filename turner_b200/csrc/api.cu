@@ -82,7 +82,11 @@ struct DeviceScene {
     std::vector<RayWave> waves;   // one per depth level in use
     std::vector<void*> wave_mem;  // backing allocations of `waves`
     ShadowWave shadow{};
+    ShadowWave shadow_alt{};        // second shadow wave: shadow waves run on stream_b next to the following closest-hit wave
     void* shadow_mem = nullptr;
+    cudaStream_t stream_b = nullptr;
+    cudaEvent_t ev_shaded = nullptr, ev_shadow_done[2] = {nullptr, nullptr};
+    bool shadow_pending[2] = {false, false};
     uint4* d_hits = nullptr;
     uint32_t *d_keys = nullptr, *d_keys_alt = nullptr, *d_order = nullptr, *d_order_alt = nullptr; // ray sorting
     void* d_sort_tmp = nullptr;
@@ -136,6 +140,10 @@ struct DeviceScene {
         cudaFree(d_jitter);
         cudaFree(d_accum);
         if (ev_sync) cudaEventDestroy(ev_sync);
+        if (ev_shaded) cudaEventDestroy(ev_shaded);
+        for (cudaEvent_t e : ev_shadow_done)
+            if (e) cudaEventDestroy(e);
+        if (stream_b) cudaStreamDestroy(stream_b);
         if (stream) cudaStreamDestroy(stream);
         device = -1;
     }
@@ -281,6 +289,10 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
         ds->pooled = leaves >= 1024 && refs_per_leaf <= 16.0;
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream_b, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_shaded, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_shadow_done[0], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_shadow_done[1], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_sync, cudaEventDisableTiming));
     ds->counter_slots = 4096;
     CUDA_TRY(cudaMalloc(&ds->d_counters, ds->counter_slots * sizeof(WaveCounters)));
@@ -400,19 +412,20 @@ static void launch_closest(DeviceScene* ds, int mode, cudaStream_t stream, const
 }
 
 // any-hit traversal of the shadow wave built by shade_bounce_kernel (count in counters->shadow_count, at most n_max)
-static void launch_shadow(DeviceScene* ds, int mode, cudaStream_t stream, uint32_t n_max, WaveCounters* counters, float4* acc) {
+static void launch_shadow(DeviceScene* ds, int mode, cudaStream_t stream, const ShadowWave& sw, uint32_t n_max, WaveCounters* counters,
+                          float4* acc) {
     if (mode == 3) {
         trace_pooled_kernel<1><<<persistent_grid(ds->grid_pooled[1], n_max), 128, 0, stream>>>(
-            ds->dev, static_cast<const float4*>(ds->d_planes), ds->shadow.a, ds->shadow.b, ds->shadow.c, nullptr, nullptr, 0,
+            ds->dev, static_cast<const float4*>(ds->d_planes), sw.a, sw.b, sw.c, nullptr, nullptr, 0,
             &counters->shadow_count, &counters->shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_PQ_REFILL", 28)),
             static_cast<int>(env_u64("TRN_PQ_WALK", 12)), pool_chunk_for(ds, n_max), static_cast<int>(env_u64("TRN_PQ_GATE", 10)));
     } else if (mode == 2) {
-        TRN_LAUNCH_WW(1, ds->two_pass, persistent_grid(ds->grid_shadow, n_max), stream, ds->dev, ds->shadow.a, ds->shadow.b,
-                      ds->shadow.c, nullptr, nullptr, 0, &counters->shadow_count, &counters->shadow_cursor, nullptr, acc,
+        TRN_LAUNCH_WW(1, ds->two_pass, persistent_grid(ds->grid_shadow, n_max), stream, ds->dev, sw.a, sw.b,
+                      sw.c, nullptr, nullptr, 0, &counters->shadow_count, &counters->shadow_cursor, nullptr, acc,
                       static_cast<int>(env_u64("TRN_REFILL", 26)), static_cast<int>(env_u64("TRN_QUANTA", 2)), nullptr,
                       ds->treelet_pairs, pool_chunk_for(ds, n_max));
     } else {
-        trace_shadow_kernel<<<blocks_for(n_max, 128), 128, 0, stream>>>(ds->dev, ds->shadow, counters, acc);
+        trace_shadow_kernel<<<blocks_for(n_max, 128), 128, 0, stream>>>(ds->dev, sw, counters, acc);
     }
 }
 
@@ -446,9 +459,10 @@ static int ensure_waves(DeviceScene* ds, uint64_t cap, int levels) {
         CUDA_TRY(cudaMalloc(&ds->d_sort_tmp, std::max<size_t>(ds->sort_tmp_bytes, 16)));
     }
     if (!ds->shadow_mem) {
-        CUDA_TRY(cudaMalloc(&ds->shadow_mem, cap * 3 * sizeof(float4)));
+        CUDA_TRY(cudaMalloc(&ds->shadow_mem, cap * 6 * sizeof(float4)));
         float4* p = static_cast<float4*>(ds->shadow_mem);
         ds->shadow = ShadowWave{p, p + cap, p + 2 * cap};
+        ds->shadow_alt = ShadowWave{p + 3 * cap, p + 4 * cap, p + 5 * cap};
     }
     while (static_cast<int>(ds->waves.size()) < levels) {
         void* mem = nullptr;
@@ -545,18 +559,21 @@ struct KernelTimer {
     cudaStream_t stream;
     bool on;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> spans;
+    cudaStream_t cur = nullptr; // stream of the span that is open
     explicit KernelTimer(cudaStream_t s) : stream(s), on(g_profiling.load() != 0) {}
-    void begin(int kind) {
+    void begin(int kind) { begin(kind, stream); }
+    void begin(int kind, cudaStream_t s) {
         if (!on) return;
         cudaEvent_t a, b;
         cudaEventCreate(&a);
         cudaEventCreate(&b);
-        cudaEventRecord(a, stream);
+        cudaEventRecord(a, s);
+        cur = s;
         spans.push_back({kind, {a, b}});
     }
     void end() {
         if (!on) return;
-        cudaEventRecord(spans.back().second.second, stream);
+        cudaEventRecord(spans.back().second.second, cur);
     }
     void collect(trn_stats* st) {
         for (auto& s : spans) {
@@ -595,6 +612,8 @@ struct Renderer {
     int mode_closest, mode_shadow;
     bool sort_rays = env_u64("TRN_SORT", 0) != 0 && ds->two_pass; // experiment: (octant, Morton) order for secondary waves; measured no gain (profiles/README.md)
     uint64_t cap;
+    bool shadow_overlap = env_u64("TRN_SHADOW_OVERLAP", 1) != 0;
+    uint32_t shadow_use = 0;
 
     Renderer(DeviceScene* d, const FrameParams& f, int integ, float4* a, cudaStream_t s)
         : ds(d), fp(f), integrator(integ), acc(a), stream(s), timer(s), mode_closest(persistent_mode(d, false)),
@@ -644,21 +663,40 @@ struct Renderer {
             }
             rays += n;
             RayWave next = spawn ? ds->waves[depth + 1] : RayWave{nullptr, nullptr, nullptr};
+            // The shadow wave of this chunk is traced on a second stream, next to the closest-hit wave of the next depth
+            // (both only depend on this shade kernel): the tail of one persistent kernel is filled by the head of the
+            // other. Two shadow buffers alternate; a buffer is rewritten only after its last shadow kernel is done.
+            // (not while every launch is timed with its own event pair: the spans of the two streams would overlap)
+            const bool overlap = shadow_overlap && !counting && !timer.on && fp.has_light;
+            const int sb = overlap ? static_cast<int>(shadow_use++ & 1u) : 0;
+            const ShadowWave& sw = sb ? ds->shadow_alt : ds->shadow;
+            if (overlap && ds->shadow_pending[sb]) CUDA_TRY(cudaStreamWaitEvent(stream, ds->ev_shadow_done[sb], 0));
             timer.begin(2);
             shade_bounce_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(ds->dev, fp, first_local_index, w, ds->d_hits, n, depth, next,
-                                                                       ds->shadow, ds->d_counters + cs, acc);
+                                                                       sw, ds->d_counters + cs, acc);
             timer.end();
             ++launches;
             CUDA_TRY(cudaMemcpyAsync(ds->h_counters + cs, ds->d_counters + cs, sizeof(WaveCounters), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaEventRecord(ds->ev_sync, stream));
             if (fp.has_light) {
-                timer.begin(1);
-                if (counting)
-                    trace_shadow_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, ds->shadow, ds->d_counters + cs, acc,
+                if (counting) {
+                    timer.begin(1);
+                    trace_shadow_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, sw, ds->d_counters + cs, acc,
                                                                                        ds->d_visits + 3);
-                else
-                    launch_shadow(ds, mode_shadow, stream, n, ds->d_counters + cs, acc);
-                timer.end();
+                    timer.end();
+                } else if (overlap) {
+                    CUDA_TRY(cudaEventRecord(ds->ev_shaded, stream));
+                    CUDA_TRY(cudaStreamWaitEvent(ds->stream_b, ds->ev_shaded, 0));
+                    timer.begin(1, ds->stream_b);
+                    launch_shadow(ds, mode_shadow, ds->stream_b, sw, n, ds->d_counters + cs, acc);
+                    timer.end();
+                    CUDA_TRY(cudaEventRecord(ds->ev_shadow_done[sb], ds->stream_b));
+                    ds->shadow_pending[sb] = true;
+                } else {
+                    timer.begin(1);
+                    launch_shadow(ds, mode_shadow, stream, sw, n, ds->d_counters + cs, acc);
+                    timer.end();
+                }
                 ++launches;
                 ++shadow_launches;
             }
@@ -724,6 +762,11 @@ struct Renderer {
             int rc = process(0, ds->waves[0], n, first);
             if (rc) return rc;
         }
+        for (int sb = 0; sb < 2; ++sb) // the caller's stream sees the frame complete only after the last shadow waves
+            if (ds->shadow_pending[sb]) {
+                CUDA_TRY(cudaStreamWaitEvent(stream, ds->ev_shadow_done[sb], 0));
+                ds->shadow_pending[sb] = false;
+            }
         if (integrator == TRN_RAYCASTER) {
             unsigned long long hc = 0;
             CUDA_TRY(cudaMemcpyAsync(&hc, ds->d_hitcount, sizeof hc, cudaMemcpyDeviceToHost, stream));
