@@ -51,3 +51,9 @@ def test_pooled_cycle_matches_per_ray_traversal(emulator, tmp_path, n):
         assert int(hits) > 0
         total += int(rays)
     assert total > 20000
+    # the shadow wave of every depth through the any-hit mode of the cycle (inclusive tmax, cells beyond the light pruned)
+    shadows = re.findall(r"shadow (\d): (\d+) rays, (\d+) occluded, completed (\d), differences (\d+)", out)
+    assert len(shadows) == 3, out
+    for depth, rays, occluded, completed, diff in shadows:
+        assert completed == "1" and diff == "0" and int(rays) > 0, out
+    assert sum(int(s[2]) for s in shadows) > 0  # some rays are occluded

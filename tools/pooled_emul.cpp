@@ -24,6 +24,7 @@ static const int kPqLeaves = 64, kPqChunkTris = 4, kPqSurv = 32 + 32 * 4;
 
 struct Ray {
     float o[3], d[3];
+    float tmax = 0.f; // any-hit (shadow) queries: inclusive distance to the light
 };
 struct Hit {
     uint32_t id = kMiss;
@@ -120,6 +121,77 @@ static void trace_plain(const Scene& sc, const Ray& ray, Hit& out) {
     }
 }
 
+// plain per-ray any-hit traversal (= traverse_pairs<true>): occluded <=> an accepted triangle with 0 <= r <= tmax
+static bool occluded_plain(const Scene& sc, const Ray& ray) {
+    const float ox = ray.o[0], oy = ray.o[1], oz = ray.o[2], dx = ray.d[0], dy = ray.d[1], dz = ray.d[2], tmax = ray.tmax;
+    const float ix = 1 / dx, iy = 1 / dy, iz = 1 / dz;
+    const float* box = sc.tree.box;
+    float tx1 = (box[0] - ox) * ix, tx2 = (box[3] - ox) * ix;
+    float tenter = std::fmin(tx1, tx2), texit = std::fmax(tx1, tx2);
+    float ty1 = (box[1] - oy) * iy, ty2 = (box[4] - oy) * iy;
+    tenter = std::fmax(tenter, std::fmin(ty1, ty2));
+    texit = std::fmin(texit, std::fmax(ty1, ty2));
+    float tz1 = (box[2] - oz) * iz, tz2 = (box[5] - oz) * iz;
+    tenter = std::fmax(tenter, std::fmin(tz1, tz2));
+    texit = std::fmin(texit, std::fmax(tz1, tz2));
+    if (texit < tenter) return false;
+    if (tenter < 0.f) tenter = 0.f;
+    struct E {
+        uint32_t x, y;
+        float a, b;
+    } stack[64];
+    int sp = 0;
+    const uint64_t* pn = sc.tree.pair_nodes.data();
+    uint32_t nx_ = uint32_t(pn[0]), ny_ = uint32_t(pn[0] >> 32);
+    for (;;) {
+        while ((ny_ & 3u) != 3u) {
+            const int ax = int(ny_ & 3u);
+            const float split = bfloat(nx_);
+            const uint32_t ci = ny_ >> 2;
+            const uint32_t px = uint32_t(pn[ci]), py = uint32_t(pn[ci] >> 32), pz = uint32_t(pn[ci + 1]), pw = uint32_t(pn[ci + 1] >> 32);
+            const float o_ax = ax == 0 ? ox : (ax == 1 ? oy : oz), i_ax = ax == 0 ? ix : (ax == 1 ? iy : iz);
+            const float t = (split - o_ax) * i_ax;
+            const bool flip = std::signbit(i_ax);
+            const uint32_t nearx = flip ? pz : px, neary = flip ? pw : py, farx = flip ? px : pz, fary = flip ? py : pw;
+            const bool near_only = texit < t, far_only = !near_only && (t < tenter), both = !near_only && !far_only;
+            const bool go_far = far_only || (both && neary == 3u);
+            if (both && neary != 3u && fary != 3u) stack[sp++] = E{farx, fary, t, texit};
+            nx_ = go_far ? farx : nearx;
+            ny_ = go_far ? fary : neary;
+            const float te = (both && go_far) ? t : tenter, tx = (both && !go_far) ? t : texit;
+            tenter = te;
+            texit = tx;
+        }
+        const uint32_t first = nx_, cnt = ny_ >> 2;
+        const float r_lo = tenter - kCellSlack * (std::fabs(tenter) + 1.f), r_hi = texit + kCellSlack * (std::fabs(texit) + 1.f);
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t id = sc.tree.pair_leaf_refs[first + i];
+            const float* q = &sc.tris.isect[size_t(id) * 16];
+            const float nx = q[3], ny = q[4], nz = q[5];
+            const float denom = nx * dx + ny * dy + nz * dz;
+            if (denom == 0.f) continue;
+            const float nom = nx * (q[0] - ox) + ny * (q[1] - oy) + nz * (q[2] - oz);
+            const float r = nom / denom;
+            if (!(r >= 0.f) || !(r <= tmax) || !(r >= r_lo && r <= r_hi)) continue;
+            const float wx = (ox + r * dx) - q[0], wy = (oy + r * dy) - q[1], wz = (oz + r * dz) - q[2];
+            const float wv = wx * q[9] + wy * q[10] + wz * q[11];
+            const float wu = wx * q[6] + wy * q[7] + wz * q[8];
+            const float s = (q[12] * wv - q[13] * wu) / q[15];
+            if (s < 0.f) continue;
+            const float t = (q[12] * wu - q[14] * wv) / q[15];
+            if (t < 0.f || 1.f < s + t) continue;
+            return true;
+        }
+        if (sp == 0) return false;
+        const E e = stack[--sp];
+        nx_ = e.x;
+        ny_ = e.y;
+        tenter = e.a;
+        texit = e.b;
+        if (tenter > tmax) return false;
+    }
+}
+
 struct U4 {
     uint32_t x, y, z, w;
 };
@@ -128,8 +200,10 @@ struct F4 {
 };
 
 // one emulated warp over rays[begin, end); returns false on a detected hang
+// any: MODE 1 of the kernel (shadow rays: occluded <=> an accepted triangle with 0 <= r <= tmax); hits[i].id is then 0 for
+// occluded, kMiss for unoccluded
 static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin, size_t end, std::vector<Hit>& hits, int refill_below,
-                     int walk_iters, int leaf_gate, uint64_t* stat) {
+                     int walk_iters, int leaf_gate, uint64_t* stat, bool any = false) {
     F4 s_ray[64];
     U4 s_leaf[kPqLeaves];
     uint32_t s_surv[kPqSurv][2];
@@ -144,7 +218,8 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
         uint32_t nx, ny;
         uint32_t best_id, best_seq, idx;
         float best_r, best_s, best_t;
-        bool busy = false, walking = false;
+        bool busy = false, walking = false, occluded = false;
+        float tmax = 0.f;
     };
     std::vector<LaneS> L(32);
     size_t next = begin;
@@ -193,7 +268,10 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
                 l.best_s = l.best_t = 0.f;
                 l.best_seq = 0;
                 l.last_texit = -kFltMax;
-                                l.busy = l.walking = true;
+                                l.busy = true;
+                l.occluded = false;
+                l.tmax = ry.tmax;
+                l.walking = !(any && l.tenter > l.tmax);
                 const float E = 1.9073486e-6f * (3.f * scale + (std::fabs(l.ox) + std::fabs(l.oy) + std::fabs(l.oz)));
                 const float F = 9.5367432e-7f * (std::fabs(dx) + std::fabs(dy) + std::fabs(dz));
                 s_ray[2 * lane] = F4{l.ox, l.oy, l.oz, E};
@@ -229,7 +307,7 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
                             float lo = l.tenter - kCellSlack * (std::fabs(l.tenter) + 1.f);
                             float hi = l.texit + kCellSlack * (std::fabs(l.texit) + 1.f);
                             lo = std::fmax(lo, 0.f);
-                            hi = std::fmin(hi, l.best_r);
+                            hi = any ? std::fmin(hi, l.tmax) : std::fmin(hi, l.best_r);
                             s_leaf[slot] = U4{l.nx, cnt | (uint32_t(lane) << 24), fbits(lo), fbits(hi)};
                         } else {
                             blocked[lane] = true;
@@ -244,7 +322,7 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
                             l.ny = e.y;
                             l.tenter = bfloat(e.z);
                             l.texit = bfloat(e.w);
-                            if (l.tenter > l.best_r) l.walking = false;
+                            if (any ? l.tenter > l.tmax : l.tenter > l.best_r) l.walking = false;
                         }
                     }
                 }
@@ -295,7 +373,7 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
                 p.id = s_surv[sbase + lane][0];
                 p.owner = s_surv[sbase + lane][1] & 31u;
                 p.seq = s_surv[sbase + lane][1] >> 5;
-                const float lim = L[p.owner].best_r;
+                const float lim = any ? L[p.owner].tmax : L[p.owner].best_r;
                 const F4 ro = s_ray[2 * p.owner], rd = s_ray[2 * p.owner + 1];
                 const float* q = &sc.tris.isect[size_t(p.id) * 16];
                 const float nx = q[3], ny = q[4], nz = q[5];
@@ -317,7 +395,9 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
                 const P& p = res[lane];
                 if (!p.pass) continue;
                 LaneS& o = L[p.owner];
-                if (p.r < o.best_r || (p.r == o.best_r && p.seq < o.best_seq)) {
+                if (any) {
+                    o.occluded = true;
+                } else if (p.r < o.best_r || (p.r == o.best_r && p.seq < o.best_seq)) {
                     o.best_id = p.id;
                     o.best_r = p.r;
                     o.best_s = p.s;
@@ -386,11 +466,12 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
             LaneS& l = L[lane];
             if (!l.busy) continue;
             l.best_seq = 0;
-            const bool finished = !l.walking || (l.best_id != kMiss && (l.best_r <= l.last_texit || l.best_r < l.tenter));
+            const bool finished = any ? (l.occluded || !l.walking)
+                                      : (!l.walking || (l.best_id != kMiss && (l.best_r <= l.last_texit || l.best_r < l.tenter)));
             if (finished) {
                 l.busy = false;
                 Hit h;
-                h.id = l.best_id;
+                h.id = any ? (l.occluded ? 0u : kMiss) : l.best_id;
                 h.r = l.best_r;
                 h.s = l.best_s;
                 h.t = l.best_t;
@@ -475,6 +556,48 @@ int main(int argc, char** argv) {
                     "tests %.1f survivors %.2f\n",
                     stat[0] / nr, double(stat[1]) / std::max<uint64_t>(1, stat[0]), stat[2] / nr, double(stat[3]) / std::max<uint64_t>(1, stat[2]),
                     stat[4] / nr, double(stat[5]) / std::max<uint64_t>(1, stat[4]), stat[6] / nr, stat[5] / nr);
+        {
+            // shadow wave of this depth (pathtracer.cpp:44-58): from the offset hit point towards the light of
+            // scenes.cubesphere(), inclusive tmax = distance to the light; any-hit mode of the kernel vs the plain traversal
+            const float Lp[3] = {3.f, 4.f, 5.f};
+            std::vector<Ray> sh;
+            for (size_t i = 0; i < wave.size(); ++i) {
+                if (ref[i].id == kMiss) continue;
+                const float* q = &sc.tris.isect[size_t(ref[i].id) * 16];
+                Ray r;
+                float l2 = 0.f, q2 = 0.f, ld[3];
+                for (int c = 0; c < 3; ++c) {
+                    const float p = wave[i].o[c] + ref[i].r * wave[i].d[c];
+                    r.o[c] = p + 0.0001f * q[3 + c];
+                    ld[c] = Lp[c] - p;
+                    l2 += ld[c] * ld[c];
+                    q2 += (Lp[c] - r.o[c]) * (Lp[c] - r.o[c]);
+                }
+                const float inv = 1 / std::sqrt(l2);
+                for (int c = 0; c < 3; ++c) r.d[c] = inv * ld[c];
+                r.tmax = std::sqrt(q2);
+                if (r.d[0] * q[3] + r.d[1] * q[4] + r.d[2] * q[5] > 0.f) sh.push_back(r); // lit side only, as shade_bounce_kernel
+            }
+            std::vector<Hit> sgot(sh.size());
+            std::vector<uint8_t> sref(sh.size());
+#pragma omp parallel for schedule(dynamic, 256)
+            for (long i = 0; i < long(sh.size()); ++i) sref[i] = occluded_plain(sc, sh[i]);
+            const long snw = long((sh.size() + per - 1) / per);
+            bool sok = true;
+#pragma omp parallel for schedule(dynamic, 1)
+            for (long w = 0; w < snw; ++w) {
+                uint64_t st[8] = {0};
+                const bool r = warp_run(sc, sh, size_t(w) * per, std::min(sh.size(), size_t(w + 1) * per), sgot, 28, 12, 10, st, true);
+#pragma omp critical
+                sok &= r;
+            }
+            size_t sdiff = 0, socc = 0;
+            for (size_t i = 0; i < sh.size(); ++i) {
+                socc += sref[i];
+                sdiff += (sgot[i].id != kMiss) != (sref[i] != 0);
+            }
+            std::printf("shadow %d: %zu rays, %zu occluded, completed %d, differences %zu\n", depth, sh.size(), socc, int(sok), sdiff);
+        }
         std::vector<Ray> next;
         for (size_t base = 0; base < wave.size(); base += 32) {
             std::vector<size_t> hl;
