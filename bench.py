@@ -200,7 +200,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     config = {"workload": w["desc"], "step": "one pixel-sample pass over the full frame per rank",
               "sample_split": "rank g renders sample (step*N+g) mod %d; one reduce(sum) of W*H*4 f32 at the end" % w["pixel_samples"],
-              "l2": "flushed between steps (256 MiB memset inside the timed region)", "seed": 1}
+              "l2": "flushed between steps (256 MiB memset inside the timed region)", "seed": 1,
+              "kernel_timing": "value: CUDA events around the K timed steps, no per-kernel events; roofline.kernel_ms: the same K "
+                               "steps once more with one event pair per launch (shadow/closest-hit waves then run serially)"}
 
     if args.impl == "reference":
         # the reference arm: rank 0 alone times the reference's CPU path; other ranks exit
