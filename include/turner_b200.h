@@ -10,9 +10,13 @@
  *
  * All entry points: plain pointers and sizes, no C++/torch types, return 0 on
  * success or a negative trn_status; trn_last_error() gives the message of the
- * last failure on the calling thread. Nothing here aborts. There is NO CPU
- * fallback: compute entry points fail with TRN_ERR_CUDA when no sm_100 device
+ * last failure on the calling thread. Nothing here aborts or throws. There is NO
+ * CPU fallback: compute entry points fail with TRN_ERR_CUDA when no sm_100 device
  * is usable.
+ *
+ * Threads: a trn_scene may be used from several threads; compute calls on the
+ * same scene AND device serialise on a per-device lock (one set of wave buffers
+ * per device), calls on different devices run concurrently.
  *
  * Citations are relative to the reference repository root.
  */
@@ -99,6 +103,10 @@ typedef struct trn_stats {
     /* ... and what the production kernels really visit on the device layout (sibling pairs + empty-space cuts) */
     uint64_t trace_actual_inner, trace_actual_leaf_nodes, trace_actual_tri_tests;
     uint64_t shadow_actual_inner, shadow_actual_leaf_nodes, shadow_actual_tri_tests;
+    /* host-buffer / multi-GPU variants: device time of the ncclReduce(sum) of the accumulation buffers and of the
+     * device->host copy of the image; both are part of ms_render */
+    double ms_reduce;
+    double ms_d2h;
 } trn_stats;
 
 typedef struct trn_scene_info {
@@ -158,6 +166,39 @@ int32_t trn_render_device(trn_scene* scene, int32_t device, const trn_camera* ca
  * of the float accumulation buffers onto devices[0]). libnccl is dlopen()ed on first use. */
 int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_devices, const trn_camera* cam,
                          const trn_render_config* cfg, float* out_rgba_sum, trn_stats* stats);
+
+/* ---- process-per-GPU jobs (one rank per process: torchrun, mpirun ...). The image reduce is this library's own
+ * ncclReduce; the launcher only has to carry the 128-byte id from rank 0 to the other ranks.
+ *   trn_comm_unique_id  rank 0: ncclGetUniqueId
+ *   trn_comm_init_rank  every rank: ncclCommInitRank on `device`
+ *   trn_render_rank     every rank: renders its share of the pixel samples (i = sample_begin + sample_stride * (rank +
+ *                       nranks * k), scene replicated), then ONE ncclReduce(sum) onto rank 0; rank 0 copies the summed
+ *                       image to out_rgba_sum (host, width*height*4 floats; NULL = leave it on the device, ignored on the
+ *                       other ranks). stats are this rank's (rays of its share; ms_reduce / ms_d2h filled). Blocking. */
+typedef struct trn_comm trn_comm;
+int32_t trn_comm_unique_id(uint8_t* id128);
+int32_t trn_comm_init_rank(const uint8_t* id128, int32_t nranks, int32_t rank, int32_t device, trn_comm** out);
+void trn_comm_destroy(trn_comm* comm);
+int32_t trn_render_rank(trn_scene* scene, trn_comm* comm, const trn_camera* cam, const trn_render_config* cfg,
+                        float* out_rgba_sum, trn_stats* stats);
+
+/* ---- asynchronous frames: trn_render_async returns at once; trn_wait blocks until out_rgba_sum (host, ideally
+ * pinned) holds the frame, fills stats and frees the job. Frames of one scene+device render one after the other, but the
+ * device->host copy of frame k runs next to the render of frame k+1 (two accumulation buffers, a copy stream). */
+typedef struct trn_job trn_job;
+int32_t trn_render_async(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
+                         float* out_rgba_sum, trn_job** job);
+int32_t trn_wait(trn_job* job, trn_stats* stats);
+
+/* ---- occlusion parity hook: the shadow predicate of pathtracer.cpp:49-53 for arbitrary rays --
+ * occluded[i] = 1 iff some triangle is accepted by intersect_ray_triangle (lib/intersection.h:63-89) with
+ * 0 <= r <= tmax[i], i.e. NOT (!hit || r_closest > dist_to_light). Runs the production any-hit kernels. */
+int32_t trn_occluded(trn_scene* scene, int32_t device, const float* origins, const float* dirs, const float* tmax, uint64_t n,
+                     uint8_t* occluded);
+
+/* ---- measured ceilings for the roofline of the traversal kernels: GB/s of independent random 16-byte gathers (the
+ * kernels' access shape) over a working set of set_bytes; mode 0 = long run for a set that fits L1, 1 = L2 / HBM sets */
+int32_t trn_measure_gather_peak(int32_t device, uint64_t set_bytes, int32_t mode, double* gbps);
 
 /* per-kernel timing inside trn_render* (adds an event pair per launch); off by default */
 void trn_set_profiling(int32_t enabled);

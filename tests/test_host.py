@@ -126,3 +126,43 @@ def test_no_cpu_fallback(api, scenes):
         with pytest.raises(api.TurnerError) as e:
             call()
         assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_write_p3_nan_inf_negative_pixels(api):
+    """a NaN channel used to index the 256-entry digit table out of range (SIGSEGV). NaN and negatives print 0,
+    +inf and anything above 255 print 255 (clamp of lib/raster.h:91-96; int(NaN) is undefined in the reference)."""
+    img = np.zeros((2, 3, 4), np.float32)
+    img[..., 3] = 1.0
+    img[0, 0, 0] = np.nan
+    img[0, 1, 1] = np.inf
+    img[0, 2, 2] = -np.inf
+    img[1, 0] = (-3.0, 0.5, 7.0, 1.0)
+    img[1, 1] = (0.25, np.nan, 1.0, np.nan)  # NaN alpha poisons every channel
+    txt = api.write_p3(img)
+    rows = txt.split("\n")
+    assert rows[0] == "P3" and rows[1] == "3 2" and rows[2] == "255"
+    assert rows[3] == "  0   0   0   0 255   0   0   0   0"
+    assert rows[4] == "  0 127 255   0   0   0   0   0   0"
+
+
+def test_tonemap_threads_do_not_change_the_result(api, monkeypatch):
+    rng = np.random.default_rng(3)
+    img = rng.random((512, 600, 4), dtype=np.float32) * 40
+    monkeypatch.setenv("TRN_HOST_THREADS", "1")
+    a = api.tonemap(img, 16, exposure=0.7)
+    monkeypatch.setenv("TRN_HOST_THREADS", "7")
+    b = api.tonemap(img, 16, exposure=0.7)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_cache_with_a_lying_header_is_refused_without_allocating(api, tmp_path):
+    """the u64 triangle count of an untrusted kdtree.cache sized five vectors before any payload was read"""
+    import struct
+    p = tmp_path / "kdtree.cache"
+    p.write_bytes(b"\x01" + struct.pack("<Q", (1 << 30) - 1))  # 9 bytes claiming 2^30-1 triangles
+    with pytest.raises(api.TurnerError) as e:
+        api.Scene.load_cache(str(p))
+    assert e.value.code == -1
+    p.write_bytes(b"\x01" + struct.pack("<Q", 5) + b"\0" * 100)  # count larger than the payload
+    with pytest.raises(api.TurnerError):
+        api.Scene.load_cache(str(p))

@@ -59,7 +59,8 @@ class Stats(C.Structure):
                 ("shadow_inner", C.c_uint64), ("shadow_leaf_nodes", C.c_uint64), ("shadow_tri_tests", C.c_uint64),
                 ("trace_actual_inner", C.c_uint64), ("trace_actual_leaf_nodes", C.c_uint64),
                 ("trace_actual_tri_tests", C.c_uint64), ("shadow_actual_inner", C.c_uint64),
-                ("shadow_actual_leaf_nodes", C.c_uint64), ("shadow_actual_tri_tests", C.c_uint64)]
+                ("shadow_actual_leaf_nodes", C.c_uint64), ("shadow_actual_tri_tests", C.c_uint64),
+                ("ms_reduce", C.c_double), ("ms_d2h", C.c_double)]
 
 
 class SceneInfo(C.Structure):
@@ -79,9 +80,20 @@ EXPORTS = [
     "trn_last_error", "trn_device_count", "trn_scene_create", "trn_scene_create_ex", "trn_scene_destroy", "trn_scene_get_info",
     "trn_scene_get_nodes", "trn_intersect", "trn_primary_hits", "trn_render", "trn_render_device", "trn_render_multi",
     "trn_set_profiling", "trn_set_counting", "trn_intersect_counted", "trn_camera_setup", "trn_tonemap", "trn_write_p3", "trn_load_blend", "trn_load_soup", "trn_loaded_scene_free", "trn_scene_save_cache", "trn_scene_load_cache",
+    "trn_comm_unique_id", "trn_comm_init_rank", "trn_comm_destroy", "trn_render_rank", "trn_render_async", "trn_wait",
+    "trn_occluded", "trn_measure_gather_peak",
 ]
 
 _lib = None
+_lib_override = None
+
+
+def use_library(path):
+    """development only (tools/ab_bench.py): load another build of the library; must be called before first use"""
+    global _lib_override
+    if _lib is not None:
+        raise RuntimeError("library already loaded")
+    _lib_override = path
 
 
 def build(verbose=False):
@@ -99,7 +111,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no fallback path)" % LIB_PATH)
-        L = C.CDLL(os.environ.get("TRN_LIB", LIB_PATH))  # TRN_LIB: A/B builds during kernel development
+        L = C.CDLL(_lib_override or LIB_PATH)
         L.trn_last_error.restype = C.c_char_p
         L.trn_device_count.restype = C.c_int32
         L.trn_scene_create.argtypes = [_f32p, _f32p, _f32p, C.c_uint32, C.POINTER(C.c_void_p)]
@@ -129,6 +141,21 @@ def lib():
         L.trn_load_soup.argtypes = [C.c_char_p, C.POINTER(LoadedScene)]
         L.trn_load_soup.restype = C.c_int32
         L.trn_loaded_scene_free.argtypes = [C.POINTER(LoadedScene)]
+        _u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+        L.trn_comm_unique_id.argtypes = [_u8p]
+        L.trn_comm_init_rank.argtypes = [_u8p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.trn_comm_destroy.argtypes = [C.c_void_p]
+        L.trn_comm_destroy.restype = None
+        L.trn_render_rank.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Camera), C.POINTER(RenderConfig), C.c_void_p,
+                                      C.POINTER(Stats)]
+        L.trn_render_async.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Camera), C.POINTER(RenderConfig), C.c_void_p,
+                                       C.POINTER(C.c_void_p)]
+        L.trn_wait.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.trn_occluded.argtypes = [C.c_void_p, C.c_int32, _f32p, _f32p, _f32p, C.c_uint64, _u8p]
+        L.trn_measure_gather_peak.argtypes = [C.c_int32, C.c_uint64, C.c_int32, C.POINTER(C.c_double)]
+        for f in ("trn_comm_unique_id", "trn_comm_init_rank", "trn_render_rank", "trn_render_async", "trn_wait",
+                  "trn_occluded", "trn_measure_gather_peak", "trn_scene_save_cache", "trn_scene_load_cache"):
+            getattr(L, f).restype = C.c_int32
         for f in ("trn_scene_create", "trn_scene_get_info", "trn_scene_get_nodes", "trn_intersect", "trn_primary_hits",
                   "trn_intersect_counted",
                   "trn_render", "trn_render_device", "trn_render_multi", "trn_camera_setup", "trn_tonemap",
@@ -291,6 +318,29 @@ class Scene:
                                        C.c_void_p(stream_ptr), C.byref(st) if want_stats else None))
         return st
 
+    def occluded(self, origins, dirs, tmax, device=-1):
+        """shadow predicate of pathtracer.cpp:49-53 for a batch of rays: True where an accepted hit has 0 <= r <= tmax"""
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(tmax, np.float32).reshape(-1)
+        assert o.shape[0] == d.shape[0] == t.shape[0]
+        out = np.zeros(o.shape[0], np.uint8)
+        _check(lib().trn_occluded(self.h, device, o, d, t, o.shape[0], out))
+        return out.astype(bool)
+
+    def render_rank(self, comm, cam, cfg, out=None, out_ptr=None):
+        """this rank's share of a process-per-GPU job + the ncclReduce onto rank 0 (+ D2H into `out` on rank 0)"""
+        st = Stats()
+        ptr = out_ptr if out_ptr is not None else (out.ctypes.data if out is not None else None)
+        _check(lib().trn_render_rank(self.h, comm.h, C.byref(cam), C.byref(cfg), C.c_void_p(ptr) if ptr else None, C.byref(st)))
+        return st
+
+    def render_async(self, cam, cfg, out, device=-1):
+        """start a frame; returns a job whose wait() gives the Stats once `out` (host array) holds the image"""
+        job = C.c_void_p()
+        _check(lib().trn_render_async(self.h, device, C.byref(cam), C.byref(cfg), C.c_void_p(out.ctypes.data), C.byref(job)))
+        return Job(job, out)
+
     def render_multi(self, cam, cfg, devices):
         out = np.zeros((cfg.height, cfg.width, 4), np.float32)
         st = Stats()
@@ -298,6 +348,43 @@ class Scene:
         _check(lib().trn_render_multi(self.h, devs, len(devices), C.byref(cam), C.byref(cfg), out.ctypes.data,
                                       C.byref(st)))
         return out, st
+
+
+class Job:
+    def __init__(self, h, out):
+        self.h, self.out = h, out
+
+    def wait(self):
+        st = Stats()
+        h, self.h = self.h, None
+        _check(lib().trn_wait(h, C.byref(st)))
+        return self.out, st
+
+
+class Comm:
+    """one rank of a process-per-GPU job: NCCL communicator owned by the library (trn_comm_*)"""
+
+    def __init__(self, unique_id, nranks, rank, device):
+        self.h = C.c_void_p()
+        self.nranks, self.rank, self.device = nranks, rank, device
+        _check(lib().trn_comm_init_rank(np.ascontiguousarray(unique_id, np.uint8), nranks, rank, device, C.byref(self.h)))
+
+    @staticmethod
+    def unique_id():
+        out = np.zeros(128, np.uint8)
+        _check(lib().trn_comm_unique_id(out))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().trn_comm_destroy(self.h)
+            self.h = None
+
+
+def measure_gather_peak(set_bytes, mode=1, device=-1):
+    g = C.c_double()
+    _check(lib().trn_measure_gather_peak(device, set_bytes, mode, C.byref(g)))
+    return g.value
 
 
 def tonemap(rgba_sum, pixel_samples, exposure=1.0, gamma_enabled=True, inverse_gamma=0.454545):

@@ -24,6 +24,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -53,6 +54,29 @@ int fail(int code, const std::string& msg) {
             return fail(TRN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
                                           std::to_string(__LINE__) + ")");                                      \
     } while (0)
+
+// extern "C" bodies: nothing may unwind through the C ABI (std::bad_alloc on a huge scene, a failed std::thread)
+#define TRN_GUARD_BEGIN try {
+#define TRN_GUARD_END                                                                            \
+    }                                                                                            \
+    catch (const std::bad_alloc&) { return fail(TRN_ERR_LIMIT, "out of host memory"); }          \
+    catch (const std::exception& e) { return fail(TRN_ERR_LIMIT, std::string("host error: ") + e.what()); }
+
+// scoped CUDA events (destroyed on every return path)
+template <int N> struct Events {
+    cudaEvent_t e[N] = {};
+    ~Events() {
+        for (cudaEvent_t x : e)
+            if (x) cudaEventDestroy(x);
+    }
+    cudaError_t create() {
+        for (cudaEvent_t& x : e) {
+            cudaError_t rc = cudaEventCreate(&x);
+            if (rc != cudaSuccess) return rc;
+        }
+        return cudaSuccess;
+    }
+};
 
 // scoped device allocation (freed on every return path)
 struct DevBuf {
@@ -107,9 +131,22 @@ struct DeviceScene {
     int jitter_w = 0, jitter_pps = 0;
     float4* d_accum = nullptr; // internal accumulation buffer for host-buffer renders
     size_t accum_pixels = 0;
+    float4* d_async[2] = {nullptr, nullptr}; // trn_render_async: two frames in flight (render k+1 next to the D2H of k)
+    size_t async_pixels[2] = {0, 0};
+    cudaEvent_t ev_async[2] = {nullptr, nullptr};
+    uint32_t async_use = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_copy = nullptr; // D2H of a finished frame next to the following render (trn_render_async)
     cudaEvent_t ev_sync = nullptr;
     double upload_ms = 0;
+    // Every compute entry point holds this for its whole duration: the wave buffers, counters ring, shadow buffers and
+    // streams above are one set of work state per device (include/turner_b200.h: calls on one scene+device serialise).
+    std::recursive_mutex mu;
+
+    DeviceScene() = default;
+    DeviceScene(const DeviceScene&) = delete;
+    DeviceScene& operator=(const DeviceScene&) = delete;
+    ~DeviceScene() { release(); }
 
     void release() {
         if (device < 0) return;
@@ -139,11 +176,16 @@ struct DeviceScene {
         cudaFree(d_visits);
         cudaFree(d_jitter);
         cudaFree(d_accum);
+        for (int k = 0; k < 2; ++k) {
+            cudaFree(d_async[k]);
+            if (ev_async[k]) cudaEventDestroy(ev_async[k]);
+        }
         if (ev_sync) cudaEventDestroy(ev_sync);
         if (ev_shaded) cudaEventDestroy(ev_shaded);
         for (cudaEvent_t e : ev_shadow_done)
             if (e) cudaEventDestroy(e);
         if (stream_b) cudaStreamDestroy(stream_b);
+        if (stream_copy) cudaStreamDestroy(stream_copy);
         if (stream) cudaStreamDestroy(stream);
         device = -1;
     }
@@ -163,6 +205,12 @@ struct trn_scene {
     std::vector<int> nccl_devs;
     std::vector<void*> nccl_comms;
     int (*nccl_destroy)(void*) = nullptr;
+};
+
+// one rank of a process-per-GPU job (trn_comm_init_rank)
+struct trn_comm {
+    void* comm = nullptr; // ncclComm_t
+    int nranks = 1, rank = 0, device = 0;
 };
 
 namespace trn {
@@ -290,6 +338,7 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream_b, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream_copy, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_shaded, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_shadow_done[0], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_shadow_done[1], cudaEventDisableTiming));
@@ -792,6 +841,7 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
     DeviceScene* ds = nullptr;
     rc = get_device_scene(scene, device, &ds);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> guard(ds->mu);
     CUDA_TRY(cudaSetDevice(ds->device));
     if (ds_out) *ds_out = ds;
     FrameParams fp = make_frame(cam, cfg);
@@ -802,15 +852,9 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
     rc = ensure_jitter(ds, cfg->width, cfg->pixel_samples);
     if (rc) return rc;
     cudaStream_t stream = use_user_stream ? user_stream : ds->stream;
-    struct EventPair {
-        cudaEvent_t a = nullptr, b = nullptr;
-        ~EventPair() {
-            if (a) cudaEventDestroy(a);
-            if (b) cudaEventDestroy(b);
-        }
-    } ev;
-    cudaEvent_t& e0 = ev.a;
-    cudaEvent_t& e1 = ev.b;
+    Events<2> ev;
+    cudaEvent_t& e0 = ev.e[0];
+    cudaEvent_t& e1 = ev.e[1];
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         CUDA_TRY(cudaEventCreate(&e0));
@@ -819,6 +863,10 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
     }
     Renderer r(ds, fp, cfg->integrator, d_accum, stream);
     rc = r.run();
+    if (rc) { // leave no shadow wave pending behind a failed frame
+        cudaStreamSynchronize(ds->stream_b);
+        ds->shadow_pending[0] = ds->shadow_pending[1] = false;
+    }
     if (stats) {
         cudaEventRecord(e1, stream);
         cudaEventSynchronize(e1);
@@ -858,9 +906,14 @@ static int ensure_accum(DeviceScene* ds, size_t pixels) {
 }
 
 // ------------------------------------------------------------------ NCCL (dlopen)
+struct NcclUniqueId {
+    char internal[128]; // ncclUniqueId (NCCL_UNIQUE_ID_BYTES)
+};
 struct NcclApi {
     void* lib = nullptr;
     int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
     int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -871,6 +924,8 @@ struct NcclApi {
 static int load_nccl(NcclApi& api) {
     // NCCL's version/debug banner goes to stdout by default; stdout is the image (main.cpp:242)
     setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+    // A libnccl.so.2 the process already holds (e.g. the one bundled with torch, when torch.distributed runs next to this
+    // library) is reused -- dlopen matches a resident object by its SONAME -- so that one process never runs two NCCLs.
     const char* names[] = {std::getenv("TRN_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
         if (!n || !*n) continue;
@@ -884,9 +939,21 @@ static int load_nccl(NcclApi& api) {
     api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(api.lib, "ncclGroupStart"));
     api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(api.lib, "ncclGroupEnd"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.lib, "ncclGetErrorString"));
-    if (!api.CommInitAll || !api.Reduce || !api.CommDestroy || !api.GroupStart || !api.GroupEnd)
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.lib, "ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.lib, "ncclCommInitRank"));
+    if (!api.CommInitAll || !api.Reduce || !api.CommDestroy || !api.GroupStart || !api.GroupEnd || !api.GetUniqueId || !api.CommInitRank) {
+        api.lib = nullptr;
         return fail(TRN_ERR_NCCL, "libnccl lacks a required symbol");
+    }
     return TRN_OK;
+}
+
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+static int ensure_nccl() {
+    std::lock_guard<std::mutex> lock(g_nccl_mu);
+    if (g_nccl.lib) return TRN_OK;
+    return load_nccl(g_nccl);
 }
 
 } // namespace trn
@@ -919,6 +986,7 @@ int32_t trn_scene_create_ex(const float* verts, const float* normals, const floa
     if (!verts || !normals || !diffuse || !out) return fail(TRN_ERR_INVALID, "null argument");
     if (n == 0) return fail(TRN_ERR_INVALID, "scene needs at least one triangle (lib/kdtree.cpp:475)");
     if (n >= TRN_MISS_ID) return fail(TRN_ERR_LIMIT, "triangle count must be < 2^30 (lib/kdtree.cpp:476)");
+    TRN_GUARD_BEGIN
     for (size_t i = 0; i < size_t(n) * 9; ++i)
         if (!std::isfinite(verts[i])) return fail(TRN_ERR_INVALID, "non-finite vertex coordinate");
     std::unique_ptr<trn_scene> sc(new trn_scene);
@@ -930,6 +998,7 @@ int32_t trn_scene_create_ex(const float* verts, const float* normals, const floa
     make_gpu_layout(*sc);
     *out = sc.release();
     return TRN_OK;
+    TRN_GUARD_END
 }
 
 void trn_scene_destroy(trn_scene* scene) {
@@ -980,6 +1049,7 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
     DeviceScene* ds = nullptr;
     int rc = get_device_scene(scene, device, &ds);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> guard(ds->mu);
     CUDA_TRY(cudaSetDevice(ds->device));
     const uint64_t chunk = 8ull << 20;
     const uint64_t cn = std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1));
@@ -1028,6 +1098,7 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
     DeviceScene* ds = nullptr;
     rc = get_device_scene(scene, device, &ds);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> guard(ds->mu);
     CUDA_TRY(cudaSetDevice(ds->device));
     trn_render_config c2 = *cfg;
     c2.sample_begin = 0;
@@ -1067,60 +1138,138 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
 int32_t trn_render_device(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
                           float* d_accum_rgba, void* cuda_stream, trn_stats* stats) {
     if (!scene || !d_accum_rgba) return fail(TRN_ERR_INVALID, "null argument");
+    TRN_GUARD_BEGIN
     return render_on_device(scene, device, cam, cfg, reinterpret_cast<float4*>(d_accum_rgba),
                             static_cast<cudaStream_t>(cuda_stream), true, stats, nullptr);
+    TRN_GUARD_END
 }
 
-int32_t trn_render(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
-                   float* out_rgba_sum, trn_stats* stats) {
-    if (!scene || !out_rgba_sum) return fail(TRN_ERR_INVALID, "null argument");
+// memset + render + (reduce) + D2H of one device's share, the common body of trn_render / trn_render_rank.
+// comm == nullptr: single device. Times the three parts with events on the device's stream.
+static int render_share(trn_scene* scene, int device, const trn_camera* cam, const trn_render_config* cfg, trn_comm* comm,
+                        float* out_rgba_sum, trn_stats* stats) {
     int rc = validate(cam, cfg);
     if (rc) return rc;
     DeviceScene* ds = nullptr;
     rc = get_device_scene(scene, device, &ds);
     if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> guard(ds->mu);
     CUDA_TRY(cudaSetDevice(ds->device));
     const size_t pixels = static_cast<size_t>(cfg->width) * cfg->height;
     rc = ensure_accum(ds, pixels);
     if (rc) return rc;
-    cudaEvent_t e0, e1;
-    CUDA_TRY(cudaEventCreate(&e0));
-    CUDA_TRY(cudaEventCreate(&e1));
-    CUDA_TRY(cudaEventRecord(e0, ds->stream));
+    Events<4> ev;
+    CUDA_TRY(ev.create());
+    CUDA_TRY(cudaEventRecord(ev.e[0], ds->stream));
     CUDA_TRY(cudaMemsetAsync(ds->d_accum, 0, pixels * sizeof(float4), ds->stream));
+    trn_render_config c = *cfg;
+    if (comm) { // sample split: rank g of G renders i = begin + stride * (g + G k)
+        const int base_stride = cfg->sample_stride > 0 ? cfg->sample_stride : 1;
+        c.sample_begin = cfg->sample_begin + comm->rank * base_stride;
+        c.sample_stride = base_stride * comm->nranks;
+    }
     trn_stats local;
-    rc = render_on_device(scene, ds->device, cam, cfg, ds->d_accum, ds->stream, true, &local, nullptr);
+    rc = render_on_device(scene, ds->device, cam, &c, ds->d_accum, ds->stream, true, &local, nullptr);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_rgba_sum, ds->d_accum, pixels * sizeof(float4), cudaMemcpyDeviceToHost, ds->stream));
-    CUDA_TRY(cudaEventRecord(e1, ds->stream));
-    CUDA_TRY(cudaEventSynchronize(e1));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    CUDA_TRY(cudaEventRecord(ev.e[1], ds->stream));
+    if (comm && comm->nranks > 1) {
+        // ONE ncclReduce(sum) of the W*H*4 float accumulation buffers onto rank 0 (in place on the root)
+        const int nrc = g_nccl.Reduce(ds->d_accum, ds->d_accum, pixels * 4, /*ncclFloat32*/ 7, /*ncclSum*/ 0, 0, comm->comm, ds->stream);
+        if (nrc != 0) return fail(TRN_ERR_NCCL, std::string("ncclReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
+    }
+    CUDA_TRY(cudaEventRecord(ev.e[2], ds->stream));
+    const bool root = !comm || comm->rank == 0;
+    if (root && out_rgba_sum)
+        CUDA_TRY(cudaMemcpyAsync(out_rgba_sum, ds->d_accum, pixels * sizeof(float4), cudaMemcpyDeviceToHost, ds->stream));
+    CUDA_TRY(cudaEventRecord(ev.e[3], ds->stream));
+    CUDA_TRY(cudaEventSynchronize(ev.e[3]));
+    float ms = 0, ms_r = 0, ms_c = 0;
+    cudaEventElapsedTime(&ms, ev.e[0], ev.e[3]);
+    cudaEventElapsedTime(&ms_r, ev.e[1], ev.e[2]);
+    cudaEventElapsedTime(&ms_c, ev.e[2], ev.e[3]);
     local.ms_render = ms;
+    local.ms_reduce = ms_r;
+    local.ms_d2h = ms_c;
     if (stats) *stats = local;
     return TRN_OK;
+}
+
+int32_t trn_render(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
+                   float* out_rgba_sum, trn_stats* stats) {
+    if (!scene || !out_rgba_sum) return fail(TRN_ERR_INVALID, "null argument");
+    TRN_GUARD_BEGIN
+    return render_share(scene, device, cam, cfg, nullptr, out_rgba_sum, stats);
+    TRN_GUARD_END
+}
+
+// ---- process-per-GPU communicator: one rank per process (torchrun / mpirun), NCCL over NVLink
+int32_t trn_comm_unique_id(uint8_t* id128) {
+    if (!id128) return fail(TRN_ERR_INVALID, "null argument");
+    TRN_GUARD_BEGIN
+    int rc = ensure_nccl();
+    if (rc) return rc;
+    NcclUniqueId id;
+    const int nrc = g_nccl.GetUniqueId(&id);
+    if (nrc != 0) return fail(TRN_ERR_NCCL, std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
+    std::memcpy(id128, id.internal, 128);
+    return TRN_OK;
+    TRN_GUARD_END
+}
+
+int32_t trn_comm_init_rank(const uint8_t* id128, int32_t nranks, int32_t rank, int32_t device, trn_comm** out) {
+    if (!id128 || !out || nranks < 1 || rank < 0 || rank >= nranks) return fail(TRN_ERR_INVALID, "bad communicator arguments");
+    TRN_GUARD_BEGIN
+    int rc = ensure_nccl();
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TRN_ERR_CUDA, "no CUDA device available (turner_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TRN_ERR_INVALID, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    NcclUniqueId id;
+    std::memcpy(id.internal, id128, 128);
+    std::unique_ptr<trn_comm> c(new trn_comm);
+    c->nranks = nranks;
+    c->rank = rank;
+    c->device = device;
+    const int nrc = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+    if (nrc != 0) return fail(TRN_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
+    *out = c.release();
+    return TRN_OK;
+    TRN_GUARD_END
+}
+
+void trn_comm_destroy(trn_comm* comm) {
+    if (!comm) return;
+    if (comm->comm && g_nccl.CommDestroy) {
+        cudaSetDevice(comm->device);
+        g_nccl.CommDestroy(comm->comm);
+    }
+    delete comm;
+}
+
+int32_t trn_render_rank(trn_scene* scene, trn_comm* comm, const trn_camera* cam, const trn_render_config* cfg,
+                        float* out_rgba_sum, trn_stats* stats) {
+    if (!scene || !comm) return fail(TRN_ERR_INVALID, "null argument");
+    TRN_GUARD_BEGIN
+    return render_share(scene, comm->device, cam, cfg, comm, out_rgba_sum, stats);
+    TRN_GUARD_END
 }
 
 int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_devices, const trn_camera* cam,
                          const trn_render_config* cfg, float* out_rgba_sum, trn_stats* stats) {
     if (!scene || !devices || num_devices < 1 || !out_rgba_sum) return fail(TRN_ERR_INVALID, "null argument");
     if (num_devices == 1) return trn_render(scene, devices[0], cam, cfg, out_rgba_sum, stats);
+    TRN_GUARD_BEGIN
     int rc = validate(cam, cfg);
     if (rc) return rc;
-    static NcclApi nccl;
-    static std::mutex nccl_mu;
-    {
-        std::lock_guard<std::mutex> lock(nccl_mu);
-        if (!nccl.lib) {
-            rc = load_nccl(nccl);
-            if (rc) return rc;
-        }
-    }
+    rc = ensure_nccl();
+    if (rc) return rc;
+    NcclApi& nccl = g_nccl;
     const size_t pixels = static_cast<size_t>(cfg->width) * cfg->height;
     std::vector<DeviceScene*> dss(num_devices, nullptr);
     for (int g = 0; g < num_devices; ++g) {
+        for (int h = 0; h < g; ++h)
+            if (devices[h] == devices[g]) return fail(TRN_ERR_INVALID, "trn_render_multi: a device is listed twice");
         rc = get_device_scene(scene, devices[g], &dss[g]);
         if (rc) return rc;
         CUDA_TRY(cudaSetDevice(dss[g]->device));
@@ -1152,18 +1301,24 @@ int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_d
     const int base_stride = cfg->sample_stride > 0 ? cfg->sample_stride : 1;
     for (int g = 0; g < num_devices; ++g) {
         workers.emplace_back([&, g]() {
-            cudaSetDevice(dss[g]->device);
-            trn_render_config c = *cfg;
-            c.sample_begin = base_begin + g * base_stride; // sample split: i = begin + stride*(g + G*k)
-            c.sample_stride = base_stride * num_devices;
-            cudaMemsetAsync(dss[g]->d_accum, 0, pixels * sizeof(float4), dss[g]->stream);
-            rcs[g] = render_on_device(scene, dss[g]->device, cam, &c, dss[g]->d_accum, dss[g]->stream, true, &st[g], nullptr);
-            if (rcs[g]) errs[g] = g_last_error;
+            try {
+                cudaSetDevice(dss[g]->device);
+                trn_render_config c = *cfg;
+                c.sample_begin = base_begin + g * base_stride; // sample split: i = begin + stride*(g + G*k)
+                c.sample_stride = base_stride * num_devices;
+                cudaMemsetAsync(dss[g]->d_accum, 0, pixels * sizeof(float4), dss[g]->stream);
+                rcs[g] = render_on_device(scene, dss[g]->device, cam, &c, dss[g]->d_accum, dss[g]->stream, true, &st[g], nullptr);
+                if (rcs[g]) errs[g] = g_last_error;
+            } catch (const std::exception& e) {
+                rcs[g] = TRN_ERR_LIMIT;
+                errs[g] = e.what();
+            }
         });
     }
     for (auto& w : workers) w.join();
     for (int g = 0; g < num_devices; ++g)
         if (rcs[g]) return fail(rcs[g], errs[g]);
+    auto t1 = std::chrono::steady_clock::now();
     // one ncclReduce(sum) of the float accumulation buffers onto devices[0]
     nccl.GroupStart();
     for (int g = 0; g < num_devices; ++g) {
@@ -1177,8 +1332,10 @@ int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_d
         cudaSetDevice(dss[g]->device);
         CUDA_TRY(cudaStreamSynchronize(dss[g]->stream));
     }
+    auto t2 = std::chrono::steady_clock::now();
     CUDA_TRY(cudaSetDevice(dss[0]->device));
     CUDA_TRY(cudaMemcpy(out_rgba_sum, dss[0]->d_accum, pixels * sizeof(float4), cudaMemcpyDeviceToHost));
+    auto t3 = std::chrono::steady_clock::now();
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         for (auto& s : st) {
@@ -1191,9 +1348,175 @@ int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_d
             stats->ms_shade = std::max(stats->ms_shade, s.ms_shade);
             stats->ms_other = std::max(stats->ms_other, s.ms_other);
         }
-        stats->ms_render = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        stats->ms_render = ms(t0, t3);
+        stats->ms_reduce = ms(t1, t2);
+        stats->ms_d2h = ms(t2, t3);
     }
     return TRN_OK;
+    TRN_GUARD_END
+}
+
+// ---- asynchronous frames: trn_render_async returns at once; the frame is rendered by a worker thread into one of two
+// accumulation buffers and copied to the host on a copy stream, so the D2H of frame k runs next to the render of k+1.
+struct trn_job {
+    std::thread worker;
+    int rc = 0;
+    std::string err;
+    trn_stats stats{};
+};
+
+int32_t trn_render_async(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
+                         float* out_rgba_sum, trn_job** job_out) {
+    if (!scene || !out_rgba_sum || !job_out) return fail(TRN_ERR_INVALID, "null argument");
+    TRN_GUARD_BEGIN
+    int rc = validate(cam, cfg);
+    if (rc) return rc;
+    DeviceScene* ds = nullptr;
+    rc = get_device_scene(scene, device, &ds);
+    if (rc) return rc;
+    std::unique_ptr<trn_job> job(new trn_job);
+    trn_job* j = job.get();
+    const trn_camera cam_c = *cam;
+    const trn_render_config cfg_c = *cfg;
+    j->worker = std::thread([scene, ds, cam_c, cfg_c, out_rgba_sum, j]() {
+        auto body = [&]() -> int {
+            const size_t pixels = static_cast<size_t>(cfg_c.width) * cfg_c.height;
+            cudaEvent_t done = nullptr;
+            float4* buf = nullptr;
+            {
+                std::lock_guard<std::recursive_mutex> guard(ds->mu); // renders serialise; the copy below does not hold it
+                CUDA_TRY(cudaSetDevice(ds->device));
+                const int slot = static_cast<int>(ds->async_use++ & 1u);
+                if (ds->async_pixels[slot] < pixels) {
+                    cudaFree(ds->d_async[slot]);
+                    ds->d_async[slot] = nullptr;
+                    ds->async_pixels[slot] = 0;
+                    CUDA_TRY(cudaMalloc(&ds->d_async[slot], pixels * sizeof(float4)));
+                    ds->async_pixels[slot] = pixels;
+                }
+                if (!ds->ev_async[slot]) CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_async[slot], cudaEventDisableTiming));
+                buf = ds->d_async[slot];
+                // the previous copy out of this buffer (two frames ago) must have left it
+                CUDA_TRY(cudaStreamWaitEvent(ds->stream, ds->ev_async[slot], 0));
+                CUDA_TRY(cudaMemsetAsync(buf, 0, pixels * sizeof(float4), ds->stream));
+                int rc2 = render_on_device(scene, ds->device, &cam_c, &cfg_c, buf, ds->stream, true, &j->stats, nullptr);
+                if (rc2) return rc2;
+                done = ds->ev_async[slot];
+                CUDA_TRY(cudaEventRecord(done, ds->stream));
+                CUDA_TRY(cudaStreamWaitEvent(ds->stream_copy, done, 0));
+                CUDA_TRY(cudaMemcpyAsync(out_rgba_sum, buf, pixels * sizeof(float4), cudaMemcpyDeviceToHost, ds->stream_copy));
+                CUDA_TRY(cudaEventRecord(done, ds->stream_copy)); // now marks "copy finished": guards the buffer's reuse
+            }
+            CUDA_TRY(cudaEventSynchronize(done));
+            return TRN_OK;
+        };
+        try {
+            j->rc = body();
+            if (j->rc) j->err = g_last_error;
+        } catch (const std::exception& e) {
+            j->rc = TRN_ERR_LIMIT;
+            j->err = e.what();
+        }
+    });
+    *job_out = job.release();
+    return TRN_OK;
+    TRN_GUARD_END
+}
+
+int32_t trn_wait(trn_job* job, trn_stats* stats) {
+    if (!job) return fail(TRN_ERR_INVALID, "null argument");
+    if (job->worker.joinable()) job->worker.join();
+    const int rc = job->rc;
+    if (rc) g_last_error = job->err;
+    else if (stats) *stats = job->stats;
+    delete job;
+    return rc;
+}
+
+// ---- occlusion parity hook: the any-hit predicate of pathtracer.cpp:49-53 for arbitrary rays, through the production
+// shadow kernels (a shadow wave whose "pixel" is the ray index and whose contribution is 1)
+int32_t trn_occluded(trn_scene* scene, int32_t device, const float* origins, const float* dirs, const float* tmax, uint64_t n,
+                     uint8_t* occluded) {
+    if (!scene || !origins || !dirs || !tmax || !occluded) return fail(TRN_ERR_INVALID, "null argument");
+    TRN_GUARD_BEGIN
+    DeviceScene* ds = nullptr;
+    int rc = get_device_scene(scene, device, &ds);
+    if (rc) return rc;
+    std::lock_guard<std::recursive_mutex> guard(ds->mu);
+    CUDA_TRY(cudaSetDevice(ds->device));
+    const uint64_t chunk = 4ull << 20;
+    const uint64_t cn = std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1));
+    DevBuf b_o, b_d, b_t, b_w, b_acc, b_out;
+    CUDA_TRY(b_o.alloc(cn * 12));
+    CUDA_TRY(b_d.alloc(cn * 12));
+    CUDA_TRY(b_t.alloc(cn * 4));
+    CUDA_TRY(b_w.alloc(cn * 3 * sizeof(float4)));
+    CUDA_TRY(b_acc.alloc(cn * sizeof(float4)));
+    CUDA_TRY(b_out.alloc(cn));
+    float4* w = b_w.as<float4>();
+    const ShadowWave sw{w, w + cn, w + 2 * cn};
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint32_t c = static_cast<uint32_t>(std::min<uint64_t>(chunk, n - off));
+        uint32_t cs;
+        rc = alloc_slot(ds, ds->stream, &cs);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(b_o.p, origins + 3 * off, size_t(c) * 12, cudaMemcpyHostToDevice, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(b_d.p, dirs + 3 * off, size_t(c) * 12, cudaMemcpyHostToDevice, ds->stream));
+        CUDA_TRY(cudaMemcpyAsync(b_t.p, tmax + off, size_t(c) * 4, cudaMemcpyHostToDevice, ds->stream));
+        CUDA_TRY(cudaMemsetAsync(b_acc.p, 0, size_t(c) * sizeof(float4), ds->stream));
+        pack_shadow_queries_kernel<<<blocks_for(c, 256), 256, 0, ds->stream>>>(b_o.as<float>(), b_d.as<float>(), b_t.as<float>(), c, sw,
+                                                                              ds->d_counters + cs);
+        launch_shadow(ds, persistent_mode(ds, true), ds->stream, sw, c, ds->d_counters + cs, b_acc.as<float4>());
+        unpack_occlusion_kernel<<<blocks_for(c, 256), 256, 0, ds->stream>>>(b_acc.as<float4>(), c, b_out.as<uint8_t>());
+        CUDA_TRY(cudaMemcpyAsync(occluded + off, b_out.p, c, cudaMemcpyDeviceToHost, ds->stream));
+        CUDA_TRY(cudaStreamSynchronize(ds->stream));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TRN_OK;
+    TRN_GUARD_END
+}
+
+// ---- measured gather peaks of this device (the denominators of bench.py's roofline): random 16-byte gathers, the access
+// shape of the traversal kernels, over a working set that lives in L1 / in L2 / in HBM.
+int32_t trn_measure_gather_peak(int32_t device, uint64_t set_bytes, int32_t mode, double* gbps) {
+    if (!gbps || set_bytes < 4096) return fail(TRN_ERR_INVALID, "bad argument");
+    TRN_GUARD_BEGIN
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TRN_ERR_CUDA, "no CUDA device available");
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= ndev) return fail(TRN_ERR_INVALID, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const uint64_t elems = set_bytes / 16;
+    DevBuf buf, sink;
+    CUDA_TRY(buf.alloc(elems * 16));
+    CUDA_TRY(sink.alloc(16));
+    CUDA_TRY(cudaMemset(buf.p, 1, elems * 16));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_peak_kernel, 256, 0));
+    const int grid = std::max(1, per_sm) * prop.multiProcessorCount;
+    const int iters = mode == 0 ? 4096 : 256; // loads per thread
+    Events<2> ev;
+    CUDA_TRY(ev.create());
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) { // first repetition warms the caches
+        CUDA_TRY(cudaEventRecord(ev.e[0], nullptr));
+        gather_peak_kernel<<<grid, 256>>>(buf.as<uint4>(), static_cast<uint32_t>(elems), iters, mode, sink.as<uint4>());
+        CUDA_TRY(cudaEventRecord(ev.e[1], nullptr));
+        CUDA_TRY(cudaEventSynchronize(ev.e[1]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev.e[0], ev.e[1]);
+        const double g = 16.0 * iters * 256.0 * grid / (ms * 1e6);
+        if (rep > 0) best = std::max(best, g);
+    }
+    CUDA_TRY(cudaGetLastError());
+    *gbps = best;
+    return TRN_OK;
+    TRN_GUARD_END
 }
 
 } // extern "C"
@@ -1218,6 +1541,8 @@ struct CacheReader {
     }
 };
 } // namespace
+
+using trn::fail;
 
 int32_t trn_scene_save_cache(const trn_scene* scene, const char* path) {
     if (!scene || !path) return trn::fail(TRN_ERR_INVALID, "null argument");
@@ -1255,14 +1580,27 @@ int32_t trn_scene_load_cache(const char* path, trn_scene** out) {
     if (!path || !out) return trn::fail(TRN_ERR_INVALID, "null argument");
     FILE* f = std::fopen(path, "rb");
     if (!f) return trn::fail(TRN_ERR_IO, std::string("cannot read ") + path);
+    TRN_GUARD_BEGIN
+    struct Closer {
+        FILE*& f;
+        ~Closer() {
+            if (f) std::fclose(f);
+        }
+    } closer{f};
     CacheReader r{f};
     uint8_t little = 0;
     r.raw(&little, 1);
     const uint64_t n = r.u64();
-    if (!r.ok || little != 1 || n == 0 || n >= TRN_MISS_ID) {
-        std::fclose(f);
-        return trn::fail(TRN_ERR_INVALID, std::string(path) + ": not a little-endian kdtree.cache");
+    // the header is untrusted: the triangle count must fit the file (1 flag + 8 count + 192 per triangle + 24 box + 8 node
+    // count) before anything is sized from it
+    uint64_t file_size = 0;
+    if (std::fseek(f, 0, SEEK_END) == 0) {
+        const long e = std::ftell(f);
+        if (e > 0) file_size = static_cast<uint64_t>(e);
     }
+    std::fseek(f, 9, SEEK_SET);
+    if (!r.ok || little != 1 || n == 0 || n >= TRN_MISS_ID || file_size < 41 || n > (file_size - 41) / 192)
+        return trn::fail(TRN_ERR_INVALID, std::string(path) + ": not a little-endian kdtree.cache (or truncated)");
     std::vector<float> verts(n * 9), normals(n * 9), diffuse(n * 4), reflective(n * 4), reflectivity(n);
     float rec[48];
     for (uint64_t i = 0; i < n && r.ok; ++i) {
@@ -1277,13 +1615,14 @@ int32_t trn_scene_load_cache(const char* path, trn_scene** out) {
     r.raw(box, sizeof box);
     const uint64_t num_nodes = r.u64();
     std::vector<uint64_t> nodes;
-    if (r.ok && num_nodes < (1ull << 32)) {
+    if (r.ok && num_nodes < (1ull << 32) && num_nodes <= (file_size - 41 - n * 192) / 8) {
         nodes.resize(num_nodes);
         r.raw(nodes.data(), num_nodes * 8);
     } else {
         r.ok = false;
     }
     std::fclose(f);
+    f = nullptr;
     if (!r.ok) return trn::fail(TRN_ERR_INVALID, std::string(path) + ": truncated kdtree.cache");
     trn_scene* sc = nullptr;
     const int32_t rc = trn_scene_create_ex(verts.data(), normals.data(), diffuse.data(), reflective.data(), reflectivity.data(),
@@ -1297,4 +1636,5 @@ int32_t trn_scene_load_cache(const char* path, trn_scene** out) {
     }
     *out = sc;
     return TRN_OK;
+    TRN_GUARD_END
 }

@@ -4,10 +4,14 @@
 #include "../../include/turner_b200.h"
 #include "host_util.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
+#include <thread>
+#include <vector>
 
 extern "C" {
 
@@ -32,14 +36,32 @@ int32_t trn_tonemap(const float* rgba_sum, uint64_t npix, int32_t pixel_samples,
                     float inverse_gamma, float* rgba_out) {
     if (!rgba_sum || !rgba_out || pixel_samples < 1) return trn::fail(TRN_ERR_INVALID, "bad argument");
     const float n = static_cast<float>(pixel_samples);
-    for (uint64_t i = 0; i < npix; ++i) {
-        float c[4];
-        for (int k = 0; k < 4; ++k) c[k] = rgba_sum[4 * i + k] / n;           // main.cpp:216
-        for (int k = 0; k < 3; ++k) c[k] = 1 - expf(-c[k] * exposure);        // effects.h:15-17
-        if (gamma_enabled)
-            for (int k = 0; k < 3; ++k) c[k] = powf(c[k], inverse_gamma);     // effects.h:36-38
-        std::memcpy(rgba_out + 4 * i, c, sizeof c);
+    // per pixel independent (the reference does it inside each row task, main.cpp:216-223): split over the host threads;
+    // same libm calls per pixel whatever the split, so the output does not depend on the thread count
+    auto span = [=](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            float c[4];
+            for (int k = 0; k < 4; ++k) c[k] = rgba_sum[4 * i + k] / n;           // main.cpp:216
+            for (int k = 0; k < 3; ++k) c[k] = 1 - expf(-c[k] * exposure);        // effects.h:15-17
+            if (gamma_enabled)
+                for (int k = 0; k < 3; ++k) c[k] = powf(c[k], inverse_gamma);     // effects.h:36-38
+            std::memcpy(rgba_out + 4 * i, c, sizeof c);
+        }
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("TRN_HOST_THREADS")) nt = static_cast<unsigned>(std::atoi(e));
+    nt = static_cast<unsigned>(std::min<uint64_t>(std::max(1u, std::min(nt, 64u)), std::max<uint64_t>(1, npix / 65536)));
+    if (nt <= 1) {
+        span(0, npix);
+        return TRN_OK;
     }
+    std::vector<std::thread> pool;
+    const uint64_t per = (npix + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+        const uint64_t lo = std::min<uint64_t>(npix, t * per), hi = std::min<uint64_t>(npix, lo + per);
+        if (lo < hi) pool.emplace_back(span, lo, hi);
+    }
+    for (auto& th : pool) th.join();
     return TRN_OK;
 }
 
@@ -63,8 +85,10 @@ uint64_t trn_write_p3(const float* rgba, int32_t width, int32_t height, char* bu
         lut[v][1] = v >= 10 ? static_cast<char>('0' + (v / 10) % 10) : ' ';
         lut[v][2] = static_cast<char>('0' + v % 10);
     }
+    // clamp(255*c*a, 0, 255) -> int (raster.h:91-96). NaN (powf of a negative colour, a degenerate vertex normal) compares
+    // false both ways: the reference then prints whatever int(NaN) is; here it becomes 0 -- the table index stays in range.
     auto q = [](float v) {
-        float c = v < 0.f ? 0.f : (255.f < v ? 255.f : v);
+        const float c = (v > 0.f) ? (v < 255.f ? v : 255.f) : 0.f;
         return static_cast<int>(c);
     };
     char tmp[12];

@@ -849,6 +849,40 @@ __global__ void __launch_bounds__(128) trace_shadow_raytrace_kernel(DevScene sc,
     accumulate(acc, __float_as_uint(b.w), c);
 }
 
+// trn_occluded: plain (o, d, tmax) arrays -> a shadow wave whose "pixel" is the ray index and whose contribution is 1
+__global__ void pack_shadow_queries_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ tmax,
+                                           uint32_t count, ShadowWave sw, WaveCounters* __restrict__ counters) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) counters->shadow_count = count;
+    if (idx >= count) return;
+    sw.a[idx] = make_float4(o[3 * idx], o[3 * idx + 1], o[3 * idx + 2], d[3 * idx]);
+    sw.b[idx] = make_float4(d[3 * idx + 1], d[3 * idx + 2], tmax[idx], __uint_as_float(idx));
+    sw.c[idx] = make_float4(1.f, 0.f, 0.f, 0.f);
+}
+__global__ void unpack_occlusion_kernel(const float4* __restrict__ acc, uint32_t count, uint8_t* __restrict__ occluded) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < count) occluded[idx] = acc[idx].x == 0.f ? 1 : 0; // the shadow kernel adds the contribution iff unoccluded
+}
+
+// Gather micro-benchmark (trn_measure_gather_peak): every lane issues independent 16-byte loads at pseudo-random
+// element indices of buf[0..elems) -- the access shape of the traversal kernels (node pairs, plane records, id vectors:
+// one 16-byte gather per lane, a different line per lane). What the set size decides is only where the lines live.
+__global__ void __launch_bounds__(256) gather_peak_kernel(const uint4* __restrict__ buf, uint32_t elems, int iters, int mode,
+                                                          uint4* __restrict__ sink) {
+    (void)mode;
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            s = s * 1664525u + 1013904223u;
+            const uint4 v = __ldg(buf + __umulhi(s, elems));
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+    }
+    if (acc.x == 0x12345678u) *sink = acc; // never true for the memset pattern: keeps the loads alive
+}
+
 __global__ void unpack_hits_kernel(const uint4* __restrict__ hits, uint32_t count, uint32_t* __restrict__ ids,
                                    float* __restrict__ rst) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
