@@ -107,6 +107,12 @@ typedef struct trn_stats {
      * device->host copy of the image; both are part of ms_render */
     double ms_reduce;
     double ms_d2h;
+    /* counting mode, pooled traversal kernel (trees with >= 1024 leaves): what the production schedule itself issues --
+     * [0] walk steps (one 16-byte node-pair load each), [1] chunks (one 16-byte id vector + four 16-byte plane records),
+     * [2] triangle pre-tests (valid ids of the chunks), [3] exact tests (32-byte hot record), [4] of those with the
+     * 32-byte cold record, [5] stack pushes, [6] pops (16 bytes of local memory each), [7] leaves */
+    uint64_t trace_pooled[8];
+    uint64_t shadow_pooled[8];
 } trn_stats;
 
 typedef struct trn_scene_info {

@@ -38,6 +38,7 @@
 
 namespace trn {
 
+constexpr int kVisitSlots = 28; // 12 of the per-ray twins (reference-shaped + device layout) + 2 x 8 PooledCounts
 thread_local std::string g_last_error;
 static std::atomic<int> g_profiling{0};
 static std::atomic<int> g_counting{0};
@@ -317,6 +318,7 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     ds->dev.tri_box = static_cast<const float4*>(ds->d_tri_box);
     ds->dev.shade = static_cast<const float4*>(ds->d_shade);
     ds->dev.mirror = static_cast<const float4*>(ds->d_mirror);
+    ds->dev.treelet_pairs = static_cast<uint32_t>(std::min<size_t>(sc->tree.pair_nodes.size(), KdTree::kTreeletNodes) / 2);
     for (int c = 0; c < 3; ++c) {
         ds->dev.lo[c] = sc->tree.box[c];
         ds->dev.hi[c] = sc->tree.box[3 + c];
@@ -347,7 +349,7 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     CUDA_TRY(cudaMalloc(&ds->d_counters, ds->counter_slots * sizeof(WaveCounters)));
     CUDA_TRY(cudaMallocHost(&ds->h_counters, ds->counter_slots * sizeof(WaveCounters)));
     CUDA_TRY(cudaMalloc(&ds->d_hitcount, sizeof(unsigned long long)));
-    CUDA_TRY(cudaMalloc(&ds->d_visits, 12 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&ds->d_visits, kVisitSlots * sizeof(unsigned long long)));
     {
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -440,11 +442,11 @@ static void launch_closest(DeviceScene* ds, int mode, cudaStream_t stream, const
         if (plain)
             trace_pooled_kernel<2><<<persistent_grid(ds->grid_pooled[2], n), 128, 0, stream>>>(
                 ds->dev, static_cast<const float4*>(ds->d_planes), nullptr, nullptr, nullptr, po, pd, n, nullptr, cursor, hits, nullptr,
-                refill, iters, pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 10)));
+                refill, iters, pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 10)), nullptr);
         else
             trace_pooled_kernel<0><<<persistent_grid(ds->grid_pooled[0], n), 128, 0, stream>>>(
                 ds->dev, static_cast<const float4*>(ds->d_planes), ra, rb, nullptr, nullptr, nullptr, n, nullptr, cursor, hits, nullptr,
-                refill, iters, pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 10)));
+                refill, iters, pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 10)), nullptr);
     } else if (mode == 2) {
         const int refill = static_cast<int>(env_u64("TRN_REFILL", 28)), quanta = static_cast<int>(env_u64("TRN_QUANTA", 2));
         if (plain)
@@ -467,7 +469,7 @@ static void launch_shadow(DeviceScene* ds, int mode, cudaStream_t stream, const 
         trace_pooled_kernel<1><<<persistent_grid(ds->grid_pooled[1], n_max), 128, 0, stream>>>(
             ds->dev, static_cast<const float4*>(ds->d_planes), sw.a, sw.b, sw.c, nullptr, nullptr, 0,
             &counters->shadow_count, &counters->shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_PQ_REFILL", 28)),
-            static_cast<int>(env_u64("TRN_PQ_WALK", 12)), pool_chunk_for(ds, n_max), static_cast<int>(env_u64("TRN_PQ_GATE", 10)));
+            static_cast<int>(env_u64("TRN_PQ_WALK", 12)), pool_chunk_for(ds, n_max), static_cast<int>(env_u64("TRN_PQ_GATE", 10)), nullptr);
     } else if (mode == 2) {
         TRN_LAUNCH_WW(1, ds->two_pass, persistent_grid(ds->grid_shadow, n_max), stream, ds->dev, sw.a, sw.b,
                       sw.c, nullptr, nullptr, 0, &counters->shadow_count, &counters->shadow_cursor, nullptr, acc,
@@ -694,9 +696,15 @@ struct Renderer {
                 launches += 4;
             }
             timer.begin(0);
-            if (counting)
+            if (counting) {
                 trace_closest_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, w.a, w.b, n, ds->d_hits, ds->d_visits);
-            else
+                if (mode_closest == 3) // and what the production schedule itself requests (same hits)
+                    trace_pooled_kernel<0, true><<<persistent_grid(ds->grid_pooled[0], n), 128, 0, stream>>>(
+                        ds->dev, static_cast<const float4*>(ds->d_planes), w.a, w.b, nullptr, nullptr, nullptr, n, nullptr,
+                        &ds->d_counters[cs].trace_cursor, ds->d_hits, nullptr, static_cast<int>(env_u64("TRN_PQ_REFILL", 28)),
+                        static_cast<int>(env_u64("TRN_PQ_WALK", 12)), pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 10)),
+                        ds->d_visits + 12);
+            } else
                 launch_closest(ds, mode_closest, stream, w.a, w.b, nullptr, nullptr, n, &ds->d_counters[cs].trace_cursor, ds->d_hits, order);
             timer.end();
             ++launches;
@@ -730,8 +738,14 @@ struct Renderer {
             if (fp.has_light) {
                 if (counting) {
                     timer.begin(1);
-                    trace_shadow_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, sw, ds->d_counters + cs, acc,
-                                                                                       ds->d_visits + 3);
+                    trace_shadow_count_kernel<<<blocks_for(n, 128), 128, 0, stream>>>(ds->dev, sw, ds->d_counters + cs,
+                                                                                       mode_shadow == 3 ? nullptr : acc, ds->d_visits + 3);
+                    if (mode_shadow == 3)
+                        trace_pooled_kernel<1, true><<<persistent_grid(ds->grid_pooled[1], n), 128, 0, stream>>>(
+                            ds->dev, static_cast<const float4*>(ds->d_planes), sw.a, sw.b, sw.c, nullptr, nullptr, 0,
+                            &ds->d_counters[cs].shadow_count, &ds->d_counters[cs].shadow_cursor, nullptr, acc,
+                            static_cast<int>(env_u64("TRN_PQ_REFILL", 28)), static_cast<int>(env_u64("TRN_PQ_WALK", 12)),
+                            pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 10)), ds->d_visits + 20);
                     timer.end();
                 } else if (overlap) {
                     CUDA_TRY(cudaEventRecord(ds->ev_shaded, stream));
@@ -798,7 +812,7 @@ struct Renderer {
     int run() {
         const uint64_t total = static_cast<uint64_t>(fp.width) * fp.height * static_cast<uint64_t>(fp.n_local);
         if (integrator != TRN_PATHTRACER) CUDA_TRY(cudaMemsetAsync(ds->d_hitcount, 0, sizeof(unsigned long long), stream));
-        if (counting) CUDA_TRY(cudaMemsetAsync(ds->d_visits, 0, 12 * sizeof(unsigned long long), stream));
+        if (counting) CUDA_TRY(cudaMemsetAsync(ds->d_visits, 0, kVisitSlots * sizeof(unsigned long long), stream));
         // primaries per batch: as many as fit one wave
         const uint64_t batch = cap;
         for (uint64_t first = 0; first < total; first += batch) {
@@ -881,8 +895,12 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
         stats->trace_queries = r.trace_queries;
         stats->shadow_launches = r.shadow_launches;
         if (r.counting) {
-            unsigned long long v[12];
+            unsigned long long v[kVisitSlots];
             cudaMemcpy(v, ds->d_visits, sizeof v, cudaMemcpyDeviceToHost);
+            for (int k = 0; k < 8; ++k) {
+                stats->trace_pooled[k] = v[12 + k];
+                stats->shadow_pooled[k] = v[20 + k];
+            }
             stats->trace_inner = v[0]; stats->trace_leaf_nodes = v[1]; stats->trace_tri_tests = v[2];
             stats->shadow_inner = v[3]; stats->shadow_leaf_nodes = v[4]; stats->shadow_tri_tests = v[5];
             stats->trace_actual_inner = v[6]; stats->trace_actual_leaf_nodes = v[7]; stats->trace_actual_tri_tests = v[8];
@@ -1062,7 +1080,7 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
     float *d_o = b_o.as<float>(), *d_d = b_d.as<float>(), *d_rst = b_rst.as<float>();
     uint4* d_h = b_h.as<uint4>();
     uint32_t* d_ids = b_ids.as<uint32_t>();
-    if (counts3) CUDA_TRY(cudaMemsetAsync(ds->d_visits, 0, 12 * sizeof(unsigned long long), ds->stream));
+    if (counts3) CUDA_TRY(cudaMemsetAsync(ds->d_visits, 0, kVisitSlots * sizeof(unsigned long long), ds->stream));
     for (uint64_t off = 0; off < n; off += chunk) {
         const uint32_t c = static_cast<uint32_t>(std::min<uint64_t>(chunk, n - off));
         CUDA_TRY(cudaMemcpyAsync(d_o, origins + 3 * off, size_t(c) * 12, cudaMemcpyHostToDevice, ds->stream));

@@ -39,6 +39,7 @@ struct DevScene {
     // reference-shaped tree and are uploaded only for the instrumented reference-schedule twin
     const uint2* pnodes;
     const uint32_t* prefs;
+    uint32_t treelet_pairs; // node pairs of the breadth-first top of pnodes (<= KdTree::kTreeletNodes / 2)
 };
 
 // ray wave, SoA of float4 (fully coalesced 16-byte lanes)
@@ -703,7 +704,7 @@ __global__ void __launch_bounds__(128) trace_shadow_count_kernel(DevScene sc, Sh
         HitRec h;
         traverse<true, true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, b.z, h, &vc);
         const bool occluded = traverse_pairs<true, true>(sc, a.x, a.y, a.z, a.w, b.x, b.y, b.z, h, &vp);
-        if (!occluded) accumulate(acc, __float_as_uint(b.w), sw.c[idx]);
+        if (!occluded && acc) accumulate(acc, __float_as_uint(b.w), sw.c[idx]); // acc == nullptr: the pooled twin adds it
     }
     flush_counts(vc, g);
     flush_counts(vp, g + 6);

@@ -8,13 +8,15 @@
 // test (6 % of the tests) are evaluated by 2-3 lanes while the rest wait. Here every warp runs a three-phase cycle:
 //
 //   WALK   up to walk_iters warp-wide iterations; in each, a lane at an inner node takes ONE step of its own ray. The
-//          lanes that have reached a leaf queue a 16-byte leaf descriptor in shared memory and pop their stack -- in a
-//          block that is only issued once leaf_gate lanes wait (or nobody can step). The walk is speculative: it does not
-//          wait for the leaf's outcome (98.6 % of the leaf visits of the benchmark's secondary rays do not end the ray).
-//   TEST   the queued leaves of ALL rays, 32 at a time (one descriptor per lane), are cut into chunks of 4 triangle
-//          references; the chunks are dealt out 32 per round, one per lane, by a shuffle binary search over the running
-//          chunk totals. The lane reads the owner ray from a table in shared memory, the chunk's ids with one 16-byte
-//          load (leaf runs are 16-byte aligned), four 16-byte plane records, and runs a division-free, conservative plane
+//          lanes that have reached a leaf cut it into chunks of 4 triangle references, queue one 16-byte descriptor per
+//          chunk in shared memory (slots by ballot/popc, or a shuffle scan when a leaf has more than one chunk; the queue
+//          fill is a warp-uniform register, no atomics) and pop their stack -- in a block that is only issued once
+//          leaf_gate lanes wait (or nobody can step). A leaf that does not fit the queue keeps its remaining references
+//          in the node register and is continued in the next cycle. The walk is speculative: it does not wait for the
+//          leaf's outcome (98.6 % of the leaf visits of the benchmark's secondary rays do not end the ray).
+//   TEST   the queued chunks of ALL rays, 32 per round, one per lane -- no search: lane l of round k takes descriptor
+//          32 k + l. The lane reads the owner ray from a table in shared memory, the chunk's ids with one 16-byte load
+//          (leaf runs are 16-byte aligned), four 16-byte plane records, and runs a division-free, conservative plane
 //          pre-filter (FMA arithmetic with explicit error bounds). Survivors are appended to the warp's survivor queue
 //          with four ballots -- no atomics.
 //   EXACT  whenever 32 survivors are waiting (and at the end of the cycle) they get, 32 at a time, the reference's exact
@@ -32,7 +34,7 @@
 namespace trn {
 
 #ifndef TRN_PQ_LEAVES
-#define TRN_PQ_LEAVES 64 // leaf descriptors per warp queue
+#define TRN_PQ_LEAVES 64 // chunk descriptors per warp queue
 #endif
 #ifndef TRN_PQ_MINBLOCKS
 #define TRN_PQ_MINBLOCKS 8
@@ -44,13 +46,21 @@ constexpr int kPqSurv = 32 + 32 * kPqChunkTris; // survivors: < 32 left over + o
 struct PooledWarpSmem {
     float4 ray_o[32];        // o.xyz, E   (E, F: error bounds of the pre-filter)
     float4 ray_d[32];        // d.xyz, F
-    uint4 leaf[kPqLeaves];   // first ref, count | owner << 24, lo bits, hi bits (parameter range of the cell)
+    uint4 leaf[kPqLeaves];   // one per chunk: first ref, count (1..4) | owner << 8, lo bits, hi bits (parameter range of the cell)
     uint2 surv[kPqSurv];     // triangle id, owner | seq << 5
     uint4 best[32];          // per lane: best hit so far (id, r, s, t) -- cold state kept out of the registers
     uint32_t ray_idx[32];    // per lane: index of its ray in the wave
     float walk_o[3][32];     // per lane: origin and reciprocal direction by axis -- the WALK step reads the split axis'
     float walk_i[3][32];     // component with one conflict-free LDS instead of holding six registers + selects
-    uint32_t nleaf, pad[3];
+};
+
+#ifndef TRN_PQ_TREELET
+#define TRN_PQ_TREELET 0 // node pairs of the top treelet staged in shared memory per CTA (0 = off; A/B in profiles/README.md)
+#endif
+
+// visit counts of the instrumented instantiation (COUNT): what the production schedule really requests from memory
+struct PooledCounts {
+    unsigned steps, chunks, tris, exact, cold, push, pop, leaves;
 };
 
 // exact-zero direction component: the reference's schedule verbatim (see traverse_pairs<>)
@@ -63,24 +73,32 @@ __device__ __noinline__ bool trace_axis_parallel(const DevScene& sc, float ox, f
 // MODE 0: closest hit, rays from a RayWave (a,b); result -> hits[idx]
 // MODE 1: any-hit shadow rays from a ShadowWave (a,b,c); unoccluded -> acc[pixel] += c
 // MODE 2: closest hit, rays from plain (o,d) float arrays; result -> hits[idx]
-template <int MODE>
+// COUNT: also tally what the schedule requests (walk steps, chunks, triangle pre-tests, exact tests, cold-record reads,
+//        stack pushes / pops, leaves) into visits[0..8) -- the roofline leg of bench.py and the counter parity test only
+template <int MODE, bool COUNT = false>
 __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
     DevScene sc, const float4* __restrict__ planes, const float4* __restrict__ ra, const float4* __restrict__ rb,
     const float4* __restrict__ rc, const float* __restrict__ po, const float* __restrict__ pd, uint32_t count_arg,
     const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor, uint4* __restrict__ hits, float4* __restrict__ acc,
-    int refill_below, int walk_iters, uint32_t pool_chunk, int leaf_gate) {
+    int refill_below, int walk_iters, uint32_t pool_chunk, int leaf_gate, unsigned long long* __restrict__ visits) {
     constexpr bool ANY = MODE == 1;
     constexpr unsigned kFull = 0xffffffffu;
     __shared__ PooledWarpSmem smem[4];
     PooledWarpSmem& sm = smem[threadIdx.x >> 5];
+#if TRN_PQ_TREELET > 0
+    // top treelet staged in shared memory: the first TRN_PQ_TREELET pairs of the breadth-first-on-top layout
+    __shared__ uint4 s_pairs[TRN_PQ_TREELET];
+    for (uint32_t k = threadIdx.x; k < TRN_PQ_TREELET; k += blockDim.x)
+        s_pairs[k] = k < sc.treelet_pairs ? __ldg(reinterpret_cast<const uint4*>(sc.pnodes) + k) : make_uint4(0u, 3u, 0u, 3u);
+    __syncthreads();
+#endif
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t count = count_ptr ? *count_ptr : count_arg;
-    if (lane == 0) sm.nleaf = 0;
-    __syncwarp();
     float scale = 0.f; // largest |coordinate| of the scene box
 #pragma unroll
     for (int c = 0; c < 3; ++c) scale = fmaxf(scale, fmaxf(fabsf(sc.lo[c]), fabsf(sc.hi[c])));
+    PooledCounts pc{0, 0, 0, 0, 0, 0, 0, 0};
 
     uint4 stack[kStackDepth];
     int sp = 0;
@@ -187,62 +205,94 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
         __syncwarp();
 
         // ------------------------------------------------------------------ WALK
-        // Every iteration the lanes at inner nodes take one step. The lanes that have reached a leaf queue it and pop --
-        // but that block is only issued when at least leaf_gate lanes wait at a leaf (or no lane can step): it is as
-        // long as the step itself and would otherwise run for 4 of 32 lanes in nearly every iteration.
-        bool blocked = false;
+        // Every iteration the lanes at inner nodes take one step. The lanes that have reached a leaf queue its chunks and
+        // pop -- but that block is only issued when at least leaf_gate lanes wait at a leaf (or no lane can step): it is
+        // as long as the step itself and would otherwise run for 4 of 32 lanes in nearly every iteration.
+        uint32_t nleaf = 0; // chunk descriptors queued in this cycle (warp-uniform)
+        bool active = busy && walking; // cleared when the lane's leaf does not fit the queue (continued in the next cycle)
         int it = 0;
 #pragma unroll 1
         for (;;) {
-            const bool can = busy && walking && !blocked;
-            const bool at_leaf = can && (n.y & 3u) == 3u;
+            const bool at_leaf = active && (n.y & 3u) == 3u;
             const unsigned lm = __ballot_sync(kFull, at_leaf);
-            const unsigned im = __ballot_sync(kFull, can && !at_leaf);
+            const unsigned im = __ballot_sync(kFull, active && !at_leaf);
             const bool last = it >= walk_iters || im == 0u;
             if (lm != 0u && (last || __popc(lm) >= leaf_gate)) {
-                // leaf: queue it (one descriptor: reference range, owner, parameter range of the cell plus slack) and pop
-                // at once. One atomic reserves the slots of all lanes. A count-0 leaf (cut-off void) can only be the
-                // root of an empty tree.
-                const uint32_t cnt = n.y >> 2;
-                const unsigned want = __ballot_sync(kFull, at_leaf && cnt > 0u);
-                uint32_t slot0 = 0;
-                if (want != 0u && lane == static_cast<unsigned>(__ffs(want) - 1)) slot0 = atomicAdd(&sm.nleaf, static_cast<uint32_t>(__popc(want)));
-                slot0 = __shfl_sync(kFull, slot0, want ? __ffs(want) - 1 : 0);
-                if (at_leaf) {
-                    if (cnt > 0u) {
-                        const uint32_t slot = slot0 + __popc(want & lt_mask);
-                        if (slot < static_cast<uint32_t>(kPqLeaves)) {
-                            float lo = tenter - kCellSlack * (fabsf(tenter) + 1.f);
-                            float hi = texit + kCellSlack * (fabsf(texit) + 1.f);
-                            lo = fmaxf(lo, 0.f);
-                            hi = ANY ? fminf(hi, tmax_any) : fminf(hi, best_r);
-                            sm.leaf[slot] = make_uint4(n.x, cnt | (lane << 24), __float_as_uint(lo), __float_as_uint(hi));
-                        } else {
-                            blocked = true; // queue full: retry in the next cycle
-                        }
+                // leaf: one descriptor per chunk of 4 references (reference range, owner, parameter range of the cell plus
+                // slack), then pop. A count-0 leaf (cut-off void) can only be the root of an empty tree.
+                const uint32_t cnt = at_leaf ? n.y >> 2 : 0u;
+                const uint32_t nch = (cnt + kPqChunkTris - 1) / kPqChunkTris;
+                uint32_t slot, total;
+                if (__ballot_sync(kFull, nch > 1u) == 0u) { // the common case: every waiting leaf is one chunk
+                    const unsigned want = __ballot_sync(kFull, nch != 0u);
+                    slot = nleaf + __popc(want & lt_mask);
+                    total = __popc(want);
+                } else {
+                    uint32_t incl = nch;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const uint32_t v = __shfl_up_sync(kFull, incl, off);
+                        if (static_cast<int>(lane) >= off) incl += v;
                     }
-                    if (!blocked) {
+                    slot = nleaf + incl - nch;
+                    total = __shfl_sync(kFull, incl, 31);
+                }
+                if (at_leaf) {
+                    uint32_t fit = nch;
+                    if (nch != 0u) {
+                        const uint32_t room = slot < static_cast<uint32_t>(kPqLeaves) ? static_cast<uint32_t>(kPqLeaves) - slot : 0u;
+                        fit = min(nch, room);
+                        float lo = tenter - kCellSlack * (fabsf(tenter) + 1.f);
+                        float hi = texit + kCellSlack * (fabsf(texit) + 1.f);
+                        lo = fmaxf(lo, 0.f);
+                        hi = ANY ? fminf(hi, tmax_any) : fminf(hi, best_r);
+                        for (uint32_t c = 0; c < fit; ++c) {
+                            const uint32_t off0 = c * kPqChunkTris;
+                            sm.leaf[slot + c] = make_uint4(n.x + off0, min(static_cast<uint32_t>(kPqChunkTris), cnt - off0) | (lane << 8),
+                                                           __float_as_uint(lo), __float_as_uint(hi));
+                        }
+                        if (COUNT) pc.leaves += 1;
+                    }
+                    if (fit < nch) {
+                        // queue full: the rest of the leaf stays in the node register (leaf runs are contiguous) and is
+                        // queued in the next cycle
+                        n.x += fit * kPqChunkTris;
+                        n.y -= (fit * kPqChunkTris) << 2;
+                        active = false;
+                    } else {
                         last_texit = texit;
                         if (sp == 0) {
                             walking = false;
+                            active = false;
                         } else {
                             const uint4 e = stack[--sp];
+                            if (COUNT) pc.pop += 1;
                             n = make_uint2(e.x, e.y);
                             tenter = __uint_as_float(e.z);
                             texit = __uint_as_float(e.w);
                             // front to back: nothing at or behind a cell that starts beyond the light / the best hit matters
-                            if (ANY ? tenter > tmax_any : tenter > best_r) walking = false;
+                            if (ANY ? tenter > tmax_any : tenter > best_r) {
+                                walking = false;
+                                active = false;
+                            }
                         }
                     }
                 }
+                nleaf = min(nleaf + total, static_cast<uint32_t>(kPqLeaves));
             }
             if (last) break;
             ++it;
-            if (can && !at_leaf) {
+            if (active && !at_leaf) {
                 // one inner-node step, lib/kdtree.cpp:540-563 on the sibling-pair layout (see traverse_pairs<>)
                 const uint32_t ax = n.y & 3u;
                 const float split = __uint_as_float(n.x);
+#if TRN_PQ_TREELET > 0
+                const uint32_t pi = n.y >> 3; // pair index
+                const uint4 pair = pi < TRN_PQ_TREELET ? s_pairs[pi] : __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
+#else
                 const uint4 pair = __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
+#endif
+                if (COUNT) pc.steps += 1;
                 const float o_ax = sm.walk_o[ax][lane], i_ax = sm.walk_i[ax][lane];
                 const float t = (split - o_ax) * i_ax;
                 const bool flip = (__float_as_uint(i_ax) >> 31) != 0u;
@@ -252,7 +302,10 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                 const bool far_only = !near_only && (t < tenter);
                 const bool both = !near_only && !far_only;
                 const bool go_far = far_only || (both && near.y == 3u);
-                if (both && near.y != 3u && far.y != 3u) stack[sp++] = make_uint4(far.x, far.y, __float_as_uint(t), __float_as_uint(texit));
+                if (both && near.y != 3u && far.y != 3u) {
+                    stack[sp++] = make_uint4(far.x, far.y, __float_as_uint(t), __float_as_uint(texit));
+                    if (COUNT) pc.push += 1;
+                }
                 n = go_far ? far : near;
                 tenter = (both && go_far) ? t : tenter;
                 texit = (both && !go_far) ? t : texit;
@@ -261,19 +314,12 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
         __syncwarp();
 
         // ------------------------------------------------------------------ TEST (pre-filter) and EXACT rounds
-        // The queued leaves are taken 32 at a time, one per lane; their triangle references are cut into chunks of 4
-        // and the chunks of the whole batch are dealt out 32 per round (a lane finds its chunk's leaf by a shuffle
-        // binary search over the running chunk totals), so that every lane tests 4 triangles per round whatever the
-        // leaf sizes are. Survivors go to the warp's survivor queue; whenever 32 are waiting (and at the end) they
-        // get the exact test, 32 at a time.
-        const uint32_t nleaf = min(*reinterpret_cast<volatile uint32_t*>(&sm.nleaf), static_cast<uint32_t>(kPqLeaves));
-        uint32_t ns = 0;        // survivors waiting (warp-uniform; only this loop appends)
-        uint32_t lb = 0;        // first leaf of the current batch
-        uint32_t base = 0, total = 0, P = 0; // chunk cursor / chunk count of the batch / inclusive chunk totals per lane
-        uint4 ld = make_uint4(0u, 0u, 0u, 0u);
-        bool have_batch = false;
+        // The queued chunks are taken 32 per round, one per lane. Survivors go to the warp's survivor queue; whenever 32
+        // are waiting (and at the end) they get the exact test, 32 at a time.
+        uint32_t ns = 0;   // survivors waiting (warp-uniform; only this loop appends)
+        uint32_t base = 0; // first descriptor of the next TEST round
         for (;;) {
-            const bool more_tests = have_batch ? (base < total || lb + 32u < nleaf) : (lb < nleaf);
+            const bool more_tests = base < nleaf;
             if (ns >= 32u || (!more_tests && ns > 0u)) {
                 // EXACT: the reference's operation sequence for up to 32 pooled survivors (taken from the tail)
                 const uint32_t take = min(32u, ns), sbase = ns - take;
@@ -292,6 +338,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                     const float4* rec = sc.isect_hot + 2 * static_cast<size_t>(id);
                     const float4* rec2 = sc.isect_cold + 2 * static_cast<size_t>(id);
                     const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
+                    if (COUNT) pc.exact += 1;
                     const float nx = q0.w, ny = q1.x, nz = q1.y;
                     const float denom = nx * rd.x + ny * rd.y + nz * rd.z; // intersect_ray_plane, lib/intersection.h:40-49
                     const float nom = nx * (q0.x - ro.x) + ny * (q0.y - ro.y) + nz * (q0.z - ro.z);
@@ -300,6 +347,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                     // below), resp. within the light distance, matters
                     if (denom != 0.f && r >= 0.f && r <= lim) {
                         const float4 q2 = __ldg(rec2), q3 = __ldg(rec2 + 1);
+                        if (COUNT) pc.cold += 1;
                         const float wx = (ro.x + r * rd.x) - q0.x, wy = (ro.y + r * rd.y) - q0.y, wz = (ro.z + r * rd.z) - q0.z; // :70-71
                         const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
                         const float wv = wx * vx + wy * vy + wz * vz;
@@ -336,51 +384,30 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                 ns = sbase;
                 __syncwarp();
             } else if (more_tests) {
-                if (!have_batch || base >= total) {
-                    // next batch of up to 32 leaves: one descriptor per lane, inclusive scan of their chunk counts
-                    if (have_batch) lb += 32u;
-                    have_batch = true;
-                    ld = lb + lane < nleaf ? sm.leaf[lb + lane] : make_uint4(0u, 0u, 0u, 0u);
-                    P = ((ld.y & 0xffffffu) + kPqChunkTris - 1) / kPqChunkTris;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const uint32_t v = __shfl_up_sync(kFull, P, off);
-                        if (static_cast<int>(lane) >= off) P += v;
-                    }
-                    total = __shfl_sync(kFull, P, 31);
-                    base = 0;
-                    continue;
-                }
                 // TEST: one chunk per lane. Pre-filter: with a ~ n.d and b ~ n.(v0 - o) (FMA arithmetic, |a - denom| <= F,
                 // |b - nom| <= E for the reference's denom, nom), A = |a|, B = b * sign(a):
                 //   0 <= lo <= nom/denom <= hi   ==>   A <= F  or  (B + E >= lo (A - F)  and  B - E <= hi (A + F)).
                 // Triangles that fail cannot have their exact plane distance inside [lo, hi].
                 const uint32_t g = base + lane;
-                // leaf of chunk g = number of lanes whose inclusive total is <= g
-                uint32_t j = 0;
-#pragma unroll
-                for (int step = 16; step > 0; step >>= 1) {
-                    const uint32_t pj = __shfl_sync(kFull, P, (j + step - 1) & 31u);
-                    if (pj <= g) j += step;
-                }
-                j &= 31u; // g >= total (idle lane): any leaf, masked below
-                const uint32_t first = __shfl_sync(kFull, ld.x, j), cw = __shfl_sync(kFull, ld.y, j);
-                const float lo = __uint_as_float(__shfl_sync(kFull, ld.z, j)), hi = __uint_as_float(__shfl_sync(kFull, ld.w, j));
-                const uint32_t pend = __shfl_sync(kFull, P, j);
-                const uint32_t lcnt = cw & 0xffffffu, owner = cw >> 24;
-                const uint32_t sub = g - (pend - (lcnt + kPqChunkTris - 1) / kPqChunkTris); // chunk index inside the leaf
-                const uint32_t off0 = sub * kPqChunkTris;
-                const uint32_t cnt = g < total ? min(static_cast<uint32_t>(kPqChunkTris), lcnt - off0) : 0u;
                 uint4 ids = make_uint4(0u, 0u, 0u, 0u); // the chunk's triangle ids
                 uint32_t km = 0;                         // bit k: triangle k survives the pre-filter
-                if (cnt > 0u) {
+                uint32_t owner = 0;
+                if (g < nleaf) {
+                    const uint4 ld = sm.leaf[g];
+                    const uint32_t cnt = ld.y & 0xffu;
+                    owner = ld.y >> 8;
+                    const float lo = __uint_as_float(ld.z), hi = __uint_as_float(ld.w);
                     const float4 ro = sm.ray_o[owner], rd = sm.ray_d[owner];
                     const float E = ro.w, F = rd.w;
                     const float c1 = fmaf(-lo, F, -E), c2 = fmaf(hi, F, E);
                     // leaf runs start at multiples of 4 references and the array is padded (kdtree_build.cpp): one 16-byte
                     // load brings the chunk's ids; ids beyond cnt are valid triangles whose result is masked
-                    ids = __ldg(reinterpret_cast<const uint4*>(sc.prefs + first + off0));
+                    ids = __ldg(reinterpret_cast<const uint4*>(sc.prefs + ld.x));
                     const float4 p0 = __ldg(&planes[ids.x]), p1 = __ldg(&planes[ids.y]), p2 = __ldg(&planes[ids.z]), p3 = __ldg(&planes[ids.w]);
+                    if (COUNT) {
+                        pc.chunks += 1;
+                        pc.tris += cnt;
+                    }
 #pragma unroll
                     for (int k = 0; k < kPqChunkTris; ++k) {
                         const float4 p = k == 0 ? p0 : (k == 1 ? p1 : (k == 2 ? p2 : p3));
@@ -394,8 +421,9 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                     }
                 }
                 // append the survivors of the round, k-major (the order inside the queue is irrelevant: seq carries the
-                // visiting order): four ballots, no scan, no atomics
-                const uint32_t seq0 = ((lb + j) << 20) + off0 + 1u;
+                // visiting order -- a ray's descriptors are queued in the order its walk visits them, so the slot index
+                // orders them): four ballots, no scan, no atomics
+                const uint32_t seq0 = (g << 2) + 1u;
                 uint32_t round_total = 0;
 #pragma unroll
                 for (int k = 0; k < kPqChunkTris; ++k) {
@@ -413,14 +441,14 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                 break;
             }
         }
-        if (lane == 0) sm.nleaf = 0;
 
         // ------------------------------------------------------------------ finished rays
         if (busy) {
             best_seq = 0;
             bool finished;
             if (ANY) finished = occluded || !walking;
-            else finished = !walking || (best_r < kFltMax && (best_r <= last_texit || best_r < tenter));
+            // (a lane whose leaf is only partly queued -- walking but not active -- waits for the rest of the leaf)
+            else finished = !walking || (active && best_r < kFltMax && (best_r <= last_texit || best_r < tenter));
             if (finished) {
                 busy = false;
                 const uint32_t idx = sm.ray_idx[lane];
@@ -432,6 +460,15 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
             }
         }
         __syncwarp();
+    }
+    if (COUNT) {
+        unsigned v[8] = {pc.steps, pc.chunks, pc.tris, pc.exact, pc.cold, pc.push, pc.pop, pc.leaves};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            unsigned x = v[k];
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(kFull, x, off);
+            if (lane == 0 && x) atomicAdd(visits + k, static_cast<unsigned long long>(x));
+        }
     }
 }
 
