@@ -176,7 +176,7 @@ int32_t trn_render_multi(trn_scene* scene, const int32_t* devices, int32_t num_d
 /* ---- process-per-GPU jobs (one rank per process: torchrun, mpirun ...). The image reduce is this library's own
  * ncclReduce; the launcher only has to carry the 128-byte id from rank 0 to the other ranks.
  *   trn_comm_unique_id  rank 0: ncclGetUniqueId
- *   trn_comm_init_rank  every rank: ncclCommInitRank on `device`
+ *   trn_comm_init_rank  every rank: ncclCommInitRank on `device` (nranks == 1: no NCCL involved, id128 is ignored)
  *   trn_render_rank     every rank: renders its share of the pixel samples (i = sample_begin + sample_stride * (rank +
  *                       nranks * k), scene replicated), then ONE ncclReduce(sum) onto rank 0; rank 0 copies the summed
  *                       image to out_rgba_sum (host, width*height*4 floats; NULL = leave it on the device, ignored on the

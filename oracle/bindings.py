@@ -225,7 +225,8 @@ class RefConfig(C.Structure):
                 ("pixel_samples", C.c_int32), ("num_threads", C.c_int32), ("gamma_enabled", C.c_int32),
                 ("bg", C.c_float * 4), ("exposure", C.c_float), ("inverse_gamma", C.c_float),
                 ("max_visibility", C.c_float), ("num_lights", C.c_int32), ("light_pos", C.c_float * 3),
-                ("light_color", C.c_float * 4), ("shadow_intensity", C.c_float)]
+                ("light_color", C.c_float * 4), ("shadow_intensity", C.c_float),
+                ("row_begin", C.c_int32), ("row_stride", C.c_int32)]
 
 
 class RefStats(C.Structure):

@@ -120,6 +120,10 @@ struct RefConfig {
     float light_pos[3];
     float light_color[4];
     float shadow_intensity; // raytracer only (config.h:113)
+    // timing sampler of bench.py's reference arm: render only rows y = row_begin + k * row_stride (whole rows, every
+    // pixel sample of them -- a row is the reference's unit of work, main.cpp:194). 0 / 0 or 0 / 1 = the whole image.
+    int32_t row_begin;
+    int32_t row_stride;
 };
 
 struct RefStats {
@@ -318,10 +322,11 @@ int ref_render(void* h, const RefCamera* rc, const RefConfig* cfg, float* out_li
         // Row-per-task FIFO over num_threads fresh worker threads (what
         // ThreadPool(conf.num_threads) + enqueue-per-row amounts to). Fresh
         // threads matter: sampling.h:12's thread-local stream restarts at seed 4.
-        std::atomic<int> next_row{0};
+        const int row_stride = cfg->row_stride > 0 ? cfg->row_stride : 1;
+        std::atomic<int> next_row{cfg->row_begin > 0 ? cfg->row_begin : 0};
         auto worker = [&]() {
             for (;;) {
-                int y = next_row.fetch_add(1);
+                int y = next_row.fetch_add(row_stride);
                 if (y >= height) break;
                 KDTreeIntersection tree_intersection(tree);
                 float dx, dy;

@@ -390,7 +390,9 @@ def test_adversarial_axis_aligned_tiles(api, ob, scenes):
         assert not ((i_g == api.MISS_ID) ^ (i_o == ob.MISS)).any(), "hit/miss decision differs"
         ties = int(bad.sum())
         print("tiled_box n=%d: %d exact-tie id differences in %d adversarial rays" % (n, ties, 2 * k))
-        assert ties < 0.06 * 2 * k
+        # the spec allows exact ties "excepted and counted"; README/DESIGN claim 0 since the cut planes were moved into
+        # their voids and axis-parallel rays take the reference's schedule verbatim -- assert the number claimed
+        assert ties == 0
 
 
 def test_ragged_image_shapes_and_degenerate_splits(api, ob, scenes):
@@ -577,3 +579,162 @@ def test_shadow_waves_on_the_second_stream_change_nothing(api, scenes, monkeypat
         assert (d <= 2e-4 * (1 + np.abs(base[0]))).all(), (k, float(d.max()))
     monkeypatch.delenv("TRN_WAVE_CAP")
     monkeypatch.delenv("TRN_SHADOW_OVERLAP")
+
+
+
+# ---------------------------------------------------------------------------------------------- round 2 additions
+def _secondary_shaped_rays(sc, n, seed):
+    """rays leaving the surface like the children shade_bounce_kernel emits (origin on a triangle + 1e-4 normal, direction
+    in the hemisphere), plus grazing rays tangent to the body"""
+    rng = np.random.RandomState(seed)
+    V = sc["vertices"].reshape(-1, 3, 3)
+    idx = rng.randint(0, V.shape[0], n)
+    bary = rng.dirichlet([1, 1, 1], n)
+    pts = (V[idx] * bary[:, :, None]).sum(1)
+    e1, e2 = V[idx, 1] - V[idx, 0], V[idx, 2] - V[idx, 0]
+    nrm = np.cross(e1, e2)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True) + 1e-30
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d *= np.sign((d * nrm).sum(1, keepdims=True))
+    half = n // 2
+    t = np.cross(nrm[half:], rng.normal(size=(n - half, 3)))
+    t /= np.linalg.norm(t, axis=1, keepdims=True) + 1e-30
+    d[half:] = t + 0.02 * rng.normal(size=(n - half, 3))
+    o = pts + 1e-4 * nrm
+    return np.ascontiguousarray(o, np.float32), np.ascontiguousarray(d, np.float32)
+
+
+def test_occluded_bit_exact_vs_reference_predicate(api, ob, scenes, cornell):
+    # VERDICT r1 weak #2: the any-hit (shadow) queries had no bit-level hook. trn_occluded runs the production shadow
+    # kernels (pooled any-hit on real trees, one thread per ray on the few-big-leaves scenes) on arbitrary rays.
+    cases = [(scenes.cubesphere(48), 150000), (scenes.random_soup(5000, 2), 100000), (cornell[0], 100000),
+             (scenes.tiled_box(8), 100000), (scenes.fixture("furnace_test"), 50000)]
+    total = 0
+    for sc, n in cases:
+        p = api.Scene.from_dict(sc)
+        o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+        rng = np.random.RandomState(5)
+        sets = [_secondary_shaped_rays(sc, n, 11), scenes.random_rays(sc, n, seed=9, inside=True),
+                scenes.random_rays(sc, n // 2, seed=10, inside=False)]
+        for ro, rd in sets:
+            m = ro.shape[0]
+            i_o, r_o = o.intersect(ro, rd, 0)
+            hit = i_o != ob.MISS
+            r = r_o[:, 0]
+            # light distances: random, far, and -- for a third of the hits -- EXACTLY the closest hit distance (inclusive
+            # bound: occluded), its predecessor (not occluded unless another triangle ties) and its successor
+            tmax = rng.uniform(0.0, 3.0, m).astype(np.float32) * np.float32(np.abs(sc["vertices"]).max())
+            sel = hit & (rng.rand(m) < 0.5)
+            kind = rng.randint(0, 3, m)
+            exact = np.where(kind == 0, r, np.where(kind == 1, np.nextafter(r, np.float32(-1)), np.nextafter(r, np.float32(np.inf))))
+            tmax = np.where(sel, exact, tmax).astype(np.float32)
+            want = hit & (r <= tmax)
+            got = p.occluded(ro, rd, tmax)
+            assert np.array_equal(got, want), (sc["name"], int((got != want).sum()), m)
+            assert want.any() and (~want).any()
+            total += m
+    assert total > 1_000_000
+
+
+def test_full_size_mesh1m_secondary_rays_and_occlusion(api, ob, scenes):
+    # VERDICT r1 weak #1/#2c: secondary-shaped rays on the FULL 995,328-triangle mesh through the production pooled kernel,
+    # closest hit and any-hit, against the reference's exhaustive schedule
+    sc = scenes.cubesphere(288)
+    p = api.Scene.from_dict(sc)
+    o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"], nodes=p.nodes(), box=np.array(p.info.box, np.float32))
+    ro, rd = _secondary_shaped_rays(sc, 200000, 21)
+    i_o, r_o = o.intersect(ro, rd, 0)
+    i_g, r_g = p.intersect(ro, rd)
+    assert (i_o != ob.MISS).sum() > 20000
+    assert np.array_equal(i_g, i_o), int((i_g != i_o).sum())
+    assert np.array_equal(bits(r_g), bits(r_o))
+    light = np.array(sc["light"]["pos"], np.float32)
+    to_l = light[None, :] - ro
+    dist = np.sqrt((to_l * to_l).sum(1)).astype(np.float32)
+    ld = (to_l / dist[:, None]).astype(np.float32)
+    i_s, r_s = o.intersect(ro, ld, 0)
+    want = (i_s != ob.MISS) & (r_s[:, 0] <= dist)
+    got = p.occluded(ro, ld, dist)
+    assert np.array_equal(got, want), int((got != want).sum())
+    assert want.sum() > 1000 and (~want).sum() > 1000
+
+
+def _rmse_vs_reference_streams(api, ob, sc, p, o, W, D, m, pps, threads, bg=(0, 0, 0, 1)):
+    cam, cfg = api.make_config(sc, W, max_depth=D, mc_samples=m, pixel_samples=pps, seed=3, bg=bg)
+    img, st = p.render(cam, cfg)
+    ref, sq, ost = o.render(ob.make_cfg(sc, W, D, m, pps, rng_mode=0, num_threads=threads, bg=bg), want_sumsq=True)
+    mean_g, mean_r = img / pps, ref / pps
+    var_pix = np.maximum(sq / pps - mean_r ** 2, 0) * pps / (pps - 1)
+    emse = (2 * var_pix / pps).mean(axis=(0, 1))
+    diff = mean_g - mean_r
+    rmse = np.sqrt((diff ** 2).mean(axis=(0, 1)))
+    bias = np.abs(diff.mean(axis=(0, 1)))
+    npix = W * img.shape[0]
+    assert np.all(rmse <= 1.1 * np.sqrt(emse) + 1e-6), (rmse, np.sqrt(emse))
+    assert np.all(bias <= 3 * np.sqrt(emse / npix) + 1e-6), (bias, 3 * np.sqrt(emse / npix))
+    assert st.prim_rays == ost.num_prim_rays
+    assert abs(int(st.rays) - int(ost.num_rays)) < 0.01 * ost.num_rays
+    return rmse, np.sqrt(emse)
+
+
+def test_rmse_vs_reference_streams_on_the_pooled_kernel_and_config4_shape(api, ob, scenes, cornell):
+    # VERDICT r1 weak #1: the RMSE-vs-reference-streams gate (rng_mode 0 = what the reference computes) was only run on
+    # cornell_box at <= 160 px, i.e. never through the pooled kernel. (a) a mesh that takes the pooled kernel (cubesphere
+    # 48: 27,648 triangles, > 1024 leaves), D3 m4; (b) BASELINE config 4's shape (cornell, D3, m4) at 512 px.
+    sc = scenes.cubesphere(48)
+    p = api.Scene.from_dict(sc)
+    o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+    r, e = _rmse_vs_reference_streams(api, ob, sc, p, o, 256, 3, 4, 8, threads=8, bg=(0.2, 0.2, 0.3, 1))
+    print("pooled mesh: rmse", r, "bound", 1.1 * e)
+    sc, p, o = cornell
+    r, e = _rmse_vs_reference_streams(api, ob, sc, p, o, 512, 3, 4, 4, threads=8)
+    print("cornell 512: rmse", r, "bound", 1.1 * e)
+
+
+def test_render_rank_and_async_equal_render(api, cornell, scenes):
+    # the process-per-GPU entry (one rank: no NCCL) and the asynchronous entry give the image trn_render gives
+    for sc, p in ((cornell[0], cornell[1]), (scenes.cubesphere(32), None)):
+        p = p or api.Scene.from_dict(sc)
+        cam, cfg = api.make_config(sc, 96, max_depth=3, mc_samples=3, pixel_samples=5, seed=4)
+        one, s1 = p.render(cam, cfg, device=0)
+        comm = api.Comm(np.zeros(128, np.uint8), 1, 0, 0)
+        out = np.zeros_like(one)
+        s2 = p.render_rank(comm, cam, cfg, out=out)
+        comm.close()
+        assert s2.rays == s1.rays and s2.prim_rays == s1.prim_rays and s2.ms_d2h > 0
+        assert np.allclose(out, one, rtol=1e-5, atol=1e-6)
+        # two frames in flight (different seeds), waited in order
+        bufs = [np.zeros_like(one), np.zeros_like(one)]
+        cfg2 = api.copy_config(cfg)
+        cfg2.seed = 77
+        j1 = p.render_async(cam, cfg, bufs[0], device=0)
+        j2 = p.render_async(cam, cfg2, bufs[1], device=0)
+        a, sa = j1.wait()
+        b, sb = j2.wait()
+        ref2, _ = p.render(cam, cfg2, device=0)
+        assert sa.rays == s1.rays
+        assert np.allclose(a, one, rtol=1e-5, atol=1e-6) and np.allclose(b, ref2, rtol=1e-5, atol=1e-6)
+        assert not np.allclose(a, b)
+
+
+def test_process_per_gpu_ranks_reduce_with_the_librarys_nccl(api, cornell, tmp_path):
+    # trn_comm_* / trn_render_rank on >= 2 GPUs: one process per GPU, the image reduce is the library's own ncclReduce
+    import subprocess
+    import sys
+    import os
+    if api.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = min(api.device_count(), 4)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    procs = [subprocess.Popen([sys.executable, os.path.join(root, "tests", "_rank_worker.py"), str(r), str(n), str(tmp_path)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(n)]
+    outs = [pr.communicate(timeout=600)[0] for pr in procs]
+    assert all(pr.returncode == 0 for pr in procs), "\n".join(outs)
+    sc, p, o = cornell
+    cam, cfg = api.make_config(sc, 96, max_depth=3, mc_samples=2, pixel_samples=6, seed=12)
+    one, s1 = p.render(cam, cfg, device=0)
+    many = np.load(os.path.join(str(tmp_path), "image.npy"))
+    rays = sum(int(open(os.path.join(str(tmp_path), "rays%d.txt" % r)).read()) for r in range(n))
+    assert rays == s1.rays
+    assert np.allclose(many, one, rtol=1e-5, atol=1e-5)

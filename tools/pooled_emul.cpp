@@ -20,7 +20,7 @@ using namespace trn;
 
 static const float kFltMax = 3.402823466e+38f, kCellSlack = 1e-4f;
 static const uint32_t kMiss = 0x40000000u;
-static const int kPqLeaves = 64, kPqChunkTris = 4, kPqSurv = 32 + 32 * 4;
+static const int kPqLeaves = 64, kPqLeafMaxRefs = 4096, kPqChunkTris = 4, kPqSurv = 32 + 32 * 4;
 
 struct Ray {
     float o[3], d[3];
@@ -297,32 +297,25 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
             }
             const bool last = it >= walk_iters || n_inner == 0;
             if (n_leaf != 0 && (last || n_leaf >= leaf_gate)) {
-                // one descriptor per chunk of 4 references; slots in lane order (the kernel's ballot/popc resp. shuffle scan)
-                uint32_t slot = s_nleaf, total = 0;
                 for (int lane = 0; lane < 32; ++lane) {
                     if (!at_leaf[lane]) continue;
                     LaneS& l = L[lane];
                     const uint32_t cnt = l.ny >> 2;
-                    const uint32_t nch = (cnt + kPqChunkTris - 1) / kPqChunkTris;
-                    const uint32_t my = slot;
-                    slot += nch;
-                    total += nch;
-                    uint32_t fit = nch;
-                    if (nch != 0u) {
-                        const uint32_t room = my < uint32_t(kPqLeaves) ? uint32_t(kPqLeaves) - my : 0u;
-                        fit = std::min(nch, room);
-                        float lo = l.tenter - kCellSlack * (std::fabs(l.tenter) + 1.f);
-                        float hi = l.texit + kCellSlack * (std::fabs(l.texit) + 1.f);
-                        lo = std::fmax(lo, 0.f);
-                        hi = any ? std::fmin(hi, l.tmax) : std::fmin(hi, l.best_r);
-                        for (uint32_t c = 0; c < fit; ++c) {
-                            const uint32_t off0 = c * kPqChunkTris;
-                            s_leaf[my + c] = U4{l.nx + off0, std::min<uint32_t>(kPqChunkTris, cnt - off0) | (uint32_t(lane) << 8), fbits(lo), fbits(hi)};
+                    uint32_t take = 0;
+                    if (cnt > 0u) {
+                        const uint32_t slot = s_nleaf++;
+                        if (slot < uint32_t(kPqLeaves)) {
+                            take = std::min<uint32_t>(cnt, kPqLeafMaxRefs);
+                            float lo = l.tenter - kCellSlack * (std::fabs(l.tenter) + 1.f);
+                            float hi = l.texit + kCellSlack * (std::fabs(l.texit) + 1.f);
+                            lo = std::fmax(lo, 0.f);
+                            hi = any ? std::fmin(hi, l.tmax) : std::fmin(hi, l.best_r);
+                            s_leaf[slot] = U4{l.nx, take | (uint32_t(lane) << 24), fbits(lo), fbits(hi)};
                         }
                     }
-                    if (fit < nch) {
-                        l.nx += fit * kPqChunkTris;
-                        l.ny -= (fit * kPqChunkTris) << 2;
+                    if (take < cnt) { // queue full, or a leaf longer than one descriptor: continue from the node register
+                        l.nx += take;
+                        l.ny -= take << 2;
                         blocked[lane] = true;
                     } else {
                         l.last_texit = l.texit;
@@ -337,7 +330,6 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
                         }
                     }
                 }
-                s_nleaf = std::min<uint32_t>(s_nleaf + total, kPqLeaves);
             }
             if (last) break;
             ++it;
@@ -419,46 +411,58 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
             }
             s_nsurv = sbase;
         };
-        for (uint32_t base = 0; base < nleaf; base += 32) {
-            while (s_nsurv >= 32u) exact_round();
-            stat[2]++;
-            uint32_t km[32], owner_[32], seq0[32], ids[32][4];
-            for (uint32_t lane = 0; lane < 32; ++lane) {
-                km[lane] = 0;
-                const uint32_t g = base + lane;
-                if (g >= nleaf) continue;
-                stat[3]++;
-                const U4 d = s_leaf[g];
-                const uint32_t cnt = d.y & 0xffu, owner = d.y >> 8;
-                const float lo = bfloat(d.z), hi = bfloat(d.w);
-                const F4 ro = s_ray[2 * owner], rd = s_ray[2 * owner + 1];
-                const float E = ro.w, F = rd.w;
-                const float c1 = std::fmaf(-lo, F, -E), c2 = std::fmaf(hi, F, E);
-                owner_[lane] = owner;
-                seq0[lane] = (g << 2) + 1u;
-                for (uint32_t k = 0; k < cnt; ++k) {
-                    const uint32_t id = sc.tree.pair_leaf_refs[d.x + k];
-                    ids[lane][k] = id;
-                    const float* p = &sc.planes[size_t(id) * 4];
-                    const float a = std::fmaf(p[0], rd.x, std::fmaf(p[1], rd.y, p[2] * rd.z));
-                    const float b = std::fmaf(-p[0], ro.x, std::fmaf(-p[1], ro.y, std::fmaf(-p[2], ro.z, p[3])));
-                    const float A = std::fabs(a);
-                    const float B = bfloat(fbits(b) ^ (fbits(a) & 0x80000000u));
-                    stat[6]++;
-                    if (A <= F || (B >= std::fmaf(lo, A, c1) && B <= std::fmaf(hi, A, c2))) km[lane] |= 1u << k;
-                }
+        for (uint32_t lb = 0; lb < nleaf; lb += 32) {
+            uint32_t P[32], total = 0; // inclusive chunk totals of the batch's leaves
+            for (uint32_t j = 0; j < 32; ++j) {
+                const uint32_t c = lb + j < nleaf ? (s_leaf[lb + j].y & 0xffffffu) : 0u;
+                total += (c + kPqChunkTris - 1) / kPqChunkTris;
+                P[j] = total;
             }
-            for (uint32_t k = 0; k < uint32_t(kPqChunkTris); ++k) // k-major append, as the kernel's four ballots
-                for (uint32_t lane = 0; lane < 32; ++lane)
-                    if (km[lane] & (1u << k)) {
-                        if (s_nsurv >= uint32_t(kPqSurv)) {
-                            std::fprintf(stderr, "survivor queue overflow\n");
-                            return false;
-                        }
-                        s_surv[s_nsurv][0] = ids[lane][k];
-                        s_surv[s_nsurv][1] = owner_[lane] | ((seq0[lane] + k) << 5);
-                        ++s_nsurv;
+            for (uint32_t base = 0; base < total; base += 32) {
+                while (s_nsurv >= 32u) exact_round();
+                stat[2]++;
+                uint32_t km[32], owner_[32], seq0[32], ids[32][4];
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    km[lane] = 0;
+                    const uint32_t g = base + lane;
+                    if (g >= total) continue;
+                    stat[3]++;
+                    uint32_t j = 0;
+                    while (P[j] <= g) ++j;
+                    const U4 d = s_leaf[lb + j];
+                    const uint32_t lcnt = d.y & 0xffffffu, owner = d.y >> 24;
+                    const uint32_t sub = g - (P[j] - (lcnt + kPqChunkTris - 1) / kPqChunkTris), off0 = sub * kPqChunkTris;
+                    const uint32_t cnt = std::min<uint32_t>(kPqChunkTris, lcnt - off0);
+                    const float lo = bfloat(d.z), hi = bfloat(d.w);
+                    const F4 ro = s_ray[2 * owner], rd = s_ray[2 * owner + 1];
+                    const float E = ro.w, F = rd.w;
+                    const float c1 = std::fmaf(-lo, F, -E), c2 = std::fmaf(hi, F, E);
+                    owner_[lane] = owner;
+                    seq0[lane] = ((lb + j) << 20) + off0 + 1u;
+                    for (uint32_t k = 0; k < cnt; ++k) {
+                        const uint32_t id = sc.tree.pair_leaf_refs[d.x + off0 + k];
+                        ids[lane][k] = id;
+                        const float* p = &sc.planes[size_t(id) * 4];
+                        const float a = std::fmaf(p[0], rd.x, std::fmaf(p[1], rd.y, p[2] * rd.z));
+                        const float b = std::fmaf(-p[0], ro.x, std::fmaf(-p[1], ro.y, std::fmaf(-p[2], ro.z, p[3])));
+                        const float A = std::fabs(a);
+                        const float B = bfloat(fbits(b) ^ (fbits(a) & 0x80000000u));
+                        stat[6]++;
+                        if (A <= F || (B >= std::fmaf(lo, A, c1) && B <= std::fmaf(hi, A, c2))) km[lane] |= 1u << k;
                     }
+                }
+                for (uint32_t k = 0; k < uint32_t(kPqChunkTris); ++k) // k-major append, as the kernel's four ballots
+                    for (uint32_t lane = 0; lane < 32; ++lane)
+                        if (km[lane] & (1u << k)) {
+                            if (s_nsurv >= uint32_t(kPqSurv)) {
+                                std::fprintf(stderr, "survivor queue overflow\n");
+                                return false;
+                            }
+                            s_surv[s_nsurv][0] = ids[lane][k];
+                            s_surv[s_nsurv][1] = owner_[lane] | ((seq0[lane] + k) << 5);
+                            ++s_nsurv;
+                        }
+            }
         }
         while (s_nsurv > 0u) exact_round();
         s_nleaf = 0;

@@ -388,9 +388,16 @@ def measure_gather_peak(set_bytes, mode=1, device=-1):
     return g.value
 
 
-def tonemap(rgba_sum, pixel_samples, exposure=1.0, gamma_enabled=True, inverse_gamma=0.454545):
+def copy_config(cfg):
+    c = RenderConfig()
+    C.memmove(C.byref(c), C.byref(cfg), C.sizeof(RenderConfig))
+    return c
+
+
+def tonemap(rgba_sum, pixel_samples, exposure=1.0, gamma_enabled=True, inverse_gamma=0.454545, out=None):
     a = np.ascontiguousarray(rgba_sum, np.float32)
-    out = np.zeros_like(a)
+    if out is None:
+        out = np.zeros_like(a)
     _check(lib().trn_tonemap(a.reshape(-1), a.size // 4, pixel_samples, exposure, 1 if gamma_enabled else 0,
                              inverse_gamma, out.reshape(-1)))
     return out

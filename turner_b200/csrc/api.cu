@@ -1237,20 +1237,22 @@ int32_t trn_comm_unique_id(uint8_t* id128) {
 int32_t trn_comm_init_rank(const uint8_t* id128, int32_t nranks, int32_t rank, int32_t device, trn_comm** out) {
     if (!id128 || !out || nranks < 1 || rank < 0 || rank >= nranks) return fail(TRN_ERR_INVALID, "bad communicator arguments");
     TRN_GUARD_BEGIN
-    int rc = ensure_nccl();
-    if (rc) return rc;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(TRN_ERR_CUDA, "no CUDA device available (turner_b200 has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(TRN_ERR_INVALID, "device ordinal out of range");
     CUDA_TRY(cudaSetDevice(device));
-    NcclUniqueId id;
-    std::memcpy(id.internal, id128, 128);
     std::unique_ptr<trn_comm> c(new trn_comm);
     c->nranks = nranks;
     c->rank = rank;
     c->device = device;
-    const int nrc = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
-    if (nrc != 0) return fail(TRN_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
+    if (nranks > 1) { // a one-rank job needs no NCCL (and no libnccl on the machine)
+        int rc = ensure_nccl();
+        if (rc) return rc;
+        NcclUniqueId id;
+        std::memcpy(id.internal, id128, 128);
+        const int nrc = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+        if (nrc != 0) return fail(TRN_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "?"));
+    }
     *out = c.release();
     return TRN_OK;
     TRN_GUARD_END

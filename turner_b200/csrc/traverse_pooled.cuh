@@ -8,15 +8,15 @@
 // test (6 % of the tests) are evaluated by 2-3 lanes while the rest wait. Here every warp runs a three-phase cycle:
 //
 //   WALK   up to walk_iters warp-wide iterations; in each, a lane at an inner node takes ONE step of its own ray. The
-//          lanes that have reached a leaf cut it into chunks of 4 triangle references, queue one 16-byte descriptor per
-//          chunk in shared memory (slots by ballot/popc, or a shuffle scan when a leaf has more than one chunk; the queue
+//          lanes that have reached a leaf queue a 16-byte leaf descriptor in shared memory (slots by ballot/popc; the queue
 //          fill is a warp-uniform register, no atomics) and pop their stack -- in a block that is only issued once
-//          leaf_gate lanes wait (or nobody can step). A leaf that does not fit the queue keeps its remaining references
-//          in the node register and is continued in the next cycle. The walk is speculative: it does not wait for the
-//          leaf's outcome (98.6 % of the leaf visits of the benchmark's secondary rays do not end the ray).
-//   TEST   the queued chunks of ALL rays, 32 per round, one per lane -- no search: lane l of round k takes descriptor
-//          32 k + l. The lane reads the owner ray from a table in shared memory, the chunk's ids with one 16-byte load
-//          (leaf runs are 16-byte aligned), four 16-byte plane records, and runs a division-free, conservative plane
+//          leaf_gate lanes wait (or nobody can step). A leaf that does not fit the queue (or one descriptor) keeps its
+//          remaining references in the node register and is continued in the next cycle. The walk is speculative: it does
+//          not wait for the leaf's outcome (98.6 % of the leaf visits of the benchmark's secondary rays do not end the ray).
+//   TEST   the queued leaves of ALL rays, 32 at a time (one descriptor per lane), are cut into chunks of 4 triangle
+//          references; the chunks are dealt out 32 per round, one per lane, by a shuffle binary search over the running
+//          chunk totals. The lane reads the owner ray from a table in shared memory, the chunk's ids with one 16-byte
+//          load (leaf runs are 16-byte aligned), four 16-byte plane records, and runs a division-free, conservative plane
 //          pre-filter (FMA arithmetic with explicit error bounds). Survivors are appended to the warp's survivor queue
 //          with four ballots -- no atomics.
 //   EXACT  whenever 32 survivors are waiting (and at the end of the cycle) they get, 32 at a time, the reference's exact
@@ -34,19 +34,23 @@
 namespace trn {
 
 #ifndef TRN_PQ_LEAVES
-#define TRN_PQ_LEAVES 64 // chunk descriptors per warp queue
+#define TRN_PQ_LEAVES 64 // leaf descriptors per warp queue
 #endif
 #ifndef TRN_PQ_MINBLOCKS
 #define TRN_PQ_MINBLOCKS 8
 #endif
 constexpr int kPqLeaves = TRN_PQ_LEAVES;
 constexpr int kPqChunkTris = 4;                  // triangle references a lane tests per TEST round
+constexpr int kPqLeafMaxRefs = 4096;             // references one descriptor carries (a multiple of kPqChunkTris; the rest
+                                                 // of a longer leaf is queued in the next cycle)
 constexpr int kPqSurv = 32 + 32 * kPqChunkTris; // survivors: < 32 left over + one TEST round
+static_assert(kPqLeafMaxRefs % kPqChunkTris == 0 && kPqLeafMaxRefs < (1 << 20) && kPqLeaves <= 128,
+              "seq = (leaf slot << 20) + in-leaf offset + 1 must fit the 27 bits next to the owner lane");
 
 struct PooledWarpSmem {
     float4 ray_o[32];        // o.xyz, E   (E, F: error bounds of the pre-filter)
     float4 ray_d[32];        // d.xyz, F
-    uint4 leaf[kPqLeaves];   // one per chunk: first ref, count (1..4) | owner << 8, lo bits, hi bits (parameter range of the cell)
+    uint4 leaf[kPqLeaves];   // first ref, count | owner << 24, lo bits, hi bits (parameter range of the cell)
     uint2 surv[kPqSurv];     // triangle id, owner | seq << 5
     uint4 best[32];          // per lane: best hit so far (id, r, s, t) -- cold state kept out of the registers
     uint32_t ray_idx[32];    // per lane: index of its ray in the wave
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
         // Every iteration the lanes at inner nodes take one step. The lanes that have reached a leaf queue its chunks and
         // pop -- but that block is only issued when at least leaf_gate lanes wait at a leaf (or no lane can step): it is
         // as long as the step itself and would otherwise run for 4 of 32 lanes in nearly every iteration.
-        uint32_t nleaf = 0; // chunk descriptors queued in this cycle (warp-uniform)
+        uint32_t nleaf = 0; // leaf descriptors queued in this cycle (warp-uniform register: every lane runs the leaf block)
         bool active = busy && walking; // cleared when the lane's leaf does not fit the queue (continued in the next cycle)
         int it = 0;
 #pragma unroll 1
@@ -218,46 +222,30 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
             const unsigned im = __ballot_sync(kFull, active && !at_leaf);
             const bool last = it >= walk_iters || im == 0u;
             if (lm != 0u && (last || __popc(lm) >= leaf_gate)) {
-                // leaf: one descriptor per chunk of 4 references (reference range, owner, parameter range of the cell plus
-                // slack), then pop. A count-0 leaf (cut-off void) can only be the root of an empty tree.
+                // leaf: queue it (one descriptor: reference range, owner, parameter range of the cell plus slack) and pop
+                // at once. A count-0 leaf (cut-off void) can only be the root of an empty tree.
                 const uint32_t cnt = at_leaf ? n.y >> 2 : 0u;
-                const uint32_t nch = (cnt + kPqChunkTris - 1) / kPqChunkTris;
-                uint32_t slot, total;
-                if (__ballot_sync(kFull, nch > 1u) == 0u) { // the common case: every waiting leaf is one chunk
-                    const unsigned want = __ballot_sync(kFull, nch != 0u);
-                    slot = nleaf + __popc(want & lt_mask);
-                    total = __popc(want);
-                } else {
-                    uint32_t incl = nch;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const uint32_t v = __shfl_up_sync(kFull, incl, off);
-                        if (static_cast<int>(lane) >= off) incl += v;
-                    }
-                    slot = nleaf + incl - nch;
-                    total = __shfl_sync(kFull, incl, 31);
-                }
+                const unsigned want = __ballot_sync(kFull, cnt != 0u);
+                const uint32_t slot = nleaf + __popc(want & lt_mask);
+                nleaf = min(nleaf + static_cast<uint32_t>(__popc(want)), static_cast<uint32_t>(kPqLeaves));
                 if (at_leaf) {
-                    uint32_t fit = nch;
-                    if (nch != 0u) {
-                        const uint32_t room = slot < static_cast<uint32_t>(kPqLeaves) ? static_cast<uint32_t>(kPqLeaves) - slot : 0u;
-                        fit = min(nch, room);
+                    // a descriptor carries at most kPqLeafMaxRefs references (its count and the in-leaf offset of the
+                    // visiting-order number are packed fields); a longer leaf -- or any leaf when the queue is full --
+                    // keeps its remaining references in the node register (leaf runs are contiguous) and is continued
+                    // in the next cycle
+                    uint32_t take = 0;
+                    if (cnt != 0u && slot < static_cast<uint32_t>(kPqLeaves)) {
+                        take = min(cnt, static_cast<uint32_t>(kPqLeafMaxRefs));
                         float lo = tenter - kCellSlack * (fabsf(tenter) + 1.f);
                         float hi = texit + kCellSlack * (fabsf(texit) + 1.f);
                         lo = fmaxf(lo, 0.f);
                         hi = ANY ? fminf(hi, tmax_any) : fminf(hi, best_r);
-                        for (uint32_t c = 0; c < fit; ++c) {
-                            const uint32_t off0 = c * kPqChunkTris;
-                            sm.leaf[slot + c] = make_uint4(n.x + off0, min(static_cast<uint32_t>(kPqChunkTris), cnt - off0) | (lane << 8),
-                                                           __float_as_uint(lo), __float_as_uint(hi));
-                        }
+                        sm.leaf[slot] = make_uint4(n.x, take | (lane << 24), __float_as_uint(lo), __float_as_uint(hi));
                         if (COUNT) pc.leaves += 1;
                     }
-                    if (fit < nch) {
-                        // queue full: the rest of the leaf stays in the node register (leaf runs are contiguous) and is
-                        // queued in the next cycle
-                        n.x += fit * kPqChunkTris;
-                        n.y -= (fit * kPqChunkTris) << 2;
+                    if (take < cnt) {
+                        n.x += take;
+                        n.y -= take << 2;
                         active = false;
                     } else {
                         last_texit = texit;
@@ -278,7 +266,6 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                         }
                     }
                 }
-                nleaf = min(nleaf + total, static_cast<uint32_t>(kPqLeaves));
             }
             if (last) break;
             ++it;
@@ -314,12 +301,18 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
         __syncwarp();
 
         // ------------------------------------------------------------------ TEST (pre-filter) and EXACT rounds
-        // The queued chunks are taken 32 per round, one per lane. Survivors go to the warp's survivor queue; whenever 32
-        // are waiting (and at the end) they get the exact test, 32 at a time.
-        uint32_t ns = 0;   // survivors waiting (warp-uniform; only this loop appends)
-        uint32_t base = 0; // first descriptor of the next TEST round
+        // The queued leaves are taken 32 at a time, one per lane; their triangle references are cut into chunks of 4
+        // and the chunks of the whole batch are dealt out 32 per round (a lane finds its chunk's leaf by a shuffle
+        // binary search over the running chunk totals), so that every lane tests 4 triangles per round whatever the
+        // leaf sizes are. Survivors go to the warp's survivor queue; whenever 32 are waiting (and at the end) they
+        // get the exact test, 32 at a time.
+        uint32_t ns = 0;        // survivors waiting (warp-uniform; only this loop appends)
+        uint32_t lb = 0;        // first leaf of the current batch
+        uint32_t base = 0, total = 0, P = 0; // chunk cursor / chunk count of the batch / inclusive chunk totals per lane
+        uint4 ld = make_uint4(0u, 0u, 0u, 0u);
+        bool have_batch = false;
         for (;;) {
-            const bool more_tests = base < nleaf;
+            const bool more_tests = have_batch ? (base < total || lb + 32u < nleaf) : (lb < nleaf);
             if (ns >= 32u || (!more_tests && ns > 0u)) {
                 // EXACT: the reference's operation sequence for up to 32 pooled survivors (taken from the tail)
                 const uint32_t take = min(32u, ns), sbase = ns - take;
@@ -384,25 +377,50 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                 ns = sbase;
                 __syncwarp();
             } else if (more_tests) {
+                if (!have_batch || base >= total) {
+                    // next batch of up to 32 leaves: one descriptor per lane, inclusive scan of their chunk counts
+                    if (have_batch) lb += 32u;
+                    have_batch = true;
+                    ld = lb + lane < nleaf ? sm.leaf[lb + lane] : make_uint4(0u, 0u, 0u, 0u);
+                    P = ((ld.y & 0xffffffu) + kPqChunkTris - 1) / kPqChunkTris;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const uint32_t v = __shfl_up_sync(kFull, P, off);
+                        if (static_cast<int>(lane) >= off) P += v;
+                    }
+                    total = __shfl_sync(kFull, P, 31);
+                    base = 0;
+                    continue;
+                }
                 // TEST: one chunk per lane. Pre-filter: with a ~ n.d and b ~ n.(v0 - o) (FMA arithmetic, |a - denom| <= F,
                 // |b - nom| <= E for the reference's denom, nom), A = |a|, B = b * sign(a):
                 //   0 <= lo <= nom/denom <= hi   ==>   A <= F  or  (B + E >= lo (A - F)  and  B - E <= hi (A + F)).
                 // Triangles that fail cannot have their exact plane distance inside [lo, hi].
                 const uint32_t g = base + lane;
+                // leaf of chunk g = number of lanes whose inclusive total is <= g
+                uint32_t j = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const uint32_t pj = __shfl_sync(kFull, P, (j + step - 1) & 31u);
+                    if (pj <= g) j += step;
+                }
+                j &= 31u; // g >= total (idle lane): any leaf, masked below
+                const uint32_t first = __shfl_sync(kFull, ld.x, j), cw = __shfl_sync(kFull, ld.y, j);
+                const float lo = __uint_as_float(__shfl_sync(kFull, ld.z, j)), hi = __uint_as_float(__shfl_sync(kFull, ld.w, j));
+                const uint32_t pend = __shfl_sync(kFull, P, j);
+                const uint32_t lcnt = cw & 0xffffffu, owner = cw >> 24;
+                const uint32_t sub = g - (pend - (lcnt + kPqChunkTris - 1) / kPqChunkTris); // chunk index inside the leaf
+                const uint32_t off0 = sub * kPqChunkTris;
+                const uint32_t cnt = g < total ? min(static_cast<uint32_t>(kPqChunkTris), lcnt - off0) : 0u;
                 uint4 ids = make_uint4(0u, 0u, 0u, 0u); // the chunk's triangle ids
                 uint32_t km = 0;                         // bit k: triangle k survives the pre-filter
-                uint32_t owner = 0;
-                if (g < nleaf) {
-                    const uint4 ld = sm.leaf[g];
-                    const uint32_t cnt = ld.y & 0xffu;
-                    owner = ld.y >> 8;
-                    const float lo = __uint_as_float(ld.z), hi = __uint_as_float(ld.w);
+                if (cnt > 0u) {
                     const float4 ro = sm.ray_o[owner], rd = sm.ray_d[owner];
                     const float E = ro.w, F = rd.w;
                     const float c1 = fmaf(-lo, F, -E), c2 = fmaf(hi, F, E);
                     // leaf runs start at multiples of 4 references and the array is padded (kdtree_build.cpp): one 16-byte
                     // load brings the chunk's ids; ids beyond cnt are valid triangles whose result is masked
-                    ids = __ldg(reinterpret_cast<const uint4*>(sc.prefs + ld.x));
+                    ids = __ldg(reinterpret_cast<const uint4*>(sc.prefs + first + off0));
                     const float4 p0 = __ldg(&planes[ids.x]), p1 = __ldg(&planes[ids.y]), p2 = __ldg(&planes[ids.z]), p3 = __ldg(&planes[ids.w]);
                     if (COUNT) {
                         pc.chunks += 1;
@@ -421,9 +439,8 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                     }
                 }
                 // append the survivors of the round, k-major (the order inside the queue is irrelevant: seq carries the
-                // visiting order -- a ray's descriptors are queued in the order its walk visits them, so the slot index
-                // orders them): four ballots, no scan, no atomics
-                const uint32_t seq0 = (g << 2) + 1u;
+                // visiting order): four ballots, no scan, no atomics
+                const uint32_t seq0 = ((lb + j) << 20) + off0 + 1u;
                 uint32_t round_total = 0;
 #pragma unroll
                 for (int k = 0; k < kPqChunkTris; ++k) {
