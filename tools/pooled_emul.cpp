@@ -188,7 +188,7 @@ static bool occluded_plain(const Scene& sc, const Ray& ray) {
         ny_ = e.y;
         tenter = e.a;
         texit = e.b;
-        if (tenter > tmax) return false;
+        if (tenter - kCellSlack * (std::fabs(tenter) + 1.f) > tmax) return false;
     }
 }
 
@@ -271,7 +271,7 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
                                 l.busy = true;
                 l.occluded = false;
                 l.tmax = ry.tmax;
-                l.walking = !(any && l.tenter > l.tmax);
+                l.walking = !(any && l.tenter - kCellSlack * (std::fabs(l.tenter) + 1.f) > l.tmax);
                 const float E = 1.9073486e-6f * (3.f * scale + (std::fabs(l.ox) + std::fabs(l.oy) + std::fabs(l.oz)));
                 const float F = 9.5367432e-7f * (std::fabs(dx) + std::fabs(dy) + std::fabs(dz));
                 s_ray[2 * lane] = F4{l.ox, l.oy, l.oz, E};
@@ -326,7 +326,7 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
                             l.ny = e.y;
                             l.tenter = bfloat(e.z);
                             l.texit = bfloat(e.w);
-                            if (any ? l.tenter > l.tmax : l.tenter > l.best_r) l.walking = false;
+                            if (any ? l.tenter - kCellSlack * (std::fabs(l.tenter) + 1.f) > l.tmax : l.tenter > l.best_r) l.walking = false;
                         }
                     }
                 }

@@ -1,12 +1,15 @@
-import json, sys
+#!/usr/bin/env python3
+"""one line per bench JSON on stdin"""
+import json
+import sys
+
 for line in sys.stdin:
     line = line.strip()
     if not line.startswith("{"):
         continue
     d = json.loads(line)
     r = d.get("roofline") or {}
-    print("value %.1f Mrays/s  ms/step %.2f  e2e %.1f  kernel_ms %s  frac %.3f  launches %s" % (
-        d["value"], d["ms_per_step"], d["e2e"]["value"], {k: round(v, 2) for k, v in (r.get("kernel_ms") or {}).items()},
-        r.get("frac", 0), d.get("gpu_launches")))
-    if r:
-        print("   per_query(ref schedule)", r.get("per_query"), "actual", r.get("per_query_actual"), "cpu", d.get("cpu_baseline"))
+    k = r.get("kernel_ms") or {}
+    print("%.1f Mrays/s  %.2f ms/step  e2e %.1f | trace %.1f shadow %.1f shade %.1f (ms, profiled leg) | frac %s" % (
+        d["value"], d["ms_per_step"], d["e2e"]["value"], k.get("ms_trace", 0), k.get("ms_shadow", 0), k.get("ms_shade", 0),
+        ("%.3f" % r["frac"]) if r else "-"))

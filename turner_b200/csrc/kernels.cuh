@@ -19,6 +19,10 @@ constexpr uint32_t kMiss = 0x40000000u;         // OptionalId miss, lib/kdtree.h
 constexpr int kStackDepth = 64;                 // >= tree height + 1 (checked at scene creation)
 constexpr float kFltMax = 3.402823466e+38f;
 constexpr float kCellSlack = 1e-4f;             // relative slack of the per-cell hit range (see traverse_pairs)
+// lower end of a cell's hit range: a plane hit up to this far in front of the cell's entry is still accepted in the cell
+// (rounding of r against the split-plane distances). Any rule that SKIPS a cell because it starts beyond a limit (the
+// light of an any-hit query) must compare this bound, not tenter itself.
+__host__ __device__ __forceinline__ float cell_lo(float tenter) { return tenter - kCellSlack * (fabsf(tenter) + 1.f); }
 
 // ------------------------------------------------------------------ device scene
 struct DevScene {
@@ -349,7 +353,9 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
         n = make_uint2(e.x, e.y);
         tenter = __uint_as_float(e.z);
         texit = __uint_as_float(e.w);
-        if (ANY_HIT && !axis_parallel && tenter > tmax_any) break;
+        // (pruned with the same slack the cell's hit range has: a hit within rounding noise in front of the cell's entry is
+        // accepted there, so the cell may only be skipped when even that lower bound lies beyond the light)
+        if (ANY_HIT && !axis_parallel && cell_lo(tenter) > tmax_any) break;
     }
     return out.id != kMiss;
 }

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_ker
                 n = make_uint2(e.x, e.y);
                 tenter = __uint_as_float(e.z);
                 texit = __uint_as_float(e.w);
-                if (ANY && !axis_parallel && tenter > tmax_any) finished = true;
+                if (ANY && !axis_parallel && cell_lo(tenter) > tmax_any) finished = true;
             }
             if (finished) {
                 busy = false;

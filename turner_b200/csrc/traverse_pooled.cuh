@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                             last_texit = -kFltMax;
                             occluded = false;
                             busy = true;
-                            walking = !(ANY && tenter > tmax_any);
+                            walking = !(ANY && cell_lo(tenter) > tmax_any);
                             // Error bounds of the pre-filter (u = 2^-24): its plane numerator b = dp - n.o (dp = n.v0 rounded
                             // once, three FMAs) and the reference's n.(v0 - o) (lib/intersection.h:47) both lie within
                             // 11 u (3 S + |o|_1) of each other, S = largest |coordinate| of the scene; the denominators
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                     uint32_t take = 0;
                     if (cnt != 0u && slot < static_cast<uint32_t>(kPqLeaves)) {
                         take = min(cnt, static_cast<uint32_t>(kPqLeafMaxRefs));
-                        float lo = tenter - kCellSlack * (fabsf(tenter) + 1.f);
+                        float lo = cell_lo(tenter);
                         float hi = texit + kCellSlack * (fabsf(texit) + 1.f);
                         lo = fmaxf(lo, 0.f);
                         hi = ANY ? fminf(hi, tmax_any) : fminf(hi, best_r);
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                             tenter = __uint_as_float(e.z);
                             texit = __uint_as_float(e.w);
                             // front to back: nothing at or behind a cell that starts beyond the light / the best hit matters
-                            if (ANY ? tenter > tmax_any : tenter > best_r) {
+                            if (ANY ? cell_lo(tenter) > tmax_any : tenter > best_r) {
                                 walking = false;
                                 active = false;
                             }
