@@ -480,8 +480,9 @@ static void launch_shadow(DeviceScene* ds, int mode, cudaStream_t stream, const 
     }
 }
 
-// wave buffers: `levels` ray waves of `cap` rays + one shadow wave + one hit buffer
-static int ensure_waves(DeviceScene* ds, uint64_t cap, int levels) {
+// wave buffers: `levels` ray waves of `cap` rays + two shadow waves + one hit buffer (+ the raytracer's child-slot array
+// and the ray-sorting scratch only when those paths are in use)
+static int ensure_waves(DeviceScene* ds, uint64_t cap, int levels, bool need_child_slot, bool need_sort) {
     if (ds->wave_cap != cap) {
         for (void* p : ds->wave_mem) cudaFree(p);
         ds->wave_mem.clear();
@@ -498,8 +499,8 @@ static int ensure_waves(DeviceScene* ds, uint64_t cap, int levels) {
         ds->wave_cap = cap;
     }
     if (!ds->d_hits) CUDA_TRY(cudaMalloc(&ds->d_hits, cap * sizeof(uint4)));
-    if (!ds->d_child_slot) CUDA_TRY(cudaMalloc(&ds->d_child_slot, cap * sizeof(uint32_t)));
-    if (!ds->d_keys) {
+    if (need_child_slot && !ds->d_child_slot) CUDA_TRY(cudaMalloc(&ds->d_child_slot, cap * sizeof(uint32_t)));
+    if (need_sort && !ds->d_keys) {
         CUDA_TRY(cudaMalloc(&ds->d_keys, cap * 4));
         CUDA_TRY(cudaMalloc(&ds->d_keys_alt, cap * 4));
         CUDA_TRY(cudaMalloc(&ds->d_order, cap * 4));
@@ -523,6 +524,27 @@ static int ensure_waves(DeviceScene* ds, uint64_t cap, int levels) {
         ds->waves.push_back(RayWave{p, p + cap, p + 2 * cap});
     }
     return TRN_OK;
+}
+
+// Rays per wave buffer. Bigger waves amortise the tails of the persistent kernels and the per-wave launches (whole-job
+// throughput on the 1M mesh: 8 Mi rays 1142, 16 Mi 1283, 32 Mi 1357, 64 Mi 1404 Mrays/s, profiles/README.md), and a B200 has
+// the memory for them: at least 16 Mi; a call with more primaries than that grows the buffers up to 128 Mi rays (48 B per
+// ray and depth level + 112 B of shadow and hit buffers: 39 GB at max-depth 3), within 60 % of the free device memory.
+// Buffers only grow. TRN_WAVE_CAP fixes the size (tests: results do not depend on it).
+static uint64_t choose_wave_cap(const DeviceScene* ds, uint64_t primaries, int levels) {
+    const uint64_t forced = env_u64("TRN_WAVE_CAP", 0);
+    if (forced) return std::max<uint64_t>(forced, 1024);
+    uint64_t want = 16ull << 20;
+    while (want < primaries && want < (128ull << 20)) want <<= 1;
+    want = std::max(want, ds->wave_cap);
+    size_t free_b = 0, total_b = 0;
+    if (want > ds->wave_cap && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const uint64_t per_ray = 48ull * static_cast<uint64_t>(levels) + 112ull;
+        const uint64_t have = ds->wave_cap * per_ray; // freed when the buffers are re-allocated
+        while (want > (16ull << 20) && want > ds->wave_cap && want * per_ray > (free_b + have) * 6 / 10) want >>= 1;
+        want = std::max(want, ds->wave_cap);
+    }
+    return want;
 }
 
 // the reference's per-row jitter stream (main.cpp:201-206): xorshift64star<float>(42), two draws per
@@ -860,8 +882,9 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
     if (ds_out) *ds_out = ds;
     FrameParams fp = make_frame(cam, cfg);
     const int levels = cfg->integrator == TRN_RAYCASTER ? 1 : cfg->max_depth + 1;
-    const uint64_t cap = env_u64("TRN_WAVE_CAP", 16ull << 20);
-    rc = ensure_waves(ds, cap, levels);
+    const uint64_t cap = choose_wave_cap(ds, static_cast<uint64_t>(fp.width) * fp.height * static_cast<uint64_t>(fp.n_local),
+                                         std::max(levels, static_cast<int>(ds->waves.size())));
+    rc = ensure_waves(ds, cap, levels, cfg->integrator == TRN_RAYTRACER, env_u64("TRN_SORT", 0) != 0);
     if (rc) return rc;
     rc = ensure_jitter(ds, cfg->width, cfg->pixel_samples);
     if (rc) return rc;
@@ -1122,8 +1145,8 @@ int32_t trn_primary_hits(trn_scene* scene, int32_t device, const trn_camera* cam
     c2.sample_begin = 0;
     c2.sample_stride = 1;
     FrameParams fp = make_frame(cam, &c2);
-    const uint64_t cap = env_u64("TRN_WAVE_CAP", 16ull << 20);
-    rc = ensure_waves(ds, cap, 1);
+    const uint64_t cap = choose_wave_cap(ds, 0, std::max(1, static_cast<int>(ds->waves.size())));
+    rc = ensure_waves(ds, cap, 1, false, false);
     if (rc) return rc;
     rc = ensure_jitter(ds, cfg->width, cfg->pixel_samples);
     if (rc) return rc;
