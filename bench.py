@@ -227,14 +227,15 @@ def cpu_reference_run(name, sc, nodes, box, steps=1, warmup=0, budget_s=100.0):
 def gather_peaks(api, device):
     """measured ceilings of random 16-byte gathers (the traversal kernels' access shape) on this device"""
     out = {}
-    for key, size, mode in (("l1_gbs", 32 << 10, 0), ("l2_gbs", 96 << 20, 1), ("hbm_gbs", 4 << 30, 1)):
+    for key, size, mode in (("l1_gbs", 32 << 10, 0), ("l2_gbs", 32 << 20, 1), ("l2_96m_gbs", 96 << 20, 1), ("hbm_gbs", 4 << 30, 1)):
         try:
             out[key] = api.measure_gather_peak(size, mode, device)
         except Exception as e:  # noqa: BLE001
             out[key] = None
             out[key + "_error"] = str(e)
     out["how"] = ("trn_measure_gather_peak: independent random 16-byte __ldg gathers, one line per lane, 8 in flight per "
-                  "thread, best of 3 after a warm-up run; working set 32 KiB (lives in every SM's L1) / 96 MiB (L2) / 4 GiB (HBM)")
+                  "thread, best of 3 after a warm-up run; working set 32 KiB (lives in every SM's L1) / 32 MiB (L2) / 96 MiB (about the "
+                  "scene's hot set: L2 with misses) / 4 GiB (HBM)")
     return out
 
 
@@ -276,6 +277,9 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # stdout carries exactly one JSON line: NCCL's version / debug banner (torch's and the library's communicator share
+    # one libnccl) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from turner_b200 import api, dist as tdist

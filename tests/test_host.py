@@ -166,3 +166,15 @@ def test_cache_with_a_lying_header_is_refused_without_allocating(api, tmp_path):
     p.write_bytes(b"\x01" + struct.pack("<Q", 5) + b"\0" * 100)  # count larger than the payload
     with pytest.raises(api.TurnerError):
         api.Scene.load_cache(str(p))
+
+
+def test_tonemap_zero_shortcut_is_bit_identical_to_the_oracle(api, ob):
+    rng = np.random.default_rng(11)
+    img = rng.random((64, 80, 4), dtype=np.float32) * 8
+    img[rng.random((64, 80)) < 0.5] = 0.0          # black background pixels
+    img[3, 5] = (-0.0, 0.0, 1.0, 1.0)              # a negative zero is not shortcut
+    for gamma in (True, False):
+        for exposure in (1.0, 0.0, 2.5):
+            a = api.tonemap(img, 4, exposure=exposure, gamma_enabled=gamma)
+            b = ob.tonemap(img, 4, exposure=exposure, gamma_enabled=gamma)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (gamma, exposure)

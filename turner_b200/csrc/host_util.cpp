@@ -42,9 +42,14 @@ int32_t trn_tonemap(const float* rgba_sum, uint64_t npix, int32_t pixel_samples,
         for (uint64_t i = lo; i < hi; ++i) {
             float c[4];
             for (int k = 0; k < 4; ++k) c[k] = rgba_sum[4 * i + k] / n;           // main.cpp:216
-            for (int k = 0; k < 3; ++k) c[k] = 1 - expf(-c[k] * exposure);        // effects.h:15-17
-            if (gamma_enabled)
-                for (int k = 0; k < 3; ++k) c[k] = powf(c[k], inverse_gamma);     // effects.h:36-38
+            // a channel that is exactly +0 stays +0 through both steps (1 - expf(-0 * e) = 0, powf(0, g) = 0 for g > 0):
+            // same bits without the two libm calls -- most of a frame whose background is black
+            const bool zero_ok = exposure >= 0.f && std::isfinite(exposure) && (!gamma_enabled || inverse_gamma > 0.f);
+            for (int k = 0; k < 3; ++k) {
+                if (zero_ok && c[k] == 0.f && !std::signbit(c[k])) continue;
+                c[k] = 1 - expf(-c[k] * exposure);                                // effects.h:15-17
+                if (gamma_enabled) c[k] = powf(c[k], inverse_gamma);              // effects.h:36-38
+            }
             std::memcpy(rgba_out + 4 * i, c, sizeof c);
         }
     };
