@@ -738,3 +738,85 @@ def test_process_per_gpu_ranks_reduce_with_the_librarys_nccl(api, cornell, tmp_p
     rays = sum(int(open(os.path.join(str(tmp_path), "rays%d.txt" % r)).read()) for r in range(n))
     assert rays == s1.rays
     assert np.allclose(many, one, rtol=1e-5, atol=1e-5)
+
+
+def _gpu_tree_cases(scenes):
+    return [scenes.four_triangles(), scenes.unit_cube(), scenes.fixture("cornell_box"), scenes.fixture("furnace_test"),
+            scenes.fixture("colored_cube"), scenes.random_soup(100, 1), scenes.random_soup(5000, 2), scenes.cubesphere(48),
+            scenes.tiled_box(8)]
+
+
+def test_device_built_tree_closest_hit_and_occlusion_parity(api, ob, scenes):
+    # the kd-tree built ON THE DEVICE (binned SAH, different shape than the reference's) must give the
+    # reference's hits: ids and (r,s,t) bit-exact against the reference's exhaustive traversal of ITS OWN tree; only which
+    # of several triangles reports an exact tie in r may differ (counted; none expected off the adversarial tiles)
+    total = 0
+    for sc in _gpu_tree_cases(scenes):
+        p = api.Scene.from_dict(sc, builder="gpu")
+        o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+        assert p.num_triangles == len(sc["vertices"])
+        n = 60000
+        sets = [scenes.random_rays(sc, n, seed=3, inside=True), scenes.random_rays(sc, n, seed=4, inside=False)]
+        if len(sc["vertices"]) >= 12:
+            sets.append(_secondary_shaped_rays(sc, n, 8))
+        for ro, rd in sets:
+            i_o, r_o = o.intersect(ro, rd, 0)
+            i_g, r_g = p.intersect(ro, rd)
+            assert not ((i_g == api.MISS_ID) ^ (i_o == ob.MISS)).any(), sc["name"]
+            assert np.array_equal(bits(r_g[:, 0]), bits(r_o[:, 0])), (sc["name"], "a hit distance differs")
+            ties = int((i_g != i_o).sum())
+            if sc["name"].startswith("tiled_box"):
+                print("device-built tree, %s: %d exact-tie id differences of %d rays" % (sc["name"], ties, len(i_o)))
+                same = i_g == i_o
+                assert np.array_equal(bits(r_g[same]), bits(r_o[same]))
+            else:
+                assert ties == 0, (sc["name"], ties)
+                assert np.array_equal(bits(r_g), bits(r_o)), sc["name"]
+            hit = i_o != ob.MISS
+            rng = np.random.RandomState(1)
+            tmax = np.where(hit & (rng.rand(len(hit)) < 0.5), r_o[:, 0], rng.uniform(0, 3, len(hit)).astype(np.float32)).astype(np.float32)
+            assert np.array_equal(p.occluded(ro, rd, tmax), hit & (r_o[:, 0] <= tmax)), sc["name"]
+            total += len(i_o)
+    assert total > 1_000_000
+
+
+def test_device_built_tree_reference_view_and_render(api, ob, scenes):
+    for sc in [scenes.fixture("cornell_box"), scenes.cubesphere(32), scenes.random_soup(3000, 4)]:
+        p = api.Scene.from_dict(sc, builder="gpu")
+        o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+        expected_nodes = p.num_nodes                       # counted by the device builder
+        nodes = p.nodes()                                  # derived from the pair layout on demand
+        assert p.num_nodes == expected_nodes == len(nodes)
+        # the derived FlatNode array is a valid reference-format tree of the same triangles: the oracle's traversal of IT
+        # finds what the oracle finds in its own tree
+        o2 = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"], nodes=nodes, box=np.array(p.info.box, np.float32))
+        ro, rd = scenes.random_rays(sc, 40000, seed=12, inside=True)
+        i1, r1 = o.intersect(ro, rd, 0)
+        i2, r2 = o2.intersect(ro, rd, 0)
+        assert np.array_equal(i1, i2) and np.array_equal(bits(r1), bits(r2)), sc["name"]
+        assert np.array_equal(np.array(p.info.box, np.float32).view(np.uint32), o.box.view(np.uint32))
+        # and the renderer on the device-built tree gives the counter-seeded oracle's image
+        _compare_counter_mode(api, ob, sc, p, o, 96, 3, 3, 2, bg=(0.2, 0.3, 0.4, 1))
+
+
+def test_device_builder_full_size_mesh1m(api, ob, scenes):
+    # BASELINE config 5's mesh: build time, primary hits and secondary rays on the device-built tree
+    import time
+    sc = scenes.cubesphere(288)
+    t0 = time.perf_counter()
+    p = api.Scene.from_dict(sc, builder="gpu")
+    wall = 1e3 * (time.perf_counter() - t0)
+    print("device kd build of %d triangles: %.1f ms (call %.1f ms incl. triangle precompute), height %d, %d refs, %d cuts"
+          % (p.num_triangles, p.info.build_ms, wall, p.height, p.info.num_leaf_refs, p.info.num_cut_nodes))
+    assert p.info.build_ms < 400.0
+    h = api.Scene.from_dict(sc)  # host-built (reference-identical) tree: same hits
+    cam, cfg = api.make_config(sc, 960, pixel_samples=1)
+    ig, rg = p.primary_hits(cam, cfg)
+    ih, rh = h.primary_hits(cam, cfg)
+    assert (ih != api.MISS_ID).sum() > 50000
+    assert np.array_equal(ig, ih) and np.array_equal(bits(rg), bits(rh))
+    ro, rd = _secondary_shaped_rays(sc, 300000, 33)
+    i1, r1 = h.intersect(ro, rd)
+    i2, r2 = p.intersect(ro, rd)
+    assert np.array_equal(i1, i2), int((i1 != i2).sum())
+    assert np.array_equal(bits(r1), bits(r2))

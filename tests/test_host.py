@@ -178,3 +178,24 @@ def test_tonemap_zero_shortcut_is_bit_identical_to_the_oracle(api, ob):
             a = api.tonemap(img, 4, exposure=exposure, gamma_enabled=gamma)
             b = ob.tonemap(img, 4, exposure=exposure, gamma_enabled=gamma)
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (gamma, exposure)
+
+
+def test_reference_shape_follows_from_the_pair_layout(api, ob, scenes, monkeypatch):
+    """a device-built scene derives the reference's FlatNode view from the sibling-pair layout on demand
+    (reference_shape_from_pairs); on a host-built tree that derivation must give back the builder's own array"""
+    monkeypatch.setenv("TRN_REDERIVE_NODES", "1")
+    for sc in [scenes.four_triangles(), scenes.unit_cube(), scenes.fixture("cornell_box"), scenes.fixture("furnace_test"),
+               scenes.random_soup(3000, 4), scenes.cubesphere(20), scenes.tiled_box(8)]:
+        o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+        p = api.Scene.from_dict(sc)
+        assert (p.num_nodes, p.height) == (o.num_nodes, o.height), sc["name"]
+        assert np.array_equal(p.nodes(), o.nodes()), sc["name"]
+
+
+def test_device_builder_needs_a_device(api, scenes):
+    if api.device_count() > 0:
+        pytest.skip("a GPU is present")
+    sc = scenes.unit_cube()
+    with pytest.raises(api.TurnerError) as e:
+        api.Scene.from_dict(sc, builder="gpu")
+    assert e.value.code == -2

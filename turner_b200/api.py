@@ -82,7 +82,7 @@ EXPORTS = [
     "trn_scene_get_nodes", "trn_intersect", "trn_primary_hits", "trn_render", "trn_render_device", "trn_render_multi",
     "trn_set_profiling", "trn_set_counting", "trn_intersect_counted", "trn_camera_setup", "trn_tonemap", "trn_write_p3", "trn_load_blend", "trn_load_soup", "trn_loaded_scene_free", "trn_scene_save_cache", "trn_scene_load_cache",
     "trn_comm_unique_id", "trn_comm_init_rank", "trn_comm_destroy", "trn_render_rank", "trn_render_async", "trn_wait",
-    "trn_occluded", "trn_measure_gather_peak",
+    "trn_occluded", "trn_measure_gather_peak", "trn_scene_create_gpu",
 ]
 
 _lib = None
@@ -118,6 +118,8 @@ def lib():
         L.trn_scene_create.argtypes = [_f32p, _f32p, _f32p, C.c_uint32, C.POINTER(C.c_void_p)]
         L.trn_scene_create_ex.argtypes = [_f32p, _f32p, _f32p, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
         L.trn_scene_create_ex.restype = C.c_int32
+        L.trn_scene_create_gpu.argtypes = [_f32p, _f32p, _f32p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(C.c_void_p)]
+        L.trn_scene_create_gpu.restype = C.c_int32
         L.trn_scene_destroy.argtypes = [C.c_void_p]
         L.trn_scene_save_cache.argtypes = [C.c_void_p, C.c_char_p]
         L.trn_scene_load_cache.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
@@ -215,13 +217,19 @@ def make_config(scene, width, max_depth=3, mc_samples=8, pixel_samples=1, integr
 class Scene:
     """KDTree(triangles_from_scene(scene)) (main.cpp:25-82,156-157): triangles + kd-tree, host + device copies"""
 
-    def __init__(self, vertices, normals, diffuse, reflective=None, reflectivity=None):
+    def __init__(self, vertices, normals, diffuse, reflective=None, reflectivity=None, builder="host", device=-1):
+        """builder: "host" = the reference's tree, node for node (trn_scene_create); "gpu" = device build (trn_scene_create_gpu)"""
         v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 9)
         n = np.ascontiguousarray(normals, np.float32).reshape(-1, 9)
         d = np.ascontiguousarray(diffuse, np.float32).reshape(-1, 4)
         assert v.shape[0] == n.shape[0] == d.shape[0]
         self.h = C.c_void_p()
-        if reflective is None and reflectivity is None:
+        if builder == "gpu":
+            m = None if reflective is None else np.ascontiguousarray(reflective, np.float32).reshape(-1, 4)
+            k = None if reflectivity is None else np.ascontiguousarray(reflectivity, np.float32).reshape(-1)
+            _check(lib().trn_scene_create_gpu(v, n, d, m.ctypes.data if m is not None else None,
+                                              k.ctypes.data if k is not None else None, v.shape[0], device, C.byref(self.h)))
+        elif reflective is None and reflectivity is None:
             _check(lib().trn_scene_create(v, n, d, v.shape[0], C.byref(self.h)))
         else:
             m = np.ascontiguousarray(reflective, np.float32).reshape(-1, 4)
@@ -232,8 +240,9 @@ class Scene:
         _check(lib().trn_scene_get_info(self.h, C.byref(self.info)))
 
     @classmethod
-    def from_dict(cls, scene):
-        return cls(scene["vertices"], scene["normals"], scene["diffuse"], scene.get("reflective"), scene.get("reflectivity"))
+    def from_dict(cls, scene, builder="host", device=-1):
+        return cls(scene["vertices"], scene["normals"], scene["diffuse"], scene.get("reflective"), scene.get("reflectivity"),
+                   builder=builder, device=device)
 
     @classmethod
     def load_cache(cls, path):
@@ -275,6 +284,7 @@ class Scene:
     def nodes(self):
         out = np.zeros(self.info.num_nodes, np.uint64)
         _check(lib().trn_scene_get_nodes(self.h, out))
+        _check(lib().trn_scene_get_info(self.h, C.byref(self.info)))  # a device-built scene has its reference view now
         return out
 
     def intersect(self, origins, dirs, device=-1):

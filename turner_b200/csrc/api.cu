@@ -6,6 +6,7 @@
 
 #include "host_util.h"
 #include "kdtree_build.h"
+#include "kdtree_build_gpu.h"
 #include "kernels.cuh"
 #include "traverse_persistent.cuh"
 #include "traverse_pooled.cuh"
@@ -200,6 +201,8 @@ struct trn_scene {
     // device layout, built once on the host
     std::vector<uint2> gpu_nodes;
     std::vector<uint32_t> leaf_refs;
+    bool reference_shape = false; // tree.nodes / gpu_nodes / leaf_refs are filled (always after a host build)
+    bool gpu_built = false;
     std::map<int, std::unique_ptr<trn::DeviceScene>> devices;
     std::mutex mu;
     // NCCL communicators of the last device set used by trn_render_multi (ncclCommInitAll costs seconds)
@@ -250,6 +253,16 @@ static void make_gpu_layout(trn_scene& sc) {
     }
 }
 
+// the reference's view of the tree (FlatNode array, leaf runs): the host builder makes it itself, a device-built scene
+// derives it from the pair layout the first time somebody asks (trn_scene_get_nodes, kdtree.cache, the counting twins)
+static void ensure_reference_shape(trn_scene* sc) {
+    std::lock_guard<std::mutex> lock(sc->mu);
+    if (sc->reference_shape) return;
+    reference_shape_from_pairs(sc->tree);
+    make_gpu_layout(*sc);
+    sc->reference_shape = true;
+}
+
 static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -271,8 +284,10 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
         if (e != cudaSuccess) return e;
         return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
     };
-    CUDA_TRY(up(&ds->d_nodes, sc->gpu_nodes.data(), sc->gpu_nodes.size() * sizeof(uint2)));
-    CUDA_TRY(up(&ds->d_refs, sc->leaf_refs.data(), sc->leaf_refs.size() * sizeof(uint32_t)));
+    if (sc->reference_shape) { // only the instrumented reference-schedule twins read these (upload_reference_shape otherwise)
+        CUDA_TRY(up(&ds->d_nodes, sc->gpu_nodes.data(), sc->gpu_nodes.size() * sizeof(uint2)));
+        CUDA_TRY(up(&ds->d_refs, sc->leaf_refs.data(), sc->leaf_refs.size() * sizeof(uint32_t)));
+    }
     CUDA_TRY(up(&ds->d_pnodes, sc->tree.pair_nodes.data(), sc->tree.pair_nodes.size() * sizeof(uint64_t)));
     CUDA_TRY(up(&ds->d_prefs, sc->tree.pair_leaf_refs.data(), sc->tree.pair_leaf_refs.size() * sizeof(uint32_t)));
     {
@@ -375,6 +390,19 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     ds->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     *out = ds.get();
     sc->devices[device] = std::move(ds);
+    return TRN_OK;
+}
+
+// the reference-shaped arrays on the device, for the instrumented reference-schedule twins of a device-built scene
+static int upload_reference_shape(trn_scene* sc, DeviceScene* ds) {
+    if (ds->d_nodes) return TRN_OK;
+    ensure_reference_shape(sc);
+    CUDA_TRY(cudaMalloc(&ds->d_nodes, std::max<size_t>(sc->gpu_nodes.size() * sizeof(uint2), 16)));
+    CUDA_TRY(cudaMemcpy(ds->d_nodes, sc->gpu_nodes.data(), sc->gpu_nodes.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&ds->d_refs, std::max<size_t>(sc->leaf_refs.size() * sizeof(uint32_t), 16)));
+    CUDA_TRY(cudaMemcpy(ds->d_refs, sc->leaf_refs.data(), sc->leaf_refs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ds->dev.nodes = static_cast<const uint2*>(ds->d_nodes);
+    ds->dev.leaf_refs = static_cast<const uint32_t*>(ds->d_refs);
     return TRN_OK;
 }
 
@@ -880,6 +908,10 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
     std::lock_guard<std::recursive_mutex> guard(ds->mu);
     CUDA_TRY(cudaSetDevice(ds->device));
     if (ds_out) *ds_out = ds;
+    if (g_counting.load() != 0) {
+        rc = upload_reference_shape(scene, ds);
+        if (rc) return rc;
+    }
     FrameParams fp = make_frame(cam, cfg);
     const int levels = cfg->integrator == TRN_RAYCASTER ? 1 : cfg->max_depth + 1;
     const uint64_t cap = choose_wave_cap(ds, static_cast<uint64_t>(fp.width) * fp.height * static_cast<uint64_t>(fp.n_local),
@@ -1022,8 +1054,8 @@ int32_t trn_scene_create(const float* verts, const float* normals, const float* 
     return trn_scene_create_ex(verts, normals, diffuse, nullptr, nullptr, n, out);
 }
 
-int32_t trn_scene_create_ex(const float* verts, const float* normals, const float* diffuse, const float* reflective,
-                            const float* reflectivity, uint32_t n, trn_scene** out) {
+static int32_t scene_create_impl(const float* verts, const float* normals, const float* diffuse, const float* reflective,
+                                 const float* reflectivity, uint32_t n, bool on_device, int32_t device, trn_scene** out) {
     if (!verts || !normals || !diffuse || !out) return fail(TRN_ERR_INVALID, "null argument");
     if (n == 0) return fail(TRN_ERR_INVALID, "scene needs at least one triangle (lib/kdtree.cpp:475)");
     if (n >= TRN_MISS_ID) return fail(TRN_ERR_LIMIT, "triangle count must be < 2^30 (lib/kdtree.cpp:476)");
@@ -1032,14 +1064,44 @@ int32_t trn_scene_create_ex(const float* verts, const float* normals, const floa
         if (!std::isfinite(verts[i])) return fail(TRN_ERR_INVALID, "non-finite vertex coordinate");
     std::unique_ptr<trn_scene> sc(new trn_scene);
     precompute_triangles(verts, normals, diffuse, n, sc->tris, reflective, reflectivity);
-    build_kdtree(sc->tris, sc->tree, static_cast<int>(env_u64("TRN_BUILD_THREADS", 0)));
+    if (on_device) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            return fail(TRN_ERR_CUDA, "no CUDA device available for the device kd-tree build (use trn_scene_create for the host build)");
+        if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+        if (device >= ndev) return fail(TRN_ERR_INVALID, "device ordinal out of range");
+        std::string err;
+        const int rc = build_kdtree_gpu(sc->tris, sc->tree, device, err);
+        if (rc) return fail(rc, err);
+        sc->gpu_built = true;
+    } else {
+        build_kdtree(sc->tris, sc->tree, static_cast<int>(env_u64("TRN_BUILD_THREADS", 0)));
+        if (env_u64("TRN_REDERIVE_NODES", 0)) { // test hook: the reference-shaped array must follow from the pair layout alone
+            sc->tree.nodes.clear();
+            reference_shape_from_pairs(sc->tree);
+        }
+        make_gpu_layout(*sc);
+        sc->reference_shape = true;
+    }
     if (sc->tree.height + 1 > static_cast<uint64_t>(kStackDepth))
         return fail(TRN_ERR_LIMIT, "kd-tree height " + std::to_string(sc->tree.height) + " exceeds the traversal stack (" +
                                        std::to_string(kStackDepth) + ")");
-    make_gpu_layout(*sc);
     *out = sc.release();
     return TRN_OK;
     TRN_GUARD_END
+}
+
+int32_t trn_scene_create_ex(const float* verts, const float* normals, const float* diffuse, const float* reflective,
+                            const float* reflectivity, uint32_t n, trn_scene** out) {
+    // TRN_BUILDER=gpu: run a whole test suite / CLI session on device-built trees without touching the callers
+    const char* b = std::getenv("TRN_BUILDER");
+    const bool on_device = b && std::strcmp(b, "gpu") == 0;
+    return scene_create_impl(verts, normals, diffuse, reflective, reflectivity, n, on_device, -1, out);
+}
+
+int32_t trn_scene_create_gpu(const float* verts, const float* normals, const float* diffuse, const float* reflective,
+                             const float* reflectivity, uint32_t n, int32_t device, trn_scene** out) {
+    return scene_create_impl(verts, normals, diffuse, reflective, reflectivity, n, true, device, out);
 }
 
 void trn_scene_destroy(trn_scene* scene) {
@@ -1053,7 +1115,7 @@ void trn_scene_destroy(trn_scene* scene) {
 int32_t trn_scene_get_info(const trn_scene* scene, trn_scene_info* info) {
     if (!scene || !info) return fail(TRN_ERR_INVALID, "null argument");
     info->num_triangles = scene->tris.count;
-    info->num_nodes = scene->tree.nodes.size();
+    info->num_nodes = scene->reference_shape ? scene->tree.nodes.size() : scene->tree.expected_nodes;
     info->kdtree_height = scene->tree.height;
     info->num_leaf_refs = scene->tree.num_leaf_refs;
     info->num_cut_nodes = scene->tree.num_cut_nodes;
@@ -1066,8 +1128,11 @@ int32_t trn_scene_get_info(const trn_scene* scene, trn_scene_info* info) {
 
 int32_t trn_scene_get_nodes(const trn_scene* scene, uint64_t* out_nodes) {
     if (!scene || !out_nodes) return fail(TRN_ERR_INVALID, "null argument");
+    TRN_GUARD_BEGIN
+    ensure_reference_shape(const_cast<trn_scene*>(scene));
     std::memcpy(out_nodes, scene->tree.nodes.data(), scene->tree.nodes.size() * sizeof(uint64_t));
     return TRN_OK;
+    TRN_GUARD_END
 }
 
 static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* origins, const float* dirs, uint64_t n,
@@ -1092,6 +1157,10 @@ static int32_t intersect_impl(trn_scene* scene, int32_t device, const float* ori
     if (rc) return rc;
     std::lock_guard<std::recursive_mutex> guard(ds->mu);
     CUDA_TRY(cudaSetDevice(ds->device));
+    if (counts3) {
+        rc = upload_reference_shape(scene, ds);
+        if (rc) return rc;
+    }
     const uint64_t chunk = 8ull << 20;
     const uint64_t cn = std::min<uint64_t>(chunk, std::max<uint64_t>(n, 1));
     DevBuf b_o, b_d, b_rst, b_h, b_ids;
@@ -1589,6 +1658,7 @@ using trn::fail;
 
 int32_t trn_scene_save_cache(const trn_scene* scene, const char* path) {
     if (!scene || !path) return trn::fail(TRN_ERR_INVALID, "null argument");
+    trn::ensure_reference_shape(const_cast<trn_scene*>(scene));
     FILE* f = std::fopen(path, "wb");
     if (!f) return trn::fail(TRN_ERR_IO, std::string("cannot write ") + path);
     CacheWriter w{f};

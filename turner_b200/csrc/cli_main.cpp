@@ -51,6 +51,8 @@ std::string usage_text() {
          "  --dump-hits=<file>                Also write primary-hit triangle ids (raw uint32).\n"
          "  --kdtree-cache=<file>             Load the triangles + kd-tree from this kdtree.cache if it exists (refused\n"
          "                                    when stale), else build them and write it [default: none].\n"
+         "  --kd-builder=<host|gpu>           Build the kd-tree on the host (the reference's tree, node for node) or on the\n"
+         "                                    GPU (binned SAH, ~20x sooner at 1 M triangles) [default: host].\n"
          "  -h --help                         Show this text.\n\n";
     if (kPathtracer) {
         u << "Pathtracer options:\n"
@@ -80,7 +82,7 @@ struct Options {
     bool verbose = false;
     long gpus = 1;
     unsigned long long seed = 1;
-    std::string dump_linear, dump_hits, kdtree_cache;
+    std::string dump_linear, dump_hits, kdtree_cache, kd_builder = "host";
     // TracerConfig defaults (config.h:106-117); the pathtracer USAGE overrides -m to 8 (pathtracer.h:24)
     long max_depth = 3;
     float max_visibility = 2;
@@ -110,7 +112,7 @@ const OptSpec kSpecs[] = {
     {nullptr, "--exposure", true, 7},    {"-v", "--verbose", false, 7},
     {nullptr, "--gpus", true, 7},        {nullptr, "--seed", true, 7},
     {nullptr, "--dump-linear", true, 7}, {nullptr, "--dump-hits", true, 7},
-    {nullptr, "--kdtree-cache", true, 7},
+    {nullptr, "--kdtree-cache", true, 7}, {nullptr, "--kd-builder", true, 7},
     {"-h", "--help", false, 7},          {"-d", "--max-depth", true, 1 | 4},
     {"-p", "--pixel-samples", true, 1},  {"-m", "--monte-carlo-samples", true, 1},
     {nullptr, "--max-visibility", true, 2}, {nullptr, "--shadow", true, 4},
@@ -140,6 +142,7 @@ void apply(Options& o, const OptSpec& s, const std::string& v) {
         else if (n == "--dump-linear") o.dump_linear = v;
         else if (n == "--dump-hits") o.dump_hits = v;
         else if (n == "--kdtree-cache") o.kdtree_cache = v;
+        else if (n == "--kd-builder") o.kd_builder = v;
         else if (n == "--max-depth") o.max_depth = std::stol(v);
         else if (n == "--pixel-samples") o.pixel_samples = std::stol(v);
         else if (n == "--monte-carlo-samples") o.mc_samples = std::stol(v);
@@ -290,6 +293,7 @@ int main(int argc, char const* argv[]) {
     require(0 <= o.shadow_intensity && o.shadow_intensity <= 1, "0 <= shadow <= 1"); // config.h:123
     require(1 <= o.width, "1 <= width");
     require(1 <= o.gpus, "1 <= gpus");
+    require(o.kd_builder == "host" || o.kd_builder == "gpu", "--kd-builder is host or gpu");
     if (o.verbose) print_config(o);
 
     std::cerr << "Loading scene..." << std::endl; // main.cpp:97
@@ -326,7 +330,10 @@ int main(int argc, char const* argv[]) {
         }
     }
     if (!from_cache) {
-        if (trn_scene_create_ex(ls.verts, ls.normals, ls.diffuse, ls.reflective, ls.reflectivity, ls.num_triangles, &scene) != TRN_OK) {
+        const int32_t crc = o.kd_builder == "gpu"
+                                ? trn_scene_create_gpu(ls.verts, ls.normals, ls.diffuse, ls.reflective, ls.reflectivity, ls.num_triangles, 0, &scene)
+                                : trn_scene_create_ex(ls.verts, ls.normals, ls.diffuse, ls.reflective, ls.reflectivity, ls.num_triangles, &scene);
+        if (crc != TRN_OK) {
             std::cerr << trn_last_error() << std::endl;
             return 2;
         }

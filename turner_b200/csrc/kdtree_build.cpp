@@ -438,6 +438,61 @@ void precompute_triangles(const float* verts, const float* normals, const float*
     }
 }
 
+void reference_shape_from_pairs(KdTree& tree) {
+    const auto& pn = tree.pair_nodes;
+    const auto& refs = tree.pair_leaf_refs;
+    auto word_x = [&](uint32_t i) { return static_cast<uint32_t>(pn[i]); };
+    auto word_y = [&](uint32_t i) { return static_cast<uint32_t>(pn[i] >> 32); };
+    auto is_void = [&](uint32_t i) { return word_y(i) == 3u; };
+    // follow empty-space cuts: an inner node with a void child is its other child (lib/kdtree.cpp:168-172)
+    auto resolve = [&](uint32_t i) {
+        for (;;) {
+            const uint32_t y = word_y(i);
+            if ((y & 3u) == 3u) return i;
+            const uint32_t pair = y >> 2;
+            if (is_void(pair)) i = pair + 1;
+            else if (is_void(pair + 1)) i = pair;
+            else return i;
+        }
+    };
+    struct Item {
+        uint32_t node, parent, level;
+    };
+    auto& nodes = tree.nodes;
+    nodes.clear();
+    tree.height = 0;
+    tree.num_leaf_refs = 0;
+    std::vector<Item> stack;
+    stack.push_back({resolve(0), kInvalid, 0});
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        if (it.level > tree.height) tree.height = it.level;
+        const uint32_t idx = static_cast<uint32_t>(nodes.size());
+        if (it.parent != kInvalid) {
+            const uint64_t p = nodes[it.parent];
+            nodes[it.parent] = (p & 0xFFFFFFFF00000000ull) | static_cast<uint32_t>((idx << 2) | (static_cast<uint32_t>(p) & 3u));
+        }
+        const uint32_t y = word_y(it.node);
+        if ((y & 3u) != 3u) {
+            const uint32_t pair = y >> 2;
+            nodes.push_back((static_cast<uint64_t>(word_x(it.node)) << 32) | static_cast<uint32_t>((kInvalid << 2) | (y & 3u)));
+            stack.push_back({resolve(pair + 1), idx, it.level + 1});
+            stack.push_back({resolve(pair), kInvalid, it.level + 1});
+        } else {
+            const uint32_t first = word_x(it.node), cnt = y >> 2;
+            tree.num_leaf_refs += cnt;
+            uint32_t i = 1;
+            for (; i < cnt; i += 2)
+                nodes.push_back((static_cast<uint64_t>(refs[first + i - 1]) << 32) | static_cast<uint32_t>((refs[first + i] << 2) | 3u));
+            if (i - 1 < cnt)
+                nodes.push_back((static_cast<uint64_t>(refs[first + i - 1]) << 32) | 0xFFFFFFFFull);
+            else
+                nodes.push_back(0); // all-zero inner node terminates the leaf run
+        }
+    }
+}
+
 void build_kdtree(const HostTriangles& tris, KdTree& out, int num_threads) {
     auto t0 = std::chrono::steady_clock::now();
     const uint32_t n = tris.count;

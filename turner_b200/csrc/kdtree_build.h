@@ -49,9 +49,15 @@ struct KdTree {
     std::vector<uint32_t> pair_leaf_refs;  // triangle ids, leaf after leaf; every run starts at a multiple of 4 (padded)
     uint64_t num_pair_refs = 0;            // references without the padding
     uint64_t num_cut_nodes = 0;
+    uint64_t expected_nodes = 0;           // device builder: size `nodes` will have once reference_shape_from_pairs() ran
 };
 
 // num_threads <= 0: hardware concurrency
 void build_kdtree(const HostTriangles& tris, KdTree& out, int num_threads = 0);
+
+// Derives the reference-shaped array `nodes` (FlatNode encoding, DFS, cut nodes dropped as lib/kdtree.cpp:168-172 drops
+// them) and `height` from the sibling-pair layout. The host builder fills both itself; the device builder
+// (kdtree_build_gpu.h) only makes the pair layout, and this runs when somebody asks for the reference's view of the tree.
+void reference_shape_from_pairs(KdTree& tree);
 
 } // namespace trn
