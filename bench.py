@@ -247,6 +247,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mesh1m", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="job", choices=["job", "pass"])
+    ap.add_argument("--kd-builder", default="gpu", choices=["gpu", "host"],
+                    help="gpu: device-built kd-tree (trn_scene_create_gpu); host: the reference's tree, node for node")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
@@ -292,7 +294,9 @@ def main():
     os.environ.setdefault("TRN_BUILD_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
 
     sc = load_scene(args.workload)
-    scene = api.Scene.from_dict(sc)
+    scene = api.Scene.from_dict(sc, builder=args.kd_builder, device=local_rank)
+    config["kd_builder"] = ("device build (binned SAH, trn_scene_create_gpu): hits equal the reference tree's, checked below"
+                            if args.kd_builder == "gpu" else "host build: the reference's tree, node for node")
     pps = w["pixel_samples"]
     cam, cfg = api.make_config(sc, w["width"], max_depth=w["max_depth"], mc_samples=w["mc_samples"], pixel_samples=pps, seed=1)
     H, W = cfg.height, cfg.width
@@ -565,17 +569,35 @@ def main():
             "fp32_frac": fp32_rate / (148 * 128 * 2 * sm_mhz / 1e3), "fp32_clock_mhz": sm_mhz,
         }
 
+    # ---- the reference-identical host tree: build time beside the device build, primary hits of the two trees compared,
+    # and the tree the CPU baseline traverses (loaded through the reference's own serialize() hook)
+    kd = {"builder": args.kd_builder, "build_ms": scene.info.build_ms, "height": int(scene.height),
+          "leaf_refs": int(scene.info.num_leaf_refs), "cut_nodes": int(scene.info.num_cut_nodes)}
+    host_scene = scene
+    if args.kd_builder == "gpu" and not (args.no_cpu_baseline and args.no_roofline):
+        host_scene = api.Scene.from_dict(sc)
+        kd["host_build_ms"] = host_scene.info.build_ms
+        kd["host_build_threads"] = int(os.environ.get("TRN_BUILD_THREADS", "0")) or (os.cpu_count() or 1)
+        c4 = api.copy_config(cfg)
+        c4.pixel_samples, c4.sample_begin, c4.sample_stride = 1, 0, 1
+        ia, ra_ = scene.primary_hits(cam, c4, device=local_rank)
+        ib, rb_ = host_scene.primary_hits(cam, c4, device=local_rank)
+        kd["primary_hits_compared"] = int(ia.size)
+        kd["primary_id_differences_vs_reference_tree"] = int((ia != ib).sum())
+        kd["primary_rst_bit_differences"] = int((ra_.view(np.uint32) != rb_.view(np.uint32)).any(-1).sum())
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        b = cpu_reference_run(args.workload, sc, scene.nodes(), np.array(scene.info.box, np.float32), budget_s=20.0)
+        b = cpu_reference_run(args.workload, sc, host_scene.nodes(), np.array(host_scene.info.box, np.float32), budget_s=20.0)
         cpu_baseline = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    scene.refresh_info()
     line = {
         "metric": "Mrays/s (incl. secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
         "rays_per_step": rays_all / args.steps, "shadow_rays_per_step_rank0": tot["shadow"] / args.steps,
-        "kd_build_ms": scene.info.build_ms, "kd_height": int(scene.height), "triangles": int(scene.num_triangles),
+        "kd_build_ms": scene.info.build_ms, "kd_height": int(scene.height), "triangles": int(scene.num_triangles), "kd": kd,
+        "time_to_image_ms": scene.info.build_ms + scene.info.upload_ms + e2e.get("ms_per_step", ms_max / args.steps),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(tot["launches"]), "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }

@@ -269,6 +269,11 @@ class Scene:
         except Exception:
             pass
 
+    def refresh_info(self):
+        """re-read trn_scene_info (upload_ms is known after the first use on a device)"""
+        _check(lib().trn_scene_get_info(self.h, C.byref(self.info)))
+        return self.info
+
     @property
     def num_triangles(self):
         return self.info.num_triangles

@@ -32,6 +32,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -41,8 +43,17 @@ namespace gpubuild {
 
 constexpr int kBins = 32;
 constexpr int kMaxLevels = 56;          // tree height bound (the traversal stack holds 64 entries)
-constexpr float kCostTraversal = 15.f;  // lib/kdtree.cpp:178
+// lib/kdtree.cpp:178 has 15: on the pooled GPU traversal an inner-node step costs more against a triangle pre-test than on
+// the CPU; 30 renders the 1M mesh 3 % faster than 15 (8: -6 %, 60: +2.5 %; profiles/README.md), the tree is as correct
+constexpr float kCostTraversal = 30.f;
 constexpr float kCostIntersection = 20.f; // lib/kdtree.cpp:179
+constexpr float kLambdaEmpty = 0.8f;    // lib/kdtree.cpp:183-188
+constexpr uint32_t kLeafMax = 3;        // lib/kdtree.cpp:133-136
+
+struct SahParams { // the reference's constants; TRN_KD_* override them for experiments (profiles/README.md)
+    float kt, ki, lambda;
+    uint32_t leaf_max;
+};
 constexpr float kFltMax = 3.402823466e+38f;
 
 #define GB_TRY(expr)                                                                                     \
@@ -157,7 +168,7 @@ __device__ inline float box_area(const float* lo, const float* hi) {
 
 // ---- select: one warp per node
 __global__ void __launch_bounds__(256) select_kernel(Level lv, uint32_t num_nodes, const uint32_t* __restrict__ hist, Decision dc, int level,
-                                                     float scene_scale) {
+                                                     float scene_scale, float touch, SahParams sah) {
     const uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31u;
     if (node >= num_nodes) return;
@@ -174,7 +185,7 @@ __global__ void __launch_bounds__(256) select_kernel(Level lv, uint32_t num_node
             bhi[c] = lv.bhi[3 * node + c];
         }
         const float area = box_area(blo, bhi);
-        if (n > 3 && level < kMaxLevels && area > 0.f) { // lib/kdtree.cpp:133-141
+        if (n > sah.leaf_max && level < kMaxLevels && area > 0.f) { // lib/kdtree.cpp:133-141
             float best = kFltMax, best_pos = 0.f;
             int best_ax = -1;
             uint32_t best_nl = 0, best_nr = 0;
@@ -182,6 +193,9 @@ __global__ void __launch_bounds__(256) select_kernel(Level lv, uint32_t num_node
                 const float tl = o2f(lv.tlo[3 * node + ax]), th = o2f(lv.thi[3 * node + ax]);
                 const float ext = th - tl;
                 if (!(ext > 0.f)) continue;
+                // a box this thin is not split along this axis any more: references within `touch` of a plane go to both
+                // children, so planes closer together than that separate nothing (and fp32 cannot resolve them from afar)
+                if (!(bhi[ax] - blo[ax] > 64.f * touch)) continue;
                 const uint32_t s = hist[size_t(node) * 6 * kBins + (2 * ax) * kBins + lane];
                 const uint32_t e = hist[size_t(node) * 6 * kBins + (2 * ax + 1) * kBins + lane];
                 uint32_t ps = s, pe = e; // inclusive scans
@@ -204,15 +218,15 @@ __global__ void __launch_bounds__(256) select_kernel(Level lv, uint32_t num_node
                     const float void_shift = 4e-6f * fmaxf(fabsf(p), scene_scale);
                     if (nl == 0u) p -= void_shift; // cut: plane into the void below the references
                     if (nr == 0u) p += void_shift;
-                    if (!(p > blo[ax] && p < bhi[ax])) continue; // the plane must split the node's box
+                    if (!(p > blo[ax] + 8.f * touch && p < bhi[ax] - 8.f * touch)) continue; // the plane must split the node's box
                     if (nl == 0u && nr == 0u) continue;
                     float llo[3] = {blo[0], blo[1], blo[2]}, lhi[3] = {bhi[0], bhi[1], bhi[2]};
                     float rlo[3] = {blo[0], blo[1], blo[2]}, rhi[3] = {bhi[0], bhi[1], bhi[2]};
                     lhi[ax] = p;
                     rlo[ax] = p;
-                    const float lam = (nl == 0u || nr == 0u) ? 0.8f : 1.f;
-                    const float cost = lam * (kCostTraversal + kCostIntersection * (box_area(llo, lhi) / area * static_cast<float>(nl) +
-                                                                                    box_area(rlo, rhi) / area * static_cast<float>(nr)));
+                    const float lam = (nl == 0u || nr == 0u) ? sah.lambda : 1.f;
+                    const float cost = lam * (sah.kt + sah.ki * (box_area(llo, lhi) / area * static_cast<float>(nl) +
+                                                                 box_area(rlo, rhi) / area * static_cast<float>(nr)));
                     if (cost < best) {
                         best = cost;
                         best_pos = p;
@@ -243,10 +257,10 @@ __global__ void __launch_bounds__(256) select_kernel(Level lv, uint32_t num_node
             best_nl = __shfl_sync(0xffffffffu, best_nl, 0);
             best_nr = __shfl_sync(0xffffffffu, best_nr, 0);
             if (best_ax >= 0) {
-                const float lam = (best_nl == 0u || best_nr == 0u) ? 0.8f : 1.f;
+                const float lam = (best_nl == 0u || best_nr == 0u) ? sah.lambda : 1.f;
                 // automatic termination, lib/kdtree.cpp:153-158; and a split that separates nothing is no split
                 const bool no_progress = best_nl >= n && best_nr >= n;
-                if (!(kCostIntersection * static_cast<float>(n) * lam < best) && !no_progress) {
+                if (!(sah.ki * static_cast<float>(n) * lam < best) && !no_progress) {
                     axis = best_ax;
                     pos = best_pos;
                 }
@@ -515,9 +529,9 @@ static inline unsigned blocks(uint64_t n, unsigned bs) { return static_cast<unsi
 
 } // namespace gpubuild
 
-int build_kdtree_gpu(const HostTriangles& tris, KdTree& out, int device, std::string& err) {
+static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::string& err, uint64_t budget,
+                      std::chrono::steady_clock::time_point t0) {
     using namespace gpubuild;
-    auto t0 = std::chrono::steady_clock::now();
     const uint32_t n = tris.count;
     GB_TRY(cudaSetDevice(device));
     // scene box exactly as the host builder / KDTree::KDTree compute it (lib/kdtree.cpp:474-490)
@@ -541,10 +555,11 @@ int build_kdtree_gpu(const HostTriangles& tris, KdTree& out, int device, std::st
     for (int c = 0; c < 6; ++c) scale = std::fmax(scale, std::fabs(box[c]));
     const float eps = 1e-6f * scale;
 
-    // capacities: references per level (duplication of a SAH kd-tree stays well below 16x), nodes per level
-    const uint64_t ref_cap = std::max<uint64_t>(uint64_t(n) * 16u, 1u << 16);
-    const uint64_t node_cap = std::max<uint64_t>(uint64_t(n) * 4u, 1u << 12);
-    const uint64_t pair_cap = std::max<uint64_t>(uint64_t(n) * 16u, 1u << 12); // nodes of the whole tree
+    // capacities: references per level (the duplication of a SAH kd-tree of a mesh stays well below 16x; overlapping
+    // soups need more: the caller retries with a larger budget), nodes per level, nodes of the whole tree
+    const uint64_t ref_cap = std::max<uint64_t>(uint64_t(n) * 16u, 1u << 18) * budget;
+    const uint64_t node_cap = std::max<uint64_t>(uint64_t(n) * 4u, 1u << 16) * budget;
+    const uint64_t pair_cap = std::max<uint64_t>(uint64_t(n) * 16u, 1u << 18) * budget;
     if (ref_cap >= (1ull << 32) || pair_cap >= (1ull << 30)) {
         err = "scene too large for the device kd builder";
         return -5;
@@ -598,6 +613,13 @@ int build_kdtree_gpu(const HostTriangles& tris, KdTree& out, int device, std::st
         GB_TRY(cudaMemcpy(pair_nodes.as<uint2>() + 1, &pad, 8, cudaMemcpyHostToDevice));
         init_refs_kernel<<<blocks(n, 256), 256>>>(d_verts.as<float>(), n, ra[0].as<float4>(), rb[0].as<float4>());
     }
+    const bool debug = std::getenv("TRN_KD_DEBUG") != nullptr;
+    auto envf = [](const char* name, float dflt) {
+        const char* v = std::getenv(name);
+        return (v && *v) ? static_cast<float>(std::atof(v)) : dflt;
+    };
+    const SahParams sah{envf("TRN_KD_KT", kCostTraversal), envf("TRN_KD_KI", kCostIntersection), envf("TRN_KD_LAMBDA", kLambdaEmpty),
+                        static_cast<uint32_t>(envf("TRN_KD_LEAF", static_cast<float>(kLeafMax)))};
     uint32_t num_nodes = 1, nrefs = n, pair_count = 2, pool_count = 0;
     uint64_t splits_total = 0;
     int cur = 0, level = 0;
@@ -606,7 +628,7 @@ int build_kdtree_gpu(const HostTriangles& tris, KdTree& out, int device, std::st
         Level lv = lm[cur].view(), nx = lm[cur ^ 1].view();
         GB_TRY(cudaMemsetAsync(hist.p, 0, size_t(num_nodes) * 6 * kBins * 4));
         if (nrefs) bin_kernel<<<blocks(nrefs, 1024), 256>>>(ra[cur].as<float4>(), rb[cur].as<float4>(), nrefs, lv, hist.as<uint32_t>());
-        select_kernel<<<blocks(uint64_t(num_nodes) * 32, 256), 256>>>(lv, num_nodes, hist.as<uint32_t>(), dc, level, scale);
+        select_kernel<<<blocks(uint64_t(num_nodes) * 32, 256), 256>>>(lv, num_nodes, hist.as<uint32_t>(), dc, level, scale, eps, sah);
         size_t tmp = scan_bytes;
         cub::DeviceScan::ExclusiveSum(scan_tmp.p, tmp, dc.is_split, dc.split_idx, static_cast<int>(num_nodes));
         tmp = scan_bytes;
@@ -616,7 +638,9 @@ int build_kdtree_gpu(const HostTriangles& tris, KdTree& out, int device, std::st
         GB_TRY(cudaMemcpy(&t, totals.p, sizeof t, cudaMemcpyDeviceToHost));
         const uint32_t num_next = 2 * t.num_split;
         if (uint64_t(pair_count) + num_next > pair_cap || uint64_t(pool_count) + t.leaf_alloc + 4 > ref_cap || num_next > node_cap) {
-            err = "device kd builder: tree exceeds its node / reference budget";
+            err = "device kd builder: tree exceeds its node / reference budget (level " + std::to_string(level) + ": " +
+                  std::to_string(num_nodes) + " nodes, " + std::to_string(t.num_split) + " splits, " + std::to_string(t.leaf_alloc) +
+                  " leaf slots, " + std::to_string(pair_count) + " pairs so far)";
             return -5;
         }
         apply_kernel<<<blocks(num_nodes, 256), 256>>>(lv, num_nodes, dc, nx, pair_nodes.as<uint2>(), pair_count, pool_count, totals.as<Totals>());
@@ -640,6 +664,9 @@ int build_kdtree_gpu(const HostTriangles& tris, KdTree& out, int device, std::st
                                                         d_verts.as<float>(), ra[cur ^ 1].as<float4>(), rb[cur ^ 1].as<float4>(), eps);
         }
         GB_TRY(cudaGetLastError());
+        if (debug)
+            std::fprintf(stderr, "[kd-gpu] level %d: nodes %u refs %u -> split %u leaf_alloc %u next_refs %u (pairs %u pool %u)\n", level,
+                         num_nodes, nrefs, t.num_split, t.leaf_alloc, next_refs, pair_count, pool_count);
         pair_count += num_next;
         pool_count += t.leaf_alloc;
         splits_total += t.num_split;
@@ -687,6 +714,16 @@ int build_kdtree_gpu(const HostTriangles& tris, KdTree& out, int device, std::st
     out.expected_nodes = splits_total - t.cut_nodes + t.leaf_ref_nodes; // its size: inner nodes that are no cuts + leaf runs
     out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return 0;
+}
+
+int build_kdtree_gpu(const HostTriangles& tris, KdTree& out, int device, std::string& err) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = 0;
+    for (uint64_t budget : {1u, 4u, 16u}) { // -5 = a level outgrew its buffers: once more with larger ones
+        rc = build_impl(tris, out, device, err, budget, t0);
+        if (rc != -5) break;
+    }
+    return rc;
 }
 
 } // namespace trn
