@@ -555,11 +555,12 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
     for (int c = 0; c < 6; ++c) scale = std::fmax(scale, std::fabs(box[c]));
     const float eps = 1e-6f * scale;
 
-    // capacities: references per level (the duplication of a SAH kd-tree of a mesh stays well below 16x; overlapping
-    // soups need more: the caller retries with a larger budget), nodes per level, nodes of the whole tree
-    const uint64_t ref_cap = std::max<uint64_t>(uint64_t(n) * 16u, 1u << 18) * budget;
-    const uint64_t node_cap = std::max<uint64_t>(uint64_t(n) * 4u, 1u << 16) * budget;
-    const uint64_t pair_cap = std::max<uint64_t>(uint64_t(n) * 16u, 1u << 18) * budget;
+    // capacities: references per level, nodes per level, nodes of the whole tree. Sized for meshes (the 1M mesh peaks at
+    // 2.1 references per triangle on a level, 0.47 nodes per triangle on a level, 4.8 nodes per triangle in total);
+    // overlapping soups need more: the caller retries with a 4x / 16x budget. Allocation is a third of the build time.
+    const uint64_t ref_cap = std::max<uint64_t>(uint64_t(n) * 6u, 1u << 18) * budget;
+    const uint64_t node_cap = std::max<uint64_t>(uint64_t(n), 1u << 16) * budget;
+    const uint64_t pair_cap = std::max<uint64_t>(uint64_t(n) * 8u, 1u << 18) * budget;
     if (ref_cap >= (1ull << 32) || pair_cap >= (1ull << 30)) {
         err = "scene too large for the device kd builder";
         return -5;
@@ -574,7 +575,8 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
         GB_TRY(rb[k].alloc(ref_cap * 16));
         GB_TRY(lm[k].alloc(node_cap));
     }
-    GB_TRY(hist.alloc(node_cap * 6 * kBins * 4));
+    uint64_t hist_nodes = std::min<uint64_t>(node_cap, std::max<uint64_t>(uint64_t(n) / 2u, 1u << 14)); // grows when a level needs more
+    GB_TRY(hist.alloc(hist_nodes * 6 * kBins * 4));
     GB_TRY(pair_nodes.alloc(pair_cap * 8));
     GB_TRY(pool_ids.alloc(ref_cap * 4));
     GB_TRY(pool_key.alloc(ref_cap * 4));
@@ -594,6 +596,7 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
                 d_leaf_off.as<uint32_t>(), d_leaf_first.as<uint32_t>()};
     GB_TRY(cudaMemset(totals.p, 0, sizeof(Totals)));
 
+    const auto t_alloc = std::chrono::steady_clock::now();
     // root
     {
         Level l0 = lm[0].view();
@@ -626,6 +629,12 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
     uint64_t height = 0;
     while (num_nodes > 0) {
         Level lv = lm[cur].view(), nx = lm[cur ^ 1].view();
+        if (num_nodes > hist_nodes) {
+            hist_nodes = std::min<uint64_t>(node_cap, std::max<uint64_t>(uint64_t(num_nodes) * 2u, hist_nodes * 2u));
+            cudaFree(hist.p);
+            hist.p = nullptr;
+            GB_TRY(hist.alloc(hist_nodes * 6 * kBins * 4));
+        }
         GB_TRY(cudaMemsetAsync(hist.p, 0, size_t(num_nodes) * 6 * kBins * 4));
         if (nrefs) bin_kernel<<<blocks(nrefs, 1024), 256>>>(ra[cur].as<float4>(), rb[cur].as<float4>(), nrefs, lv, hist.as<uint32_t>());
         select_kernel<<<blocks(uint64_t(num_nodes) * 32, 256), 256>>>(lv, num_nodes, hist.as<uint32_t>(), dc, level, scale, eps, sah);
@@ -656,7 +665,7 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
             GB_TRY(cudaMemcpy(&t, totals.p, sizeof t, cudaMemcpyDeviceToHost));
             next_refs = t.next_refs;
             if (next_refs > ref_cap) {
-                err = "device kd builder: more than 16 references per triangle on one level";
+                err = "device kd builder: a level outgrew the reference buffer";
                 return -5;
             }
             GB_TRY(cudaMemsetAsync(cursor.p, 0, size_t(num_next) * 4));
@@ -680,6 +689,7 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
             return -5;
         }
     }
+    const auto t_levels = std::chrono::steady_clock::now();
     // ids inside every leaf in ascending order (the reference's leaves hold ascending ids as well), padding last
     const uint32_t pool_total = pool_count + 4; // a 4-wide read of the last chunk stays inside
     std::vector<uint32_t> host_pool(pool_total, 0u);
@@ -713,6 +723,13 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
     out.nodes.clear(); // the reference-shaped array is derived on demand (reference_shape_from_pairs)
     out.expected_nodes = splits_total - t.cut_nodes + t.leaf_ref_nodes; // its size: inner nodes that are no cuts + leaf runs
     out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (debug) {
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        std::fprintf(stderr, "[kd-gpu] box + alloc + upload %.1f ms, %d levels %.1f ms, leaf sort + download %.1f ms, total %.1f ms\n",
+                     ms(t0, t_alloc), level, ms(t_alloc, t_levels), ms(t_levels, std::chrono::steady_clock::now()), out.build_ms);
+    }
     return 0;
 }
 
