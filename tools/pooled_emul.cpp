@@ -20,7 +20,7 @@ using namespace trn;
 
 static const float kFltMax = 3.402823466e+38f, kCellSlack = 1e-4f;
 static const uint32_t kMiss = 0x40000000u;
-static const int kPqLeaves = 64, kPqLeafMaxRefs = 4096, kPqChunkTris = 4, kPqSurv = 32 + 32 * 4;
+static const int kPqSteps = 2, kPqLeaves = 64, kPqLeafMaxRefs = 4096, kPqChunkTris = 4, kPqSurv = 32 + 32 * 4;
 
 struct Ray {
     float o[3], d[3];
@@ -337,6 +337,7 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
             for (int lane = 0; lane < 32; ++lane) {
                 if (!(can[lane] && !at_leaf[lane])) continue;
                 LaneS& l = L[lane];
+                for (int rep = 0; rep < kPqSteps && (l.ny & 3u) != 3u; ++rep) { // TRN_PQ_STEPS inner steps per iteration
                 stat[1]++;
                 const uint32_t ax = l.ny & 3u;
                 const float split = bfloat(l.nx);
@@ -356,6 +357,7 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
                 const float te = (both && go_far) ? t : l.tenter, tx = (both && !go_far) ? t : l.texit;
                 l.tenter = te;
                 l.texit = tx;
+                }
             }
         }
         // TEST / EXACT: leaves 32 at a time, their chunks of 4 references dealt out 32 per round

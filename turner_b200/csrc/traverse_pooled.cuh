@@ -58,6 +58,9 @@ struct PooledWarpSmem {
     float walk_i[3][32];     // component with one conflict-free LDS instead of holding six registers + selects
 };
 
+#ifndef TRN_PQ_STEPS
+#define TRN_PQ_STEPS 2 // inner-node steps per walk iteration (1: 1602, 2: 1669, 3: 1648 Mrays/s on the 1M mesh, profiles/README.md)
+#endif
 #ifndef TRN_PQ_TREELET
 #define TRN_PQ_TREELET 0 // node pairs of the top treelet staged in shared memory per CTA (0 = off; A/B in profiles/README.md)
 #endif
@@ -105,12 +108,17 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
     PooledCounts pc{0, 0, 0, 0, 0, 0, 0, 0};
 
     uint4 stack[kStackDepth];
-    int sp = 0;
+    // Walk state of the lane's ray without extra flags (they cost register moves in the hot loop): sp >= 0 = walking with
+    // sp stack entries, sp == -1 = the walk is over (or the lane is idle); bit 31 of a LEAF's n.y = "blocked": the leaf did
+    // not fit the queue in this cycle and continues from n in the next one (a leaf's count has 24 bits, an inner node's
+    // pair index 29: the bit is free).
+    constexpr uint32_t kBlocked = 0x80000000u;
+    int sp = -1;
     float tenter = 0, texit = 0, tmax_any = 0, last_texit = -kFltMax;
     uint2 n = make_uint2(0u, 3u);
     uint32_t best_seq = 0;
     float best_r = kFltMax; // mirrors sm.best[lane].y (kFltMax while there is no hit)
-    bool busy = false, walking = false, occluded = false, exhausted = false;
+    bool busy = false, occluded = false, exhausted = false;
     uint32_t pool_next = 0, pool_end = 0;
 
     for (;;) {
@@ -168,7 +176,6 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                         } else {
                             tenter = t0 < 0.f ? 0.f : t0;
                             texit = t1;
-                            sp = 0;
                             n = __ldg(&sc.pnodes[0]);
                             best_r = kFltMax;
                             best_seq = 0;
@@ -177,7 +184,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                             last_texit = -kFltMax;
                             occluded = false;
                             busy = true;
-                            walking = !(ANY && cell_lo(tenter) > tmax_any);
+                            sp = (ANY && cell_lo(tenter) > tmax_any) ? -1 : 0;
                             // Error bounds of the pre-filter (u = 2^-24): its plane numerator b = dp - n.o (dp = n.v0 rounded
                             // once, three FMAs) and the reference's n.(v0 - o) (lib/intersection.h:47) both lie within
                             // 11 u (3 S + |o|_1) of each other, S = largest |coordinate| of the scene; the denominators
@@ -213,13 +220,13 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
         // pop -- but that block is only issued when at least leaf_gate lanes wait at a leaf (or no lane can step): it is
         // as long as the step itself and would otherwise run for 4 of 32 lanes in nearly every iteration.
         uint32_t nleaf = 0; // leaf descriptors queued in this cycle (warp-uniform register: every lane runs the leaf block)
-        bool active = busy && walking; // cleared when the lane's leaf does not fit the queue (continued in the next cycle)
         int it = 0;
 #pragma unroll 1
         for (;;) {
-            const bool at_leaf = active && (n.y & 3u) == 3u;
+            const bool at_leaf = sp >= 0 && (n.y & (kBlocked | 3u)) == 3u;
+            const bool at_inner = sp >= 0 && (n.y & 3u) != 3u;
             const unsigned lm = __ballot_sync(kFull, at_leaf);
-            const unsigned im = __ballot_sync(kFull, active && !at_leaf);
+            const unsigned im = __ballot_sync(kFull, at_inner);
             const bool last = it >= walk_iters || im == 0u;
             if (lm != 0u && (last || __popc(lm) >= leaf_gate)) {
                 // leaf: queue it (one descriptor: reference range, owner, parameter range of the cell plus slack) and pop
@@ -245,13 +252,11 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                     }
                     if (take < cnt) {
                         n.x += take;
-                        n.y -= take << 2;
-                        active = false;
+                        n.y = (n.y - (take << 2)) | kBlocked;
                     } else {
                         last_texit = texit;
                         if (sp == 0) {
-                            walking = false;
-                            active = false;
+                            sp = -1;
                         } else {
                             const uint4 e = stack[--sp];
                             if (COUNT) pc.pop += 1;
@@ -259,43 +264,46 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                             tenter = __uint_as_float(e.z);
                             texit = __uint_as_float(e.w);
                             // front to back: nothing at or behind a cell that starts beyond the light / the best hit matters
-                            if (ANY ? cell_lo(tenter) > tmax_any : tenter > best_r) {
-                                walking = false;
-                                active = false;
-                            }
+                            if (ANY ? cell_lo(tenter) > tmax_any : tenter > best_r) sp = -1;
                         }
                     }
                 }
             }
             if (last) break;
             ++it;
-            if (active && !at_leaf) {
-                // one inner-node step, lib/kdtree.cpp:540-563 on the sibling-pair layout (see traverse_pairs<>)
-                const uint32_t ax = n.y & 3u;
-                const float split = __uint_as_float(n.x);
+            // one inner-node step, lib/kdtree.cpp:540-563 on the sibling-pair layout (see traverse_pairs<>); TRN_PQ_STEPS > 1
+            // repeats it for the lanes that are still at an inner node, halving the loop control per step
+            bool stepping = at_inner;
+#pragma unroll
+            for (int rep = 0; rep < TRN_PQ_STEPS; ++rep) {
+                if (stepping) {
+                    const uint32_t ax = n.y & 3u;
+                    const float split = __uint_as_float(n.x);
 #if TRN_PQ_TREELET > 0
-                const uint32_t pi = n.y >> 3; // pair index
-                const uint4 pair = pi < TRN_PQ_TREELET ? s_pairs[pi] : __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
+                    const uint32_t pi = n.y >> 3; // pair index
+                    const uint4 pair = pi < TRN_PQ_TREELET ? s_pairs[pi] : __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
 #else
-                const uint4 pair = __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
+                    const uint4 pair = __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
 #endif
-                if (COUNT) pc.steps += 1;
-                const float o_ax = sm.walk_o[ax][lane], i_ax = sm.walk_i[ax][lane];
-                const float t = (split - o_ax) * i_ax;
-                const bool flip = (__float_as_uint(i_ax) >> 31) != 0u;
-                const uint2 near = flip ? make_uint2(pair.z, pair.w) : make_uint2(pair.x, pair.y);
-                const uint2 far = flip ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
-                const bool near_only = texit < t;
-                const bool far_only = !near_only && (t < tenter);
-                const bool both = !near_only && !far_only;
-                const bool go_far = far_only || (both && near.y == 3u);
-                if (both && near.y != 3u && far.y != 3u) {
-                    stack[sp++] = make_uint4(far.x, far.y, __float_as_uint(t), __float_as_uint(texit));
-                    if (COUNT) pc.push += 1;
+                    if (COUNT) pc.steps += 1;
+                    const float o_ax = sm.walk_o[ax][lane], i_ax = sm.walk_i[ax][lane];
+                    const float t = (split - o_ax) * i_ax;
+                    const bool flip = (__float_as_uint(i_ax) >> 31) != 0u;
+                    const uint2 near = flip ? make_uint2(pair.z, pair.w) : make_uint2(pair.x, pair.y);
+                    const uint2 far = flip ? make_uint2(pair.x, pair.y) : make_uint2(pair.z, pair.w);
+                    const bool near_only = texit < t;
+                    const bool far_only = !near_only && (t < tenter);
+                    const bool both = !near_only && !far_only;
+                    const bool go_far = far_only || (both && near.y == 3u);
+                    if (both && near.y != 3u && far.y != 3u) {
+                        stack[sp++] = make_uint4(far.x, far.y, __float_as_uint(t), __float_as_uint(texit));
+                        if (COUNT) pc.push += 1;
+                    }
+                    n = go_far ? far : near;
+                    tenter = (both && go_far) ? t : tenter;
+                    texit = (both && !go_far) ? t : texit;
+                    if (TRN_PQ_STEPS > 1) stepping = (n.y & 3u) != 3u;
                 }
-                n = go_far ? far : near;
-                tenter = (both && go_far) ? t : tenter;
-                texit = (both && !go_far) ? t : texit;
             }
         }
         __syncwarp();
@@ -463,11 +471,14 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
         if (busy) {
             best_seq = 0;
             bool finished;
-            if (ANY) finished = occluded || !walking;
-            // (a lane whose leaf is only partly queued -- walking but not active -- waits for the rest of the leaf)
-            else finished = !walking || (active && best_r < kFltMax && (best_r <= last_texit || best_r < tenter));
+            const bool blocked = sp >= 0 && (n.y & (kBlocked | 3u)) == (kBlocked | 3u);
+            if (blocked) n.y &= ~kBlocked;
+            if (ANY) finished = occluded || sp < 0;
+            // (a lane whose leaf is only partly queued waits for the rest of the leaf)
+            else finished = sp < 0 || (!blocked && best_r < kFltMax && (best_r <= last_texit || best_r < tenter));
             if (finished) {
                 busy = false;
+                sp = -1;
                 const uint32_t idx = sm.ray_idx[lane];
                 if (ANY) {
                     if (!occluded) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx]));
