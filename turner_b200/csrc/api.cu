@@ -10,6 +10,7 @@
 #include "kernels.cuh"
 #include "traverse_persistent.cuh"
 #include "traverse_pooled.cuh"
+#include "traverse_flat.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
@@ -124,6 +125,9 @@ struct DeviceScene {
     uint32_t treelet_pairs = 0; // node pairs of the top treelet present in pnodes (<= kTreeletNodes / 2)
     bool two_pass = true; // leaf evaluation schedule of the persistent kernels (small leaves: two-pass)
     bool pooled = true;   // pooled kernel for both kinds of wave (a real tree: many leaves of moderate size)
+    bool flat = false;    // the tree is ONE leaf of <= kFlatMaxTris triangles (cornell_box): brute-force kernel, no walk
+    uint32_t flat_first = 0, flat_count = 0; // that leaf's references
+    int grid_flat[3] = {0, 0, 0};
     int grid_closest = 0, grid_shadow = 0, grid_plain = 0; // persistent grids: resident CTAs per SM x SMs
     int grid_pooled[3] = {0, 0, 0};                        // same for trace_pooled_kernel<MODE>
     unsigned long long* d_hitcount = nullptr;
@@ -352,6 +356,16 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
         // 110k-triangle mesh +6 %, 1M-triangle mesh +17 %), ties around 12k leaves and loses on trees that are a handful of
         // big leaves (furnace_test 155 leaves: -4 %; cornell_box, one 36-triangle leaf: -44 %)
         ds->pooled = leaves >= 1024 && refs_per_leaf <= 16.0;
+        if (leaves == 1 && sc->tree.num_pair_refs <= static_cast<uint64_t>(kFlatMaxTris)) {
+            for (uint64_t nd : sc->tree.pair_nodes) {
+                const uint32_t y = static_cast<uint32_t>(nd >> 32);
+                if ((y & 3u) == 3u && (y >> 2) > 0) {
+                    ds->flat = true;
+                    ds->flat_first = static_cast<uint32_t>(nd);
+                    ds->flat_count = y >> 2;
+                }
+            }
+        }
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream_b, cudaStreamNonBlocking));
@@ -380,6 +394,13 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p0, trace_pooled_kernel<0>, 128, 0));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p1, trace_pooled_kernel<1>, 128, 0));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, trace_pooled_kernel<2>, 128, 0));
+        int f0 = 0, f1 = 0, f2 = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f0, trace_flat_kernel<0>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f1, trace_flat_kernel<1>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f2, trace_flat_kernel<2>, 128, 0));
+        ds->grid_flat[0] = std::max(1, f0) * prop.multiProcessorCount;
+        ds->grid_flat[1] = std::max(1, f1) * prop.multiProcessorCount;
+        ds->grid_flat[2] = std::max(1, f2) * prop.multiProcessorCount;
         ds->grid_pooled[0] = std::max(1, p0) * prop.multiProcessorCount;
         ds->grid_pooled[1] = std::max(1, p1) * prop.multiProcessorCount;
         ds->grid_pooled[2] = std::max(1, p2) * prop.multiProcessorCount;
@@ -432,6 +453,7 @@ static inline unsigned persistent_grid(int full, uint64_t n) {
 //   2  persistent warps with lane refill, while-while quantum (traverse_persistent.cuh) -- closest-hit waves of scenes
 //      that are a few big leaves (cornell_box)
 //   0  one thread per ray (kernels.cuh) -- shadow waves of those scenes
+//   4  brute force over the single leaf of a one-leaf tree (traverse_flat.cuh) -- cornell_box, both kinds of wave
 // TRN_PERSISTENT=0|2|3 forces one mode for both kinds of wave.
 static int persistent_mode(const struct DeviceScene* ds, bool shadow);
 
@@ -455,8 +477,10 @@ static int persistent_mode(const DeviceScene* ds, bool shadow) {
     const char* v = std::getenv("TRN_PERSISTENT");
     if (v && *v) {
         const int m = std::atoi(v);
+        if (m == 4) return ds->flat ? 4 : (shadow ? 0 : 2);
         return m == 3 ? 3 : (m != 0 ? 2 : 0);
     }
+    if (ds->flat) return 4;
     if (ds->pooled) return 3;
     return shadow ? 0 : 2;
 }
@@ -465,7 +489,15 @@ static int persistent_mode(const DeviceScene* ds, bool shadow) {
 static void launch_closest(DeviceScene* ds, int mode, cudaStream_t stream, const float4* ra, const float4* rb, const float* po,
                            const float* pd, uint32_t n, uint32_t* cursor, uint4* hits, const uint32_t* order = nullptr) {
     const bool plain = po != nullptr;
-    if (mode == 3) {
+    if (mode == 4) {
+        const float4* pl = static_cast<const float4*>(ds->d_planes);
+        if (plain)
+            trace_flat_kernel<2><<<persistent_grid(ds->grid_flat[2], n), 128, 0, stream>>>(ds->dev, pl, ds->flat_first, ds->flat_count, nullptr, nullptr,
+                                                                                          nullptr, po, pd, n, nullptr, cursor, hits, nullptr);
+        else
+            trace_flat_kernel<0><<<persistent_grid(ds->grid_flat[0], n), 128, 0, stream>>>(ds->dev, pl, ds->flat_first, ds->flat_count, ra, rb, nullptr,
+                                                                                          nullptr, nullptr, n, nullptr, cursor, hits, nullptr);
+    } else if (mode == 3) {
         const int refill = static_cast<int>(env_u64("TRN_PQ_REFILL", 28)), iters = static_cast<int>(env_u64("TRN_PQ_WALK", 12));
         if (plain)
             trace_pooled_kernel<2><<<persistent_grid(ds->grid_pooled[2], n), 128, 0, stream>>>(
@@ -493,7 +525,11 @@ static void launch_closest(DeviceScene* ds, int mode, cudaStream_t stream, const
 // any-hit traversal of the shadow wave built by shade_bounce_kernel (count in counters->shadow_count, at most n_max)
 static void launch_shadow(DeviceScene* ds, int mode, cudaStream_t stream, const ShadowWave& sw, uint32_t n_max, WaveCounters* counters,
                           float4* acc) {
-    if (mode == 3) {
+    if (mode == 4) {
+        trace_flat_kernel<1><<<persistent_grid(ds->grid_flat[1], n_max), 128, 0, stream>>>(
+            ds->dev, static_cast<const float4*>(ds->d_planes), ds->flat_first, ds->flat_count, sw.a, sw.b, sw.c, nullptr, nullptr, 0,
+            &counters->shadow_count, &counters->shadow_cursor, nullptr, acc);
+    } else if (mode == 3) {
         trace_pooled_kernel<1><<<persistent_grid(ds->grid_pooled[1], n_max), 128, 0, stream>>>(
             ds->dev, static_cast<const float4*>(ds->d_planes), sw.a, sw.b, sw.c, nullptr, nullptr, 0,
             &counters->shadow_count, &counters->shadow_cursor, nullptr, acc, static_cast<int>(env_u64("TRN_PQ_REFILL", 28)),

@@ -500,6 +500,41 @@ __global__ void finish_pool_kernel(const unsigned long long* __restrict__ keys, 
     out[i] = id == 0xFFFFFFFFu ? 0u : id;
 }
 
+// ---- depth-first re-layout of the finished tree. The levels are built breadth-first (a level's pairs are contiguous);
+// a walk then jumps across the whole level array at every step. In depth-first order the children pair of a pair's first
+// inner node follows it directly (same 128-byte line), and a subtree is contiguous: L1 / L2 lines are shared along a path.
+__global__ void subtree_count_kernel(const uint2* __restrict__ nodes, uint32_t begin, uint32_t end, uint32_t* __restrict__ cnt) {
+    const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    const uint2 n = nodes[i];
+    uint32_t c = 0;
+    if ((n.y & 3u) != 3u) {
+        const uint32_t child = n.y >> 2;
+        c = 1u + cnt[child] + cnt[child + 1];
+    }
+    cnt[i] = c; // pairs in the subtree below this node
+}
+__global__ void assign_pos_kernel(const uint2* __restrict__ nodes, uint32_t begin, uint32_t end, const uint32_t* __restrict__ cnt,
+                                  uint32_t* __restrict__ pos) {
+    const uint32_t q = begin / 2u + blockIdx.x * blockDim.x + threadIdx.x; // pair index
+    if (2u * q >= end) return;
+    const uint2 a = nodes[2u * q], b = nodes[2u * q + 1];
+    const uint32_t P = pos[q];
+    if ((a.y & 3u) != 3u) pos[(a.y >> 2) / 2u] = P + 1u;
+    if ((b.y & 3u) != 3u) pos[(b.y >> 2) / 2u] = P + 1u + cnt[2u * q];
+}
+__global__ void relayout_kernel(const uint2* __restrict__ nodes, uint32_t npairs, const uint32_t* __restrict__ pos, uint2* __restrict__ out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npairs) return;
+    const uint32_t P = pos[q];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        uint2 n = nodes[2u * q + k];
+        if ((n.y & 3u) != 3u) n.y = ((2u * pos[(n.y >> 2) / 2u]) << 2) | (n.y & 3u);
+        out[2u * P + k] = n;
+    }
+}
+
 struct Buf {
     void* p = nullptr;
     ~Buf() { cudaFree(p); }
@@ -625,6 +660,7 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
                         static_cast<uint32_t>(envf("TRN_KD_LEAF", static_cast<float>(kLeafMax)))};
     uint32_t num_nodes = 1, nrefs = n, pair_count = 2, pool_count = 0;
     uint64_t splits_total = 0;
+    std::vector<uint32_t> level_begin{0u}; // first node of every level in pair_nodes (level 0 = the root pair)
     int cur = 0, level = 0;
     uint64_t height = 0;
     while (num_nodes > 0) {
@@ -676,6 +712,7 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
         if (debug)
             std::fprintf(stderr, "[kd-gpu] level %d: nodes %u refs %u -> split %u leaf_alloc %u next_refs %u (pairs %u pool %u)\n", level,
                          num_nodes, nrefs, t.num_split, t.leaf_alloc, next_refs, pair_count, pool_count);
+        if (num_next) level_begin.push_back(pair_count);
         pair_count += num_next;
         pool_count += t.leaf_alloc;
         splits_total += t.num_split;
@@ -688,6 +725,31 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
             err = "device kd builder: did not terminate";
             return -5;
         }
+    }
+    // depth-first re-layout (TRN_KD_LAYOUT=bfs keeps the level order, for A/B)
+    const char* layout_env = std::getenv("TRN_KD_LAYOUT");
+    Buf relaid;
+    uint2* final_nodes = pair_nodes.as<uint2>();
+    if (!(layout_env && std::strcmp(layout_env, "bfs") == 0) && pair_count > 2) {
+        Buf cnt, pos;
+        GB_TRY(cnt.alloc(size_t(pair_count) * 4));
+        GB_TRY(pos.alloc(size_t(pair_count / 2) * 4));
+        GB_TRY(relaid.alloc(size_t(pair_count) * 8));
+        level_begin.push_back(pair_count);
+        const int nl = static_cast<int>(level_begin.size()) - 1;
+        for (int l = nl - 1; l >= 0; --l) {
+            const uint32_t b = level_begin[l], e = level_begin[l + 1];
+            subtree_count_kernel<<<blocks(e - b, 256), 256>>>(pair_nodes.as<uint2>(), b, e, cnt.as<uint32_t>());
+        }
+        GB_TRY(cudaMemsetAsync(pos.p, 0, 4)); // the root pair stays first
+        for (int l = 0; l < nl; ++l) {
+            const uint32_t b = level_begin[l], e = level_begin[l + 1];
+            assign_pos_kernel<<<blocks((e - b) / 2, 256), 256>>>(pair_nodes.as<uint2>(), b, e, cnt.as<uint32_t>(), pos.as<uint32_t>());
+        }
+        relayout_kernel<<<blocks(pair_count / 2, 256), 256>>>(pair_nodes.as<uint2>(), pair_count / 2, pos.as<uint32_t>(), relaid.as<uint2>());
+        GB_TRY(cudaGetLastError());
+        GB_TRY(cudaDeviceSynchronize()); // cnt / pos go out of scope
+        final_nodes = relaid.as<uint2>();
     }
     const auto t_levels = std::chrono::steady_clock::now();
     // ids inside every leaf in ascending order (the reference's leaves hold ascending ids as well), padding last
@@ -713,7 +775,7 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
     GB_TRY(cudaMemcpy(&t, totals.p, sizeof t, cudaMemcpyDeviceToHost));
     out.pair_nodes.resize(pair_count);
     static_assert(sizeof(uint2) == sizeof(uint64_t), "pair node = 8 bytes");
-    GB_TRY(cudaMemcpy(out.pair_nodes.data(), pair_nodes.p, size_t(pair_count) * 8, cudaMemcpyDeviceToHost)); // little-endian: x low, y high
+    GB_TRY(cudaMemcpy(out.pair_nodes.data(), final_nodes, size_t(pair_count) * 8, cudaMemcpyDeviceToHost)); // little-endian: x low, y high
     out.pair_leaf_refs.swap(host_pool);
     for (int c = 0; c < 6; ++c) out.box[c] = box[c];
     out.height = height;
