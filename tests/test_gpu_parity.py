@@ -500,11 +500,17 @@ def test_all_scheduling_modes_bit_exact(api, ob, scenes, monkeypatch):
             rd[::17, 0] = 0
             rd[::19, 2] = 0
             i_o, r_o = o.intersect(ro, rd, 0)
-            for mode in ("0", "2", "3"):
+            # "4": the brute-force kernel of one-leaf trees (traverse_flat.cuh; it falls back to "2" / "0" on real trees)
+            for mode in ("0", "2", "3", "4"):
                 monkeypatch.setenv("TRN_PERSISTENT", mode)
                 i_g, r_g = p.intersect(ro, rd)
                 assert np.array_equal(i_g, i_o), (sc["name"], inside, mode, int((i_g != i_o).sum()))
                 assert np.array_equal(bits(r_g), bits(r_o)), (sc["name"], inside, mode)
+                if mode == "4" and sc["name"].startswith("cornell"):
+                    hit = i_o != ob.MISS
+                    tmax = np.where(hit, r_o[:, 0], np.float32(1.0)).astype(np.float32)
+                    tmax[::3] = np.nextafter(tmax[::3], np.float32(-1))
+                    assert np.array_equal(p.occluded(ro, rd, tmax), hit & (r_o[:, 0] <= tmax))
     monkeypatch.delenv("TRN_PERSISTENT")
 
 

@@ -480,7 +480,8 @@ static int persistent_mode(const DeviceScene* ds, bool shadow) {
         if (m == 4) return ds->flat ? 4 : (shadow ? 0 : 2);
         return m == 3 ? 3 : (m != 0 ? 2 : 0);
     }
-    if (ds->flat) return 4;
+    // (the brute-force kernel of one-leaf scenes is bit-exact but measured slower than mode 2 on cornell_box -- 4248 vs 4819
+    // Mrays/s, profiles/README.md -- so it only runs when asked for: TRN_PERSISTENT=4)
     if (ds->pooled) return 3;
     return shadow ? 0 : 2;
 }

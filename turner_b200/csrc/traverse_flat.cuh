@@ -20,6 +20,9 @@
 
 namespace trn {
 
+#ifndef TRN_FLAT_SCAN_BOX
+#define TRN_FLAT_SCAN_BOX 0 // 1: SCAN also tests the approximate hit point against the triangle's box (fewer survivors, 2.5x the scan cost)
+#endif
 constexpr int kFlatMaxTris = 256;  // triangles of the single leaf this kernel accepts (48 + 4 bytes of shared memory each)
 constexpr int kFlatSurv = 64;      // survivor queue: < 32 left over + one triangle's 32 lanes
 
@@ -131,7 +134,13 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const floa
                 const float denom = nx * rd.x + ny * rd.y + nz * rd.z; // intersect_ray_plane, lib/intersection.h:40-49
                 const float nom = nx * (q0.x - ro.x) + ny * (q0.y - ro.y) + nz * (q0.z - ro.z);
                 r = nom / denom;
-                if (denom != 0.f && r >= 0.f && r <= lim) {
+                bool cand = denom != 0.f && r >= 0.f && r <= lim;
+                if (cand) { // a hit point outside the triangle's (grown) box cannot pass the barycentric part (as traverse_pairs<>)
+                    const float4 blo = s_blo[slot], bhi = s_bhi[slot];
+                    const float hx = ro.x + r * rd.x, hy = ro.y + r * rd.y, hz = ro.z + r * rd.z;
+                    cand = !(hx < blo.x || hy < blo.y || hz < blo.z || hx > bhi.x || hy > bhi.y || hz > bhi.z);
+                }
+                if (cand) {
                     const float4 q2 = __ldg(rec2), q3 = __ldg(rec2 + 1);
                     const float wx = (ro.x + r * rd.x) - q0.x, wy = (ro.y + r * rd.y) - q0.y, wz = (ro.z + r * rd.z) - q0.z; // :70-71
                     const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const floa
         if (__ballot_sync(kFull, valid) != 0u) {
 #pragma unroll 1
             for (uint32_t k = 0; k < ntris; ++k) {
-                const float4 p = s_plane[k], blo = s_blo[k], bhi = s_bhi[k];
+                const float4 p = s_plane[k];
                 const float a = fmaf(p.x, dx, fmaf(p.y, dy, p.z * dz));
                 const float b = fmaf(-p.x, ox, fmaf(-p.y, oy, fmaf(-p.z, oz, p.w)));
                 const float A = fabsf(a);
@@ -181,12 +190,19 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const floa
                 // 0 <= nom/denom <= lim  ==>  A <= F  or  (B + E >= 0  and  B - E <= lim (A + F))   (traverse_pooled.cuh)
                 const float lim = ANY ? tmax_any : best_r;
                 const bool in_range = (B >= -E) & (B <= fmaf(lim, A + F, E));
+#if TRN_FLAT_SCAN_BOX
                 // approximate hit point against the triangle's grown box (kernels.cuh: tri_box is grown by 1e-4 x scene scale)
-                const float rcp = __frcp_rn(fmaxf(A - F, 1e-30f));
+                const float4 blo = s_blo[k], bhi = s_bhi[k];
+                const float rcp = __fdividef(1.f, fmaxf(A - F, 1e-30f));
                 const float rr = B * rcp;
                 const float hx = fmaf(rr, dx, ox), hy = fmaf(rr, dy, oy), hz = fmaf(rr, dz, oz);
                 const bool trust = fmaf(fabsf(rr), F, E) * rcp * dmax <= box_tol;
                 const bool inside = !trust | ((hx >= blo.x) & (hy >= blo.y) & (hz >= blo.z) & (hx <= bhi.x) & (hy <= bhi.y) & (hz <= bhi.z));
+#else
+                const bool inside = true;
+                (void)dmax;
+                (void)box_tol;
+#endif
                 const bool keep = valid & !(ANY && occluded) & ((A <= F) | (in_range & inside));
                 const unsigned bk = __ballot_sync(kFull, keep);
                 if (keep) sm.surv[ns + __popc(bk & lt_mask)] = make_uint2(k, lane);
