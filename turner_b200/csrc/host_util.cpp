@@ -5,6 +5,7 @@
 #include "host_util.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -60,12 +61,20 @@ int32_t trn_tonemap(const float* rgba_sum, uint64_t npix, int32_t pixel_samples,
         span(0, npix);
         return TRN_OK;
     }
+    // chunks of 8 Ki pixels handed out by an atomic counter: the work per pixel is very uneven (a black background pixel
+    // costs nothing), contiguous equal shares would leave most threads idle
+    constexpr uint64_t kChunk = 8192;
+    std::atomic<uint64_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const uint64_t lo = next.fetch_add(kChunk);
+            if (lo >= npix) break;
+            span(lo, std::min<uint64_t>(npix, lo + kChunk));
+        }
+    };
     std::vector<std::thread> pool;
-    const uint64_t per = (npix + nt - 1) / nt;
-    for (unsigned t = 0; t < nt; ++t) {
-        const uint64_t lo = std::min<uint64_t>(npix, t * per), hi = std::min<uint64_t>(npix, lo + per);
-        if (lo < hi) pool.emplace_back(span, lo, hi);
-    }
+    for (unsigned t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
     for (auto& th : pool) th.join();
     return TRN_OK;
 }

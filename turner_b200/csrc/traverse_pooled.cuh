@@ -61,6 +61,12 @@ struct PooledWarpSmem {
 #ifndef TRN_PQ_STEPS
 #define TRN_PQ_STEPS 2 // inner-node steps per walk iteration (1: 1602, 2: 1669, 3: 1648 Mrays/s on the 1M mesh, profiles/README.md)
 #endif
+#ifndef TRN_PQ_NODE_HINT
+#define TRN_PQ_NODE_HINT 0 // 1: node-pair loads carry L1::evict_last (A/B in profiles/README.md)
+#endif
+#ifndef TRN_PQ_TRI_HINT
+#define TRN_PQ_TRI_HINT 0 // 1: id vectors and plane records are loaded L1::evict_first
+#endif
 #ifndef TRN_PQ_TREELET
 #define TRN_PQ_TREELET 0 // node pairs of the top treelet staged in shared memory per CTA (0 = off; A/B in profiles/README.md)
 #endif
@@ -69,6 +75,23 @@ struct PooledWarpSmem {
 struct PooledCounts {
     unsigned steps, chunks, tris, exact, cold, push, pop, leaves;
 };
+
+__device__ __forceinline__ uint4 ld_node_pair(const uint4* p) {
+#if TRN_PQ_NODE_HINT == 1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+template <typename T> __device__ __forceinline__ T ld_tri(const T* p) {
+#if TRN_PQ_TRI_HINT == 1
+    return __ldcs(p);
+#else
+    return __ldg(p);
+#endif
+}
 
 // exact-zero direction component: the reference's schedule verbatim (see traverse_pairs<>)
 template <bool ANY>
@@ -281,9 +304,9 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                     const float split = __uint_as_float(n.x);
 #if TRN_PQ_TREELET > 0
                     const uint32_t pi = n.y >> 3; // pair index
-                    const uint4 pair = pi < TRN_PQ_TREELET ? s_pairs[pi] : __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
+                    const uint4 pair = pi < TRN_PQ_TREELET ? s_pairs[pi] : ld_node_pair(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
 #else
-                    const uint4 pair = __ldg(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
+                    const uint4 pair = ld_node_pair(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
 #endif
                     if (COUNT) pc.steps += 1;
                     const float o_ax = sm.walk_o[ax][lane], i_ax = sm.walk_i[ax][lane];
@@ -428,8 +451,8 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                     const float c1 = fmaf(-lo, F, -E), c2 = fmaf(hi, F, E);
                     // leaf runs start at multiples of 4 references and the array is padded (kdtree_build.cpp): one 16-byte
                     // load brings the chunk's ids; ids beyond cnt are valid triangles whose result is masked
-                    ids = __ldg(reinterpret_cast<const uint4*>(sc.prefs + first + off0));
-                    const float4 p0 = __ldg(&planes[ids.x]), p1 = __ldg(&planes[ids.y]), p2 = __ldg(&planes[ids.z]), p3 = __ldg(&planes[ids.w]);
+                    ids = ld_tri(reinterpret_cast<const uint4*>(sc.prefs + first + off0));
+                    const float4 p0 = ld_tri(&planes[ids.x]), p1 = ld_tri(&planes[ids.y]), p2 = ld_tri(&planes[ids.z]), p3 = ld_tri(&planes[ids.w]);
                     if (COUNT) {
                         pc.chunks += 1;
                         pc.tris += cnt;
