@@ -495,6 +495,22 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    # ---- the reference-identical host tree: build time beside the device build, primary hits of the two trees compared,
+    # and the tree the CPU baseline traverses (loaded through the reference's own serialize() hook)
+    kd = {"builder": args.kd_builder, "build_ms": scene.info.build_ms, "height": int(scene.height),
+          "leaf_refs": int(scene.info.num_leaf_refs), "cut_nodes": int(scene.info.num_cut_nodes)}
+    host_scene = scene
+    if args.kd_builder == "gpu" and not (args.no_cpu_baseline and args.no_roofline):
+        host_scene = api.Scene.from_dict(sc)
+        kd["host_build_ms"] = host_scene.info.build_ms
+        kd["host_build_threads"] = int(os.environ.get("TRN_BUILD_THREADS", "0")) or (os.cpu_count() or 1)
+        c4 = api.copy_config(cfg)
+        c4.pixel_samples, c4.sample_begin, c4.sample_stride = 1, 0, 1
+        ia, ra_ = scene.primary_hits(cam, c4, device=local_rank)
+        ib, rb_ = host_scene.primary_hits(cam, c4, device=local_rank)
+        kd["primary_hits_compared"] = int(ia.size)
+        kd["primary_id_differences_vs_reference_tree"] = int((ia != ib).sum())
+        kd["primary_rst_bit_differences"] = int((ra_.view(np.uint32) != rb_.view(np.uint32)).any(-1).sum())
     roofline = None
     if not args.no_roofline:
         # ---- per-kernel durations for the roofline leg: one CUDA-event pair per kernel launch on the launching stream.
@@ -510,14 +526,19 @@ def main():
         c3.sample_begin, c3.sample_stride = 0, pps
         scratch = torch.zeros(H, W, 4, device="cuda", dtype=torch.float32)
         cst = scene.render_device(cam, c3, scratch.data_ptr(), stream.cuda_stream, device=local_rank, want_stats=True)
+        # the reference-shaped counters that define B_alg are taken on the REFERENCE's tree (host build); the
+        # reference view of a device-built tree has its empty-space cuts dropped and says nothing about either program
+        rst = cst if host_scene is scene else host_scene.render_device(cam, c3, scratch.data_ptr(), stream.cuda_stream,
+                                                                     device=local_rank, want_stats=True)
         api.set_counting(False)
         torch.cuda.synchronize()
         del scratch
         q, sq = max(cst.trace_queries, 1), max(cst.shadow_rays, 1)
+        rq, rsq = max(rst.trace_queries, 1), max(rst.shadow_rays, 1)
         pooled = sum(cst.trace_pooled) > 0
         peak_hbm, peak_src = measured_peaks()
         peaks = gather_peaks(api, local_rank)
-        b_alg = alg_bytes(cst.trace_inner, cst.trace_leaf_nodes, cst.trace_tri_tests, cst.trace_queries) / q
+        b_alg = alg_bytes(rst.trace_inner, rst.trace_leaf_nodes, rst.trace_tri_tests, rst.trace_queries) / rq
         b_req = requested_bytes(cst.trace_pooled, cst.trace_queries) / q if pooled else None
         ms_trace = max(pst.ms_trace, 1e-9)
         # the bytes the dominant kernel REQUESTS per second (all of them pass the L1 tag/data pipe as divergent 16-byte
@@ -538,7 +559,7 @@ def main():
             except Exception:
                 traffic = None
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        fp32_rate = 37.0 * (cst.trace_tri_tests / q) * pst.trace_queries / ms_trace / 1e6
+        fp32_rate = 37.0 * (rst.trace_tri_tests / rq) * pst.trace_queries / ms_trace / 1e6
         roofline = {
             "bound": bound, "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "how": unit_note,
@@ -553,7 +574,8 @@ def main():
                                "peak": peak_hbm, "peak_source": peak_src,
                                "frac": b_alg * pst.trace_queries / ms_trace / 1e6 / peak_hbm},
             "ncu": ncu_fig,
-            "per_query": {"inner": cst.trace_inner / q, "leaf_nodes": cst.trace_leaf_nodes / q, "tri_tests": cst.trace_tri_tests / q},
+            "per_query": {"inner": rst.trace_inner / rq, "leaf_nodes": rst.trace_leaf_nodes / rq, "tri_tests": rst.trace_tri_tests / rq,
+                          "note": "reference-shaped early-exit schedule on the reference's tree: the n_* of B_alg"},
             "per_query_actual": {"inner": cst.trace_actual_inner / q, "leaf_nodes": cst.trace_actual_leaf_nodes / q,
                                  "tri_tests": cst.trace_actual_tri_tests / q,
                                  "note": "visits of the per-ray schedule on the device layout (empty-space cuts kept)"},
@@ -562,7 +584,7 @@ def main():
             "profiled_ms_per_step": pst.ms_render / prof_steps,
             "kernel_ms": {k: getattr(pst, k) for k in ("ms_trace", "ms_shadow", "ms_shade", "ms_other")},
             "shadow_kernel": {
-                "alg_bytes_per_query": alg_bytes(cst.shadow_inner, cst.shadow_leaf_nodes, cst.shadow_tri_tests, cst.shadow_rays) / sq,
+                "alg_bytes_per_query": alg_bytes(rst.shadow_inner, rst.shadow_leaf_nodes, rst.shadow_tri_tests, rst.shadow_rays) / rsq,
                 "requested_bytes_per_query": (requested_bytes(cst.shadow_pooled, cst.shadow_rays) / sq) if pooled else None,
                 "achieved_requested": (requested_bytes(cst.shadow_pooled, cst.shadow_rays) / sq * pst.shadow_rays
                                        / max(pst.ms_shadow, 1e-9) / 1e6) if pooled else None},
@@ -573,22 +595,6 @@ def main():
             "fp32_frac": fp32_rate / (148 * 128 * 2 * sm_mhz / 1e3), "fp32_clock_mhz": sm_mhz,
         }
 
-    # ---- the reference-identical host tree: build time beside the device build, primary hits of the two trees compared,
-    # and the tree the CPU baseline traverses (loaded through the reference's own serialize() hook)
-    kd = {"builder": args.kd_builder, "build_ms": scene.info.build_ms, "height": int(scene.height),
-          "leaf_refs": int(scene.info.num_leaf_refs), "cut_nodes": int(scene.info.num_cut_nodes)}
-    host_scene = scene
-    if args.kd_builder == "gpu" and not (args.no_cpu_baseline and args.no_roofline):
-        host_scene = api.Scene.from_dict(sc)
-        kd["host_build_ms"] = host_scene.info.build_ms
-        kd["host_build_threads"] = int(os.environ.get("TRN_BUILD_THREADS", "0")) or (os.cpu_count() or 1)
-        c4 = api.copy_config(cfg)
-        c4.pixel_samples, c4.sample_begin, c4.sample_stride = 1, 0, 1
-        ia, ra_ = scene.primary_hits(cam, c4, device=local_rank)
-        ib, rb_ = host_scene.primary_hits(cam, c4, device=local_rank)
-        kd["primary_hits_compared"] = int(ia.size)
-        kd["primary_id_differences_vs_reference_tree"] = int((ia != ib).sum())
-        kd["primary_rst_bit_differences"] = int((ra_.view(np.uint32) != rb_.view(np.uint32)).any(-1).sum())
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         b = cpu_reference_run(args.workload, sc, host_scene.nodes(), np.array(host_scene.info.box, np.float32), budget_s=20.0)

@@ -535,10 +535,38 @@ __global__ void relayout_kernel(const uint2* __restrict__ nodes, uint32_t npairs
     }
 }
 
+// One device allocation for the whole build: ~35 separate cudaMalloc / cudaFree pairs cost more than the build's kernels
+// (and their cost varies with the state of the process). Buffers are carved from the arena; one that does not fit any more
+// (a retry with a larger budget estimates generously, so this is rare) falls back to its own allocation.
+struct Arena {
+    char* base = nullptr;
+    size_t off = 0, cap = 0;
+    ~Arena() { cudaFree(base); }
+    cudaError_t reserve(size_t bytes) {
+        cap = bytes;
+        return cudaMalloc(reinterpret_cast<void**>(&base), bytes);
+    }
+    void* take(size_t bytes) {
+        const size_t at = (off + 255) & ~size_t(255);
+        if (!base || at + bytes > cap) return nullptr;
+        off = at + bytes;
+        return base + at;
+    }
+};
+static thread_local Arena* t_arena = nullptr;
+
 struct Buf {
     void* p = nullptr;
-    ~Buf() { cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    bool owned = false;
+    ~Buf() {
+        if (owned) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        if (t_arena && (p = t_arena->take(bytes)) != nullptr) return cudaSuccess;
+        owned = true;
+        return cudaMalloc(&p, bytes);
+    }
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 
@@ -600,6 +628,19 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
         err = "scene too large for the device kd builder";
         return -5;
     }
+    Arena arena;
+    {
+        const size_t total = size_t(n) * 36 + 4 * ref_cap * 16 + 2 * node_cap * 60 + node_cap * 6 * kBins * 4 + pair_cap * 8 + 2 * ref_cap * 4 +
+                             node_cap * 4 * 8 + pair_cap * 14 + ref_cap * 28 + (size_t(8) << 20);
+        if (arena.reserve(total) != cudaSuccess) { // not enough memory in one piece: separate allocations may still fit
+            cudaGetLastError();
+            arena.base = nullptr;
+        }
+    }
+    struct ArenaScope {
+        explicit ArenaScope(Arena* a) { t_arena = a; }
+        ~ArenaScope() { t_arena = nullptr; }
+    } arena_scope(&arena);
     Buf d_verts, ra[2], rb[2], hist, pair_nodes, pool_ids, pool_key, cursor, totals, scan_tmp, keys, keys_alt, pool_out;
     Buf d_axis, d_pos, d_is_split, d_split_idx, d_leaf_alloc, d_leaf_off, d_leaf_first;
     LevelMem lm[2];
@@ -610,8 +651,7 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
         GB_TRY(rb[k].alloc(ref_cap * 16));
         GB_TRY(lm[k].alloc(node_cap));
     }
-    uint64_t hist_nodes = std::min<uint64_t>(node_cap, std::max<uint64_t>(uint64_t(n) / 2u, 1u << 14)); // grows when a level needs more
-    GB_TRY(hist.alloc(hist_nodes * 6 * kBins * 4));
+    GB_TRY(hist.alloc(node_cap * 6 * kBins * 4));
     GB_TRY(pair_nodes.alloc(pair_cap * 8));
     GB_TRY(pool_ids.alloc(ref_cap * 4));
     GB_TRY(pool_key.alloc(ref_cap * 4));
@@ -665,12 +705,6 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
     uint64_t height = 0;
     while (num_nodes > 0) {
         Level lv = lm[cur].view(), nx = lm[cur ^ 1].view();
-        if (num_nodes > hist_nodes) {
-            hist_nodes = std::min<uint64_t>(node_cap, std::max<uint64_t>(uint64_t(num_nodes) * 2u, hist_nodes * 2u));
-            cudaFree(hist.p);
-            hist.p = nullptr;
-            GB_TRY(hist.alloc(hist_nodes * 6 * kBins * 4));
-        }
         GB_TRY(cudaMemsetAsync(hist.p, 0, size_t(num_nodes) * 6 * kBins * 4));
         if (nrefs) bin_kernel<<<blocks(nrefs, 1024), 256>>>(ra[cur].as<float4>(), rb[cur].as<float4>(), nrefs, lv, hist.as<uint32_t>());
         select_kernel<<<blocks(uint64_t(num_nodes) * 32, 256), 256>>>(lv, num_nodes, hist.as<uint32_t>(), dc, level, scale, eps, sah);
