@@ -239,7 +239,21 @@ def gather_peaks(api, device):
     return out
 
 
+def emit(line):
+    """the ONE JSON line of the driver's contract, on the process's real stdout"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner, loader chatter) goes to
+    # stderr -- file descriptor 1 is pointed at stderr for the run, the line is written to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -280,12 +294,9 @@ def main():
                 "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": base["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
-    # stdout carries exactly one JSON line: NCCL's version / debug banner (torch's and the library's communicator share
-    # one libnccl) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from turner_b200 import api, dist as tdist
@@ -612,7 +623,7 @@ def main():
         "cpu_baseline": cpu_baseline,
     }
     line.update(extra)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
