@@ -819,6 +819,36 @@ static int build_impl(const HostTriangles& tris, KdTree& out, int device, std::s
     out.nodes.clear(); // the reference-shaped array is derived on demand (reference_shape_from_pairs)
     out.expected_nodes = splits_total - t.cut_nodes + t.leaf_ref_nodes; // its size: inner nodes that are no cuts + leaf runs
     out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (debug) { // chains of empty-space cuts: how many cut nodes sit directly below another cut
+        const auto& pn = out.pair_nodes;
+        auto y_of = [&](uint32_t i) { return static_cast<uint32_t>(pn[i] >> 32); };
+        auto is_cut = [&](uint32_t i) {
+            const uint32_t y = y_of(i);
+            if ((y & 3u) == 3u) return false;
+            const uint32_t c = y >> 2;
+            return (y_of(c) == 3u) != (y_of(c + 1) == 3u);
+        };
+        uint64_t hist[8] = {0};
+        std::vector<uint8_t> below_cut(pn.size(), 0);
+        for (uint32_t i = 0; i < pn.size(); ++i)
+            if (is_cut(i)) {
+                const uint32_t c = y_of(i) >> 2;
+                below_cut[y_of(c) == 3u ? c + 1 : c] = 1;
+            }
+        for (uint32_t i = 0; i < pn.size(); ++i)
+            if (is_cut(i) && !below_cut[i]) { // head of a chain
+                uint32_t len = 0, j = i;
+                while (is_cut(j)) {
+                    ++len;
+                    const uint32_t c = y_of(j) >> 2;
+                    j = y_of(c) == 3u ? c + 1 : c;
+                }
+                hist[std::min<uint32_t>(len, 7)]++;
+            }
+        std::fprintf(stderr, "[kd-gpu] cut chains by length 1..7+: %llu %llu %llu %llu %llu %llu %llu\n", (unsigned long long)hist[1],
+                     (unsigned long long)hist[2], (unsigned long long)hist[3], (unsigned long long)hist[4], (unsigned long long)hist[5],
+                     (unsigned long long)hist[6], (unsigned long long)hist[7]);
+    }
     if (debug) {
         auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
             return std::chrono::duration<double, std::milli>(b - a).count();

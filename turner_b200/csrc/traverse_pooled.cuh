@@ -308,7 +308,10 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
 #else
                     const uint4 pair = ld_node_pair(reinterpret_cast<const uint4*>(sc.pnodes + (n.y >> 2)));
 #endif
-                    if (COUNT) pc.steps += 1;
+                    if (COUNT) {
+                        pc.steps += 1;
+                        if ((pair.y == 3u) != (pair.w == 3u)) pc.leaves += 1u << 16; // cut steps ride in the high half of `leaves`
+                    }
                     const float o_ax = sm.walk_o[ax][lane], i_ax = sm.walk_i[ax][lane];
                     const float t = (split - o_ax) * i_ax;
                     const bool flip = (__float_as_uint(i_ax) >> 31) != 0u;
