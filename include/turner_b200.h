@@ -198,7 +198,8 @@ int32_t trn_render_rank(trn_scene* scene, trn_comm* comm, const trn_camera* cam,
 
 /* ---- asynchronous frames: trn_render_async returns at once; trn_wait blocks until out_rgba_sum (host, ideally
  * pinned) holds the frame, fills stats and frees the job. Frames of one scene+device render one after the other, but the
- * device->host copy of frame k runs next to the render of frame k+1 (two accumulation buffers, a copy stream). */
+ * device->host copy of frame k runs next to the render of frame k+1 (two accumulation buffers, a copy stream). Every job
+ * must be waited for (trn_wait releases it) before its scene is destroyed. */
 typedef struct trn_job trn_job;
 int32_t trn_render_async(trn_scene* scene, int32_t device, const trn_camera* cam, const trn_render_config* cfg,
                          float* out_rgba_sum, trn_job** job);

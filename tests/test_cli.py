@@ -159,3 +159,26 @@ def test_render_from_kdtree_cache_is_identical(api, soup, tmp_path):
     c = run(RC, soup, "-w", "64")
     assert a.returncode == b.returncode == c.returncode == 0, a.stderr
     assert a.stdout == b.stdout == c.stdout
+
+
+@pytest.mark.gpu
+def test_device_built_tree_and_multi_gpu_flags(api, soup, tmp_path):
+    # --kd-builder=gpu: same primary hits, byte-identical raycaster image (one sample per pixel: no summation order involved);
+    # --gpus 2 (where two are present): the sample split + ncclReduce of trn_render_multi gives the single-GPU image
+    a = run(RC, soup, "-w", "96")
+    b = run(RC, soup, "-w", "96", "--kd-builder=gpu")
+    assert a.returncode == b.returncode == 0, b.stderr
+    assert a.stdout == b.stdout
+    assert "Kd-Tree Height : 0" in a.stderr and "Kd-Tree Height : " in b.stderr
+    ha, hb = tmp_path / "a.u32", tmp_path / "b.u32"
+    la, lb = tmp_path / "a.f32", tmp_path / "b.f32"
+    p1 = run(PT, soup, "-w", "48", "-d", "3", "-m", "2", "-p", "4", "--dump-hits", str(ha), "--dump-linear", str(la))
+    p2 = run(PT, soup, "-w", "48", "-d", "3", "-m", "2", "-p", "4", "--kd-builder", "gpu", "--dump-hits", str(hb), "--dump-linear", str(lb))
+    assert p1.returncode == p2.returncode == 0, p2.stderr
+    assert np.array_equal(np.fromfile(ha, np.uint32), np.fromfile(hb, np.uint32))
+    assert np.allclose(np.fromfile(la, np.float32), np.fromfile(lb, np.float32), rtol=2e-4, atol=2e-4)
+    assert run(PT, soup, "--kd-builder", "fpga").returncode == 2
+    if api.device_count() >= 2:
+        p3 = run(PT, soup, "-w", "48", "-d", "3", "-m", "2", "-p", "4", "--gpus", "2", "--dump-linear", str(lb))
+        assert p3.returncode == 0, p3.stderr
+        assert np.allclose(np.fromfile(la, np.float32), np.fromfile(lb, np.float32), rtol=2e-4, atol=2e-4)
