@@ -338,10 +338,13 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     ds->dev.shade = static_cast<const float4*>(ds->d_shade);
     ds->dev.mirror = static_cast<const float4*>(ds->d_mirror);
     ds->dev.treelet_pairs = static_cast<uint32_t>(std::min<size_t>(sc->tree.pair_nodes.size(), KdTree::kTreeletNodes) / 2);
+    float extent = 0.f;
     for (int c = 0; c < 3; ++c) {
         ds->dev.lo[c] = sc->tree.box[c];
         ds->dev.hi[c] = sc->tree.box[3 + c];
+        extent = std::max(extent, sc->tree.box[3 + c] - sc->tree.box[c]);
     }
+    ds->dev.verbatim = extent < 0.1f ? 1u : 0u; // see DevScene::verbatim
     {
         // average triangles per non-empty leaf decides the leaf schedule (a one-leaf scene like cornell_box: one pass)
         uint64_t leaves = 0;
@@ -482,6 +485,7 @@ static int persistent_mode(const DeviceScene* ds, bool shadow) {
     }
     // (the brute-force kernel of one-leaf scenes is bit-exact but measured slower than mode 2 on cornell_box -- 4248 vs 4819
     // Mrays/s, profiles/README.md -- so it only runs when asked for: TRN_PERSISTENT=4)
+    if (ds->dev.verbatim) return 0; // every ray takes the reference's schedule: the one-thread-per-ray kernels do exactly that
     if (ds->pooled) return 3;
     return shadow ? 0 : 2;
 }

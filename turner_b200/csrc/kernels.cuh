@@ -44,6 +44,12 @@ struct DevScene {
     const uint2* pnodes;
     const uint32_t* prefs;
     uint32_t treelet_pairs; // node pairs of the breadth-first top of pnodes (<= KdTree::kTreeletNodes / 2)
+    // 1: every ray takes the reference's schedule verbatim (negative tenter, solid side of every cut, no early exit, no
+    // per-cell hit range). Set for scenes smaller than 0.1 units: the reference's builder clips with an ABSOLUTE thickness
+    // (EPS = 1e-5, lib/clipping.h:135-187, lib/types.h:13), which at that size is no longer small against the relative 1e-4
+    // slack the shortcuts rely on -- its tree then holds triangles in cells they do not overlap and misses them in cells they
+    // do, and what the reference finds depends on every cell it visits (tools/diag_tiny.py: differences appear below ~0.02).
+    uint32_t verbatim;
 };
 
 // ray wave, SoA of float4 (fully coalesced 16-byte lanes)
@@ -248,7 +254,7 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
     const float fdy = dy == 0.f ? kEpsDir : dy;
     const float fdz = dz == 0.f ? kEpsDir : dz;
     const float ix = 1 / fdx, iy = 1 / fdy, iz = 1 / fdz;
-    const bool axis_parallel = dx == 0.f || dy == 0.f || dz == 0.f;
+    const bool axis_parallel = dx == 0.f || dy == 0.f || dz == 0.f || sc.verbatim != 0u;
 
     float tx1 = (sc.lo[0] - ox) * ix, tx2 = (sc.hi[0] - ox) * ix;
     float tenter = fminf(tx1, tx2), texit = fmaxf(tx1, tx2);
@@ -264,7 +270,7 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
     out.s = 0.f;
     out.t = 0.f;
     if (texit < tenter) return false;
-    // Rays with an exact-zero direction component are traversed with the "fixed" direction of lib/kdtree.cpp:503-511 but
+    // Rays with an exact-zero direction component (and every ray of a `verbatim` scene) are traversed with the "fixed" direction of lib/kdtree.cpp:503-511 but
     // tested with the real one: their interval is not the real ray's, and what the reference finds depends on every cell
     // it happens to visit. They take the reference's schedule verbatim: negative tenter, solid side of every cut, no
     // early exit, no per-cell hit range.

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128, TRN_WW_MINBLOCKS) trace_persistent_ww_ker
                         if (ANY) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx]));
                         else __stcs(&hits[idx], make_uint4(kMiss, __float_as_uint(kFltMax), 0u, 0u));
                     } else {
-                        axis_parallel = dx == 0.f || dy == 0.f || dz == 0.f; // reference schedule verbatim, see traverse_pairs<>
+                        axis_parallel = dx == 0.f || dy == 0.f || dz == 0.f || sc.verbatim != 0u; // reference schedule verbatim, see traverse_pairs<>
                         tenter = (t0 < 0.f && !axis_parallel) ? 0.f : t0;
                         texit = t1;
                         sp = 0;

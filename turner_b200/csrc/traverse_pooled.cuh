@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                         ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
                         if (ANY) tmax_any = b.z;
                     }
-                    const bool axis_parallel = dx == 0.f || dy == 0.f || dz == 0.f;
+                    const bool axis_parallel = dx == 0.f || dy == 0.f || dz == 0.f || sc.verbatim != 0u;
                     bool done = false, hit = false;
                     HitRec h;
                     h.id = kMiss; h.r = kFltMax; h.s = 0.f; h.t = 0.f;
