@@ -167,7 +167,7 @@ def requested_bytes(pc, queries):
     """bytes the pooled schedule itself requests through L1 (trn_stats.trace_pooled, include/turner_b200.h): 16 per walk
     step (node pair), 16 + 4*16 per chunk (id vector + four plane records), 32 per exact test (+32 with the cold record),
     16 per stack push / pop (local memory), 32 ray in + 16 hit out per query"""
-    steps, chunks, tris, exact, cold, push, pop, leaves = [int(x) for x in pc]
+    steps, chunks, tris, exact, cold, push, pop = [int(x) for x in list(pc)[:7]]
     return 16 * steps + 80 * chunks + 32 * exact + 32 * cold + 16 * (push + pop) + 48 * queries
 
 
@@ -577,7 +577,7 @@ def main():
             "peaks_measured": peaks,
             "requested_bytes_per_query": b_req,
             "requested_per_query": ({k: v / q for k, v in zip(("walk_steps", "chunks", "tri_pretests", "exact_tests", "cold_records",
-                                                               "stack_pushes", "stack_pops", "leaves"), cst.trace_pooled)} if pooled else None),
+                                                               "stack_pushes", "stack_pops", "leaves", "walk_steps_at_cuts"), list(cst.trace_pooled)[:9])} if pooled else None),
             "l2_gather_frac": (achieved / peaks["l2_gbs"]) if (pooled and peaks.get("l2_gbs")) else None,
             # secondary, SURVEY 8(d)'s definition: algorithmic bytes of the reference-shaped schedule against the HBM copy
             # peak. The scene is L2-resident, so this is a normalised work rate, not a DRAM utilisation (it can exceed 1).

@@ -14,5 +14,5 @@ api.set_counting(True)
 st = scene.render_device(cam, cfg, acc.data_ptr(), 0, device=0)
 api.set_counting(False)
 tp = list(st.trace_pooled); sp = list(st.shadow_pooled)
-print("closest: queries", st.trace_queries, "steps/q %.2f cut steps/q %.2f leaves/q %.2f" % (tp[0]/st.trace_queries, (tp[7] >> 16)/st.trace_queries, (tp[7] & 0xffff)/st.trace_queries))
+print("closest: queries", st.trace_queries, "steps/q %.2f cut steps/q %.2f leaves/q %.2f" % (tp[0]/st.trace_queries, tp[8]/st.trace_queries, tp[7]/st.trace_queries))
 print("raw", tp, sp)

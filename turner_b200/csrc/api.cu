@@ -40,7 +40,7 @@
 
 namespace trn {
 
-constexpr int kVisitSlots = 28; // 12 of the per-ray twins (reference-shaped + device layout) + 2 x 8 PooledCounts
+constexpr int kVisitSlots = 32; // 12 of the per-ray twins (reference-shaped + device layout) + 2 x 10 PooledCounts
 thread_local std::string g_last_error;
 static std::atomic<int> g_profiling{0};
 static std::atomic<int> g_counting{0};
@@ -836,7 +836,7 @@ struct Renderer {
                             ds->dev, static_cast<const float4*>(ds->d_planes), sw.a, sw.b, sw.c, nullptr, nullptr, 0,
                             &ds->d_counters[cs].shadow_count, &ds->d_counters[cs].shadow_cursor, nullptr, acc,
                             static_cast<int>(env_u64("TRN_PQ_REFILL", 28)), static_cast<int>(env_u64("TRN_PQ_WALK", 12)),
-                            pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 10)), ds->d_visits + 20);
+                            pool_chunk_for(ds, n), static_cast<int>(env_u64("TRN_PQ_GATE", 10)), ds->d_visits + 22);
                     timer.end();
                 } else if (overlap) {
                     CUDA_TRY(cudaEventRecord(ds->ev_shaded, stream));
@@ -993,9 +993,9 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
         if (r.counting) {
             unsigned long long v[kVisitSlots];
             cudaMemcpy(v, ds->d_visits, sizeof v, cudaMemcpyDeviceToHost);
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 10; ++k) {
                 stats->trace_pooled[k] = v[12 + k];
-                stats->shadow_pooled[k] = v[20 + k];
+                stats->shadow_pooled[k] = v[22 + k];
             }
             stats->trace_inner = v[0]; stats->trace_leaf_nodes = v[1]; stats->trace_tri_tests = v[2];
             stats->shadow_inner = v[3]; stats->shadow_leaf_nodes = v[4]; stats->shadow_tri_tests = v[5];

@@ -73,8 +73,9 @@ struct PooledWarpSmem {
 
 // visit counts of the instrumented instantiation (COUNT): what the production schedule really requests from memory
 struct PooledCounts {
-    unsigned steps, chunks, tris, exact, cold, push, pop, leaves;
+    unsigned steps, chunks, tris, exact, cold, push, pop, leaves, cut_steps;
 };
+constexpr int kPooledCounters = 10; // slots per kernel mode in the visit array (9 used)
 
 __device__ __forceinline__ uint4 ld_node_pair(const uint4* p) {
 #if TRN_PQ_NODE_HINT == 1
@@ -104,7 +105,7 @@ __device__ __noinline__ bool trace_axis_parallel(const DevScene& sc, float ox, f
 // MODE 1: any-hit shadow rays from a ShadowWave (a,b,c); unoccluded -> acc[pixel] += c
 // MODE 2: closest hit, rays from plain (o,d) float arrays; result -> hits[idx]
 // COUNT: also tally what the schedule requests (walk steps, chunks, triangle pre-tests, exact tests, cold-record reads,
-//        stack pushes / pops, leaves) into visits[0..8) -- the roofline leg of bench.py and the counter parity test only
+//        stack pushes / pops, leaves, steps at empty-space cuts) into visits[0..9) -- the roofline leg of bench.py and the counter parity test only
 template <int MODE, bool COUNT = false>
 __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
     DevScene sc, const float4* __restrict__ planes, const float4* __restrict__ ra, const float4* __restrict__ rb,
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
     float scale = 0.f; // largest |coordinate| of the scene box
 #pragma unroll
     for (int c = 0; c < 3; ++c) scale = fmaxf(scale, fmaxf(fabsf(sc.lo[c]), fabsf(sc.hi[c])));
-    PooledCounts pc{0, 0, 0, 0, 0, 0, 0, 0};
+    PooledCounts pc{0, 0, 0, 0, 0, 0, 0, 0, 0};
 
     uint4 stack[kStackDepth];
     // Walk state of the lane's ray without extra flags (they cost register moves in the hot loop): sp >= 0 = walking with
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
 #endif
                     if (COUNT) {
                         pc.steps += 1;
-                        if ((pair.y == 3u) != (pair.w == 3u)) pc.leaves += 1u << 16; // cut steps ride in the high half of `leaves`
+                        if ((pair.y == 3u) != (pair.w == 3u)) pc.cut_steps += 1; // the node is an empty-space cut
                     }
                     const float o_ax = sm.walk_o[ax][lane], i_ax = sm.walk_i[ax][lane];
                     const float t = (split - o_ax) * i_ax;
@@ -516,9 +517,9 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
         __syncwarp();
     }
     if (COUNT) {
-        unsigned v[8] = {pc.steps, pc.chunks, pc.tris, pc.exact, pc.cold, pc.push, pc.pop, pc.leaves};
+        unsigned v[9] = {pc.steps, pc.chunks, pc.tris, pc.exact, pc.cold, pc.push, pc.pop, pc.leaves, pc.cut_steps};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 9; ++k) {
             unsigned x = v[k];
             for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(kFull, x, off);
             if (lane == 0 && x) atomicAdd(visits + k, static_cast<unsigned long long>(x));
