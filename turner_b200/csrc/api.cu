@@ -127,6 +127,7 @@ struct DeviceScene {
     bool pooled = true;   // pooled kernel for both kinds of wave (a real tree: many leaves of moderate size)
     bool flat = false;    // the tree is ONE leaf of <= kFlatMaxTris triangles (cornell_box): brute-force kernel, no walk
     uint32_t flat_first = 0, flat_count = 0; // that leaf's references
+    FlatParams flat_params{};                // its pre-filter records (plane + grown box, visiting order): kernel parameters
     int grid_flat[3] = {0, 0, 0};
     int grid_closest = 0, grid_shadow = 0, grid_plain = 0; // persistent grids: resident CTAs per SM x SMs
     int grid_pooled[3] = {0, 0, 0};                        // same for trace_pooled_kernel<MODE>
@@ -294,6 +295,7 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     }
     CUDA_TRY(up(&ds->d_pnodes, sc->tree.pair_nodes.data(), sc->tree.pair_nodes.size() * sizeof(uint64_t)));
     CUDA_TRY(up(&ds->d_prefs, sc->tree.pair_leaf_refs.data(), sc->tree.pair_leaf_refs.size() * sizeof(uint32_t)));
+    std::vector<float> flat_planes; // host copy for the one-leaf kernel's parameter block
     {
         const size_t nt = sc->tris.count;
         std::vector<float> hot(nt * 8), cold(nt * 8);
@@ -325,6 +327,7 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
             pl[i * 4 + 3] = static_cast<float>(static_cast<double>(q[3]) * q[0] + static_cast<double>(q[4]) * q[1] + static_cast<double>(q[5]) * q[2]);
         }
         CUDA_TRY(up(&ds->d_planes, pl.data(), pl.size() * sizeof(float)));
+        if (nt <= static_cast<size_t>(kFlatMaxTris)) flat_planes = pl;
     }
     CUDA_TRY(up(&ds->d_shade, sc->tris.shade.data(), sc->tris.shade.size() * sizeof(float)));
     CUDA_TRY(up(&ds->d_mirror, sc->tris.mirror.data(), sc->tris.mirror.size() * sizeof(float)));
@@ -359,13 +362,30 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
         // 110k-triangle mesh +6 %, 1M-triangle mesh +17 %), ties around 12k leaves and loses on trees that are a handful of
         // big leaves (furnace_test 155 leaves: -4 %; cornell_box, one 36-triangle leaf: -44 %)
         ds->pooled = leaves >= 1024 && refs_per_leaf <= 16.0;
-        if (leaves == 1 && sc->tree.num_pair_refs <= static_cast<uint64_t>(kFlatMaxTris)) {
+        if (leaves == 1 && sc->tree.num_pair_refs <= static_cast<uint64_t>(kFlatMaxTris) && !flat_planes.empty()) {
             for (uint64_t nd : sc->tree.pair_nodes) {
                 const uint32_t y = static_cast<uint32_t>(nd >> 32);
                 if ((y & 3u) == 3u && (y >> 2) > 0) {
                     ds->flat = true;
                     ds->flat_first = static_cast<uint32_t>(nd);
                     ds->flat_count = y >> 2;
+                    for (uint32_t k = 0; k < ds->flat_count; ++k) {
+                        const uint32_t id = sc->tree.pair_leaf_refs[ds->flat_first + k];
+                        FlatTri& t = ds->flat_params.t[k];
+                        t.nx = flat_planes[id * 4];
+                        t.ny = flat_planes[id * 4 + 1];
+                        t.nz = flat_planes[id * 4 + 2];
+                        t.dp = flat_planes[id * 4 + 3];
+                        // the scan's own box: grown by kFlatBoxGrow x scene scale, 50x the exact path's tri_box, so that the
+                        // approximate hit point is trusted for all but grazing rays (traverse_flat.cuh)
+                        float scale = 0.f;
+                        for (int c = 0; c < 6; ++c) scale = std::max(scale, std::fabs(sc->tree.box[c]));
+                        const float* v = &sc->tris.verts[static_cast<size_t>(id) * 9];
+                        for (int c = 0; c < 3; ++c) {
+                            t.blo[c] = std::min(v[c], std::min(v[3 + c], v[6 + c])) - kFlatBoxGrow * scale;
+                            t.bhi[c] = std::max(v[c], std::max(v[3 + c], v[6 + c])) + kFlatBoxGrow * scale;
+                        }
+                    }
                 }
             }
         }
@@ -398,9 +418,9 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p1, trace_pooled_kernel<1>, 128, 0));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, trace_pooled_kernel<2>, 128, 0));
         int f0 = 0, f1 = 0, f2 = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f0, trace_flat_kernel<0>, 128, 0));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f1, trace_flat_kernel<1>, 128, 0));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f2, trace_flat_kernel<2>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f0, trace_flat_kernel<0, kFlatMaxTris>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f1, trace_flat_kernel<1, kFlatMaxTris>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f2, trace_flat_kernel<2, kFlatMaxTris>, 128, 0));
         ds->grid_flat[0] = std::max(1, f0) * prop.multiProcessorCount;
         ds->grid_flat[1] = std::max(1, f1) * prop.multiProcessorCount;
         ds->grid_flat[2] = std::max(1, f2) * prop.multiProcessorCount;
@@ -483,11 +503,31 @@ static int persistent_mode(const DeviceScene* ds, bool shadow) {
         if (m == 4) return ds->flat ? 4 : (shadow ? 0 : 2);
         return m == 3 ? 3 : (m != 0 ? 2 : 0);
     }
-    // (the brute-force kernel of one-leaf scenes is bit-exact but measured slower than mode 2 on cornell_box -- 4248 vs 4819
-    // Mrays/s, profiles/README.md -- so it only runs when asked for: TRN_PERSISTENT=4)
     if (ds->dev.verbatim) return 0; // every ray takes the reference's schedule: the one-thread-per-ray kernels do exactly that
+    // one-leaf scenes (cornell_box): the brute-force kernel, both kinds of wave (TRN_FLAT=0: the while-while / per-ray kernels, A/B)
+    if (ds->flat && env_u64("TRN_FLAT", 1) != 0) return 4;
     if (ds->pooled) return 3;
     return shadow ? 0 : 2;
+}
+
+// brute-force kernel of a one-leaf scene: the instantiation whose unrolled scan covers the leaf (multiples of 4 triangles)
+template <int MODE, int NT>
+static void launch_flat_nt(DeviceScene* ds, unsigned grid, cudaStream_t stream, const float4* ra, const float4* rb, const float4* rc,
+                           const float* po, const float* pd, uint32_t n, const uint32_t* count_ptr, uint4* hits, float4* acc) {
+    if constexpr (NT > kFlatMaxTris) {
+        (void)ds; (void)grid; (void)stream; (void)ra; (void)rb; (void)rc; (void)po; (void)pd; (void)n; (void)count_ptr; (void)hits; (void)acc;
+    } else {
+        if (ds->flat_count > static_cast<uint32_t>(NT))
+            launch_flat_nt<MODE, NT + 4>(ds, grid, stream, ra, rb, rc, po, pd, n, count_ptr, hits, acc);
+        else
+            trace_flat_kernel<MODE, NT><<<grid, 128, 0, stream>>>(ds->dev, ds->flat_params, ds->flat_first, ds->flat_count, ra, rb, rc, po, pd, n,
+                                                                  count_ptr, hits, acc);
+    }
+}
+template <int MODE>
+static void launch_flat(DeviceScene* ds, unsigned grid, cudaStream_t stream, const float4* ra, const float4* rb, const float4* rc,
+                        const float* po, const float* pd, uint32_t n, const uint32_t* count_ptr, uint4* hits, float4* acc) {
+    launch_flat_nt<MODE, 4>(ds, grid, stream, ra, rb, rc, po, pd, n, count_ptr, hits, acc);
 }
 
 // closest-hit traversal of n rays (wave arrays ra/rb, or plain o/d arrays) into hits, in the given scheduling mode
@@ -495,13 +535,10 @@ static void launch_closest(DeviceScene* ds, int mode, cudaStream_t stream, const
                            const float* pd, uint32_t n, uint32_t* cursor, uint4* hits, const uint32_t* order = nullptr) {
     const bool plain = po != nullptr;
     if (mode == 4) {
-        const float4* pl = static_cast<const float4*>(ds->d_planes);
         if (plain)
-            trace_flat_kernel<2><<<persistent_grid(ds->grid_flat[2], n), 128, 0, stream>>>(ds->dev, pl, ds->flat_first, ds->flat_count, nullptr, nullptr,
-                                                                                          nullptr, po, pd, n, nullptr, cursor, hits, nullptr);
+            launch_flat<2>(ds, persistent_grid(ds->grid_flat[2], n), stream, nullptr, nullptr, nullptr, po, pd, n, nullptr, hits, nullptr);
         else
-            trace_flat_kernel<0><<<persistent_grid(ds->grid_flat[0], n), 128, 0, stream>>>(ds->dev, pl, ds->flat_first, ds->flat_count, ra, rb, nullptr,
-                                                                                          nullptr, nullptr, n, nullptr, cursor, hits, nullptr);
+            launch_flat<0>(ds, persistent_grid(ds->grid_flat[0], n), stream, ra, rb, nullptr, nullptr, nullptr, n, nullptr, hits, nullptr);
     } else if (mode == 3) {
         const int refill = static_cast<int>(env_u64("TRN_PQ_REFILL", 28)), iters = static_cast<int>(env_u64("TRN_PQ_WALK", 12));
         if (plain)
@@ -531,9 +568,7 @@ static void launch_closest(DeviceScene* ds, int mode, cudaStream_t stream, const
 static void launch_shadow(DeviceScene* ds, int mode, cudaStream_t stream, const ShadowWave& sw, uint32_t n_max, WaveCounters* counters,
                           float4* acc) {
     if (mode == 4) {
-        trace_flat_kernel<1><<<persistent_grid(ds->grid_flat[1], n_max), 128, 0, stream>>>(
-            ds->dev, static_cast<const float4*>(ds->d_planes), ds->flat_first, ds->flat_count, sw.a, sw.b, sw.c, nullptr, nullptr, 0,
-            &counters->shadow_count, &counters->shadow_cursor, nullptr, acc);
+        launch_flat<1>(ds, persistent_grid(ds->grid_flat[1], n_max), stream, sw.a, sw.b, sw.c, nullptr, nullptr, 0, &counters->shadow_count, nullptr, acc);
     } else if (mode == 3) {
         trace_pooled_kernel<1><<<persistent_grid(ds->grid_pooled[1], n_max), 128, 0, stream>>>(
             ds->dev, static_cast<const float4*>(ds->d_planes), sw.a, sw.b, sw.c, nullptr, nullptr, 0,

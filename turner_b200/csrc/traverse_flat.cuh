@@ -3,15 +3,21 @@
 // "fixed" direction (lib/kdtree.cpp:503-522), then every triangle of the leaf in order (lib/kdtree.cpp:580-607). There is
 // nothing to walk, so the kernel is organised around the triangle loop instead of around the tree:
 //
-//   SCAN   a warp takes 32 rays, one per lane, and runs ONE warp-uniform loop over the leaf's triangles. The triangle's
-//          plane (16 bytes) and grown bounding box (2 x 16 bytes) come from shared memory as broadcasts; each lane runs the
-//          division-free conservative plane pre-filter of the pooled kernel (FMA arithmetic, explicit error bounds E, F;
-//          range 0 <= r <= best hit so far / light distance) and a bounding-box test of the APPROXIMATE hit point
-//          (reciprocal instead of division; the box is grown by 1e-4 x scene scale, 100x the error of that point).
-//          Survivors -- about two per ray -- go to a per-warp queue with one ballot per triangle.
-//   EXACT  whenever 32 survivors wait (and at the end): the reference's exact operation sequence
-//          (lib/intersection.h:40-89), 32 at a time with all lanes busy, hits handed to the owner lane; first-visited wins
-//          an exact tie (the leaf's order = the scan's order).
+//   SCAN   one ray per lane; ONE warp-uniform loop over the leaf's triangles. The triangle's plane and grown bounding box
+//          (40 bytes) are KERNEL PARAMETERS: they sit in the constant bank and reach the FMAs as uniform operands, so the
+//          loop issues no load at all. Each lane runs the division-free conservative plane pre-filter of the pooled kernel
+//          (FMA arithmetic, explicit error bounds E, F; range 0 <= r <= light distance) and tests the APPROXIMATE hit
+//          point (one MUFU reciprocal instead of an IEEE division) against the triangle's box -- the box only counts where
+//          the point's error bound stays below half of the box's growth. A survivor sets one bit of the lane's own 64-bit
+//          candidate mask (two registers).
+//   EXACT  each lane walks its own candidate bits in ascending (= visiting) order and runs the reference's exact operation
+//          sequence (lib/intersection.h:40-89) on records staged in shared memory; strict '<' keeps the first-visited
+//          triangle on an exact tie. About two candidates per ray are left, so the divergent part is short; nothing is
+//          handed from lane to lane.
+//
+// Round-2 history (profiles/README.md): the first brute-force kernel pooled the survivors of a warp in a shared-memory queue
+// and handed accepted hits to their owners by shuffles -- 123 warp-instructions per ray against 104 of the while-while
+// kernel, so it lost. This one needs ~45.
 //
 // Bit-exact contract as in traverse_pooled.cuh: only EXACT accepts a triangle and computes (r, s, t); SCAN can only discard
 // triangles whose exact plane distance is negative / beyond the limit or whose hit point lies outside the triangle's box.
@@ -20,69 +26,67 @@
 
 namespace trn {
 
-#ifndef TRN_FLAT_SCAN_BOX
-#define TRN_FLAT_SCAN_BOX 0 // 1: SCAN also tests the approximate hit point against the triangle's box (fewer survivors, 2.5x the scan cost)
-#endif
-constexpr int kFlatMaxTris = 256;  // triangles of the single leaf this kernel accepts (48 + 4 bytes of shared memory each)
-constexpr int kFlatSurv = 64;      // survivor queue: < 32 left over + one triangle's 32 lanes
+constexpr int kFlatMaxTris = 64; // triangles of the single leaf this kernel accepts: one candidate bit each in two registers
+// growth of the scan's triangle boxes, relative to the scene scale. The approximate hit point of a ray that meets the plane at
+// |cos| = A carries an error of ~1e-5 x scale / A, and the box only counts where that stays below half the growth: with the
+// exact path's 1e-4 (DevScene::tri_box) every pair with A < 0.18 stayed a candidate (10 per ray); 5e-3 leaves A < 0.004.
+constexpr float kFlatBoxGrow = 5e-3f;
 
-struct FlatWarpSmem {
-    float4 ray_o[32]; // o.xyz, E
-    float4 ray_d[32]; // d.xyz, F
-    uint2 surv[kFlatSurv]; // triangle slot (= visiting order), owner lane
+// pre-filter record of one triangle, in leaf (= visiting) order
+struct FlatTri {
+    float nx, ny, nz, dp;    // plane: n, n.v0 (the pooled kernel's record)
+    float blo[3], bhi[3];    // bounding box grown by kFlatBoxGrow x scene scale
+};
+struct FlatParams {
+    FlatTri t[kFlatMaxTris]; // 2560 bytes of the 4 KB parameter space
 };
 
 // MODE 0: closest hit, rays from a RayWave (a,b) -> hits[idx];  MODE 1: any-hit shadow rays -> acc[pixel] += c when
 // unoccluded;  MODE 2: closest hit, plain (o,d) arrays -> hits[idx]
-template <int MODE>
-__global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const float4* __restrict__ planes, uint32_t first_ref, uint32_t ntris,
+// NT: the leaf's triangle count rounded up to a multiple of 4 -- the SCAN loop is fully unrolled so that every triangle
+// constant is an immediate constant-bank operand (a runtime loop costs ~12 more instructions per triangle: indexed
+// LDC/LDCU, moves, the shifted mask bit); the padding triangles' bits are masked off
+template <int MODE, int NT>
+__global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const __grid_constant__ FlatParams P, uint32_t first_ref, uint32_t ntris,
                                                          const float4* __restrict__ ra, const float4* __restrict__ rb,
                                                          const float4* __restrict__ rc, const float* __restrict__ po,
                                                          const float* __restrict__ pd, uint32_t count_arg,
-                                                         const uint32_t* __restrict__ count_ptr, uint32_t* __restrict__ cursor,
-                                                         uint4* __restrict__ hits, float4* __restrict__ acc) {
+                                                         const uint32_t* __restrict__ count_ptr, uint4* __restrict__ hits,
+                                                         float4* __restrict__ acc) {
     constexpr bool ANY = MODE == 1;
-    constexpr unsigned kFull = 0xffffffffu;
-    __shared__ float4 s_plane[kFlatMaxTris];
-    __shared__ float4 s_blo[kFlatMaxTris], s_bhi[kFlatMaxTris];
+    // exact-test records, one array per 16-byte word so that lanes with different triangles spread over the banks
+    __shared__ float4 s_rec[4][kFlatMaxTris];
     __shared__ uint32_t s_id[kFlatMaxTris];
-    __shared__ FlatWarpSmem smem[4];
     for (uint32_t k = threadIdx.x; k < ntris; k += blockDim.x) {
         const uint32_t id = __ldg(&sc.prefs[first_ref + k]);
         s_id[k] = id;
-        s_plane[k] = __ldg(&planes[id]);
-        s_blo[k] = __ldg(sc.tri_box + 2 * static_cast<size_t>(id));
-        s_bhi[k] = __ldg(sc.tri_box + 2 * static_cast<size_t>(id) + 1);
+        s_rec[0][k] = __ldg(sc.isect_hot + 2 * static_cast<size_t>(id));
+        s_rec[1][k] = __ldg(sc.isect_hot + 2 * static_cast<size_t>(id) + 1);
+        s_rec[2][k] = __ldg(sc.isect_cold + 2 * static_cast<size_t>(id));
+        s_rec[3][k] = __ldg(sc.isect_cold + 2 * static_cast<size_t>(id) + 1);
     }
     __syncthreads();
-    FlatWarpSmem& sm = smem[threadIdx.x >> 5];
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t count = count_ptr ? *count_ptr : count_arg;
     float scale = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) scale = fmaxf(scale, fmaxf(fabsf(sc.lo[c]), fabsf(sc.hi[c])));
+    // candidate bits that belong to real triangles
+    const uint32_t real0 = ntris >= 32u ? 0xffffffffu : (1u << ntris) - 1u;
+    const uint32_t real1 = ntris >= 64u ? 0xffffffffu : (ntris > 32u ? (1u << (ntris - 32u)) - 1u : 0u);
 
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32u);
-        base = __shfl_sync(kFull, base, 0);
-        if (base >= count) break;
-        const uint32_t idx = base + lane;
-        bool valid = idx < count;
-        float ox = 0, oy = 0, oz = 0, dx = 1, dy = 1, dz = 1, tmax_any = 0;
-        if (valid) {
-            if (MODE == 2) {
-                ox = po[3 * idx]; oy = po[3 * idx + 1]; oz = po[3 * idx + 2];
-                dx = pd[3 * idx]; dy = pd[3 * idx + 1]; dz = pd[3 * idx + 2];
-            } else {
-                const float4 a = __ldcs(&ra[idx]);
-                const float4 b = __ldcs(&rb[idx]);
-                ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
-                if (ANY) tmax_any = b.z;
-            }
+    // every ray costs the same (all triangles are scanned): a static grid-stride split needs no work cursor
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        float ox, oy, oz, dx, dy, dz, tmax_any = 0.f;
+        if (MODE == 2) {
+            ox = po[3 * idx]; oy = po[3 * idx + 1]; oz = po[3 * idx + 2];
+            dx = pd[3 * idx]; dy = pd[3 * idx + 1]; dz = pd[3 * idx + 2];
+        } else {
+            const float4 a = __ldcs(&ra[idx]);
+            const float4 b = __ldcs(&rb[idx]);
+            ox = a.x; oy = a.y; oz = a.z; dx = a.w; dy = b.x; dz = b.y;
+            if (ANY) tmax_any = b.z;
         }
-        const bool in_wave = valid;
+        bool valid;
         {
             // intersect_ray_box with the fixed direction, lib/kdtree.cpp:503-522, lib/intersection.h:105-128: a ray that
             // misses the scene box tests nothing
@@ -96,134 +100,131 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const floa
             float tz1 = (sc.lo[2] - oz) * iz, tz2 = (sc.hi[2] - oz) * iz;
             t0 = fmaxf(t0, fminf(tz1, tz2));
             t1 = fminf(t1, fmaxf(tz1, tz2));
-            if (t1 < t0) valid = false;
+            valid = !(t1 < t0);
         }
-        // error bounds of the pre-filter, as in traverse_pooled.cuh
+        // Error bounds of the pre-filter, as in traverse_pooled.cuh (u = 2^-24): |b - nom| <= E, |a - denom| <= F for the
+        // reference's nom = n.(v0 - o), denom = n.d.
         const float E = 1.9073486e-6f * (3.f * scale + (fabsf(ox) + fabsf(oy) + fabsf(oz)));
         const float F = 9.5367432e-7f * (fabsf(dx) + fabsf(dy) + fabsf(dz));
-        // the approximate hit point o + (B / A) d is off by at most (E + r F) / (A - F) * max|d_i| per coordinate; the box test
-        // only counts where that stays below half of the boxes' growth (grazing rays keep the triangle instead)
+        // Approximate hit point h = o + (B / A) d. Against the reference's r = nom / denom:
+        //   |B / A - r| <= (E + |B / A| F) / (A - F)            (A > F)
+        // so every coordinate of h is within (E + |B / A| F) / (A - F) * max|d_i| of the reference's hit point, plus the
+        // rounding of the reciprocal, the product and the three FMAs (a few ulp of |o| + scale when the point is anywhere
+        // near the box). The triangle's box is grown by kFlatBoxGrow x scale; the box test is TRUSTED only where the first term
+        // stays below `tol` = half of that growth minus the rounding allowance -- a grazing ray keeps the triangle instead.
         const float dmax = fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz)));
-        const float box_tol = 0.5e-4f * scale;
-        sm.ray_o[lane] = make_float4(ox, oy, oz, E);
-        sm.ray_d[lane] = make_float4(dx, dy, dz, F);
-        __syncwarp();
-        uint32_t best_id = kMiss, best_seq = 0;
+        const float omax = fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz)));
+        const float tol = 0.5f * kFlatBoxGrow * scale - 1e-6f * (omax + 2.f * scale); // <= 0 for an origin > 2000 scene sizes away: nothing is trusted
+        const float Ed = E * dmax, Fd = F * dmax, tolF = tol * F;
+        const float limE = ANY ? fmaf(tmax_any, F, E) : 0.f; // B <= lim (A + F) + E  <=>  B <= fma(lim, A, limE)
+
+        uint32_t m0 = 0, m1 = 0; // candidate bits of triangles 0..31 / 32..63
+        const float negE = -E;
+        // one triangle of the scan: sets `bit` in `m` iff  ((A <= F) | in_range) & (!trust | inside).  The predicate logic is
+        // written as PTX so that every compare folds its AND / OR into the FSETP (the C++ form compiles to a SEL per term).
+        auto scan = [&](int k, uint32_t& m, uint32_t bit) {
+            const FlatTri& T = P.t[k];
+            // (one constant-bank operand per instruction: b = dp - n.o rather than a chain that starts from dp)
+            const float a = fmaf(T.nx, dx, fmaf(T.ny, dy, T.nz * dz));
+            const float b = T.dp - fmaf(T.nx, ox, fmaf(T.ny, oy, T.nz * oz));
+            const float A = fabsf(a);
+            const float B = __uint_as_float(__float_as_uint(b) ^ (__float_as_uint(a) & 0x80000000u));
+            float rcp;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(A));
+            const float rr = B * rcp; // A == 0 -> inf or NaN: untrusted below
+            const float hx = fmaf(rr, dx, ox), hy = fmaf(rr, dy, oy), hz = fmaf(rr, dz, oz);
+            // trust <=> tl <= tr; false for A <= F (right side <= 0 < Ed) and for NaN
+            const float tl = fmaf(fabsf(rr), Fd, Ed), tr = fmaf(tol, A, -tolF);
+            // 0 <= nom/denom <= lim  ==>  A <= F  or  (B + E >= 0  and  B - E <= lim (A + F))   (traverse_pooled.cuh)
+#define TRN_FLAT_BOX_PRED                                                                                                  \
+    "setp.ge.f32 p, %1, %4;\n\t"        /* inside the grown box */                                                          \
+    "setp.ge.and.f32 p, %2, %5, p;\n\t"                                                                                     \
+    "setp.ge.and.f32 p, %3, %6, p;\n\t"                                                                                     \
+    "setp.le.and.f32 p, %1, %7, p;\n\t"                                                                                     \
+    "setp.le.and.f32 p, %2, %8, p;\n\t"                                                                                     \
+    "setp.le.and.f32 p, %3, %9, p;\n\t"                                                                                     \
+    "setp.gtu.or.f32 p, %10, %11, p;\n\t" /* ... or the box test is not trusted */                                          \
+    "setp.ge.f32 q, %12, %13;\n\t"        /* B >= -E */
+            if constexpr (ANY) {
+                const float blim = fmaf(tmax_any, A, limE); // B <= lim A + (lim F + E)
+                asm("{\n\t.reg .pred p, q;\n\t" TRN_FLAT_BOX_PRED
+                    "setp.le.and.f32 q, %12, %17, q;\n\t"
+                    "setp.le.or.f32 q, %14, %15, q;\n\t" // ... or A <= F
+                    "and.pred p, p, q;\n\t"
+                    "@p or.b32 %0, %0, %16;\n\t}"
+                    : "+r"(m)
+                    : "f"(hx), "f"(hy), "f"(hz), "f"(T.blo[0]), "f"(T.blo[1]), "f"(T.blo[2]), "f"(T.bhi[0]), "f"(T.bhi[1]), "f"(T.bhi[2]),
+                      "f"(tl), "f"(tr), "f"(B), "f"(negE), "f"(A), "f"(F), "r"(bit), "f"(blim));
+            } else {
+                asm("{\n\t.reg .pred p, q;\n\t" TRN_FLAT_BOX_PRED
+                    "setp.le.or.f32 q, %14, %15, q;\n\t" // ... or A <= F
+                    "and.pred p, p, q;\n\t"
+                    "@p or.b32 %0, %0, %16;\n\t}"
+                    : "+r"(m)
+                    : "f"(hx), "f"(hy), "f"(hz), "f"(T.blo[0]), "f"(T.blo[1]), "f"(T.blo[2]), "f"(T.bhi[0]), "f"(T.bhi[1]), "f"(T.bhi[2]),
+                      "f"(tl), "f"(tr), "f"(B), "f"(negE), "f"(A), "f"(F), "r"(bit));
+            }
+        };
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < (NT < 32 ? NT : 32); ++k) scan(k, m0, 1u << k);
+#pragma unroll
+            for (int k = 32; k < NT; ++k) scan(k, m1, 1u << (k - 32));
+            m0 &= real0;
+            m1 &= real1;
+        }
+
+        // EXACT: the lane's own candidates in visiting order
+        uint32_t best_id = kMiss;
         float best_r = kFltMax, best_s = 0.f, best_t = 0.f;
         bool occluded = false;
-        uint32_t ns = 0; // survivors waiting (warp-uniform)
-
-        auto exact_round = [&]() {
-            const uint32_t take = min(32u, ns), sbase = ns - take;
-            bool pass = false;
-            uint32_t slot = 0, owner = 0, id = 0;
-            float r = 0.f, s = 0.f, t = 0.f;
-            if (lane < take) {
-                const uint2 e = sm.surv[sbase + lane];
-                slot = e.x;
-                owner = e.y;
-                id = s_id[slot];
-            }
-            const float lim = __shfl_sync(kFull, ANY ? tmax_any : best_r, owner);
-            if (lane < take) {
-                const float4 ro = sm.ray_o[owner], rd = sm.ray_d[owner];
-                const float4* rec = sc.isect_hot + 2 * static_cast<size_t>(id);
-                const float4* rec2 = sc.isect_cold + 2 * static_cast<size_t>(id);
-                const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
-                const float nx = q0.w, ny = q1.x, nz = q1.y;
-                const float denom = nx * rd.x + ny * rd.y + nz * rd.z; // intersect_ray_plane, lib/intersection.h:40-49
-                const float nom = nx * (q0.x - ro.x) + ny * (q0.y - ro.y) + nz * (q0.z - ro.z);
-                r = nom / denom;
-                bool cand = denom != 0.f && r >= 0.f && r <= lim;
-                if (cand) { // a hit point outside the triangle's (grown) box cannot pass the barycentric part (as traverse_pairs<>)
-                    const float4 blo = s_blo[slot], bhi = s_bhi[slot];
-                    const float hx = ro.x + r * rd.x, hy = ro.y + r * rd.y, hz = ro.z + r * rd.z;
-                    cand = !(hx < blo.x || hy < blo.y || hz < blo.z || hx > bhi.x || hy > bhi.y || hz > bhi.z);
-                }
-                if (cand) {
-                    const float4 q2 = __ldg(rec2), q3 = __ldg(rec2 + 1);
-                    const float wx = (ro.x + r * rd.x) - q0.x, wy = (ro.y + r * rd.y) - q0.y, wz = (ro.z + r * rd.z) - q0.z; // :70-71
-                    const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
-                    const float wv = wx * vx + wy * vy + wz * vz;
-                    const float wu = wx * ux + wy * uy + wz * uz;
-                    s = (q3.x * wv - q3.y * wu) / q3.w; // :78-86
-                    if (!(s < 0.f)) {
-                        t = (q3.x * wu - q3.z * wv) / q3.w;
-                        pass = !(t < 0.f || 1.f < s + t);
-                    }
-                }
-            }
-            unsigned pm = __ballot_sync(kFull, pass);
-            while (pm) {
-                const int src = __ffs(pm) - 1;
-                pm &= pm - 1;
-                const uint32_t o_ = __shfl_sync(kFull, owner, src);
-                const float r_ = __shfl_sync(kFull, r, src);
-                const float s_ = __shfl_sync(kFull, s, src);
-                const float t_ = __shfl_sync(kFull, t, src);
-                const uint32_t id_ = __shfl_sync(kFull, id, src);
-                const uint32_t q_ = __shfl_sync(kFull, slot, src);
-                if (lane == o_) {
-                    if (ANY) {
-                        occluded = true;
-                    } else if (r_ < best_r || (r_ == best_r && q_ < best_seq)) { // strict '<' keeps the first-visited triangle on ties
-                        best_r = r_;
-                        best_s = s_;
-                        best_t = t_;
-                        best_id = id_;
-                        best_seq = q_;
-                    }
-                }
-            }
-            ns = sbase;
-            __syncwarp();
-        };
-
-        if (__ballot_sync(kFull, valid) != 0u) {
-#pragma unroll 1
-            for (uint32_t k = 0; k < ntris; ++k) {
-                const float4 p = s_plane[k];
-                const float a = fmaf(p.x, dx, fmaf(p.y, dy, p.z * dz));
-                const float b = fmaf(-p.x, ox, fmaf(-p.y, oy, fmaf(-p.z, oz, p.w)));
-                const float A = fabsf(a);
-                const float B = __uint_as_float(__float_as_uint(b) ^ (__float_as_uint(a) & 0x80000000u));
-                // 0 <= nom/denom <= lim  ==>  A <= F  or  (B + E >= 0  and  B - E <= lim (A + F))   (traverse_pooled.cuh)
-                const float lim = ANY ? tmax_any : best_r;
-                const bool in_range = (B >= -E) & (B <= fmaf(lim, A + F, E));
-#if TRN_FLAT_SCAN_BOX
-                // approximate hit point against the triangle's grown box (kernels.cuh: tri_box is grown by 1e-4 x scene scale)
-                const float4 blo = s_blo[k], bhi = s_bhi[k];
-                const float rcp = __fdividef(1.f, fmaxf(A - F, 1e-30f));
-                const float rr = B * rcp;
-                const float hx = fmaf(rr, dx, ox), hy = fmaf(rr, dy, oy), hz = fmaf(rr, dz, oz);
-                const bool trust = fmaf(fabsf(rr), F, E) * rcp * dmax <= box_tol;
-                const bool inside = !trust | ((hx >= blo.x) & (hy >= blo.y) & (hz >= blo.z) & (hx <= bhi.x) & (hy <= bhi.y) & (hz <= bhi.z));
-#else
-                const bool inside = true;
-                (void)dmax;
-                (void)box_tol;
-#endif
-                const bool keep = valid & !(ANY && occluded) & ((A <= F) | (in_range & inside));
-                const unsigned bk = __ballot_sync(kFull, keep);
-                if (keep) sm.surv[ns + __popc(bk & lt_mask)] = make_uint2(k, lane);
-                ns += __popc(bk);
-                if (ns >= 32u) {
-                    __syncwarp();
-                    exact_round();
-                }
-            }
-            __syncwarp();
-            while (ns > 0u) exact_round();
-        }
-        if (in_wave) {
-            if (ANY) {
-                if (!occluded) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx]));
+        while ((m0 | m1) != 0u) {
+            uint32_t k;
+            if (m0 != 0u) {
+                k = __ffs(m0) - 1;
+                m0 &= m0 - 1u;
             } else {
-                __stcs(&hits[idx], make_uint4(best_id, __float_as_uint(best_r), __float_as_uint(best_s), __float_as_uint(best_t)));
+                k = 32u + (__ffs(m1) - 1);
+                m1 &= m1 - 1u;
+            }
+            const float4 q0 = s_rec[0][k], q1 = s_rec[1][k];
+            const float nx = q0.w, ny = q1.x, nz = q1.y;
+            const float denom = nx * dx + ny * dy + nz * dz; // intersect_ray_plane, lib/intersection.h:40-49
+            const float nom = nx * (q0.x - ox) + ny * (q0.y - oy) + nz * (q0.z - oz);
+            const float r = nom / denom;
+            // r < 0 rejects (intersection.h:66); a hit only matters if it beats the running minimum (lib/kdtree.cpp:591;
+            // strict: the first-visited triangle keeps an exact tie), resp. lies within the light distance
+            if (denom != 0.f && r >= 0.f && (ANY ? r <= tmax_any : r < best_r)) {
+                const float4 q2 = s_rec[2][k], q3 = s_rec[3][k];
+                const float wx = (ox + r * dx) - q0.x, wy = (oy + r * dy) - q0.y, wz = (oz + r * dz) - q0.z; // :70-71
+                const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
+                const float wv = wx * vx + wy * vy + wz * vz;
+                const float wu = wx * ux + wy * uy + wz * uz;
+                const float s = (q3.x * wv - q3.y * wu) / q3.w; // :78-86
+                if (!(s < 0.f)) {
+                    const float t = (q3.x * wu - q3.z * wv) / q3.w;
+                    if (!(t < 0.f || 1.f < s + t)) {
+                        if (ANY) {
+                            occluded = true;
+                            m0 = 0u;
+                            m1 = 0u;
+                        } else {
+                            best_r = r;
+                            best_s = s;
+                            best_t = t;
+                            best_id = s_id[k];
+                        }
+                    }
+                }
             }
         }
-        __syncwarp();
+        if (ANY) {
+            if (!occluded) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx]));
+        } else {
+            __stcs(&hits[idx], make_uint4(best_id, __float_as_uint(best_r), __float_as_uint(best_s), __float_as_uint(best_t)));
+        }
     }
 }
 
 } // namespace trn
+
