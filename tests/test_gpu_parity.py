@@ -883,3 +883,97 @@ def test_device_builder_degenerate_and_awkward_inputs(api, ob, scenes):
             i_r, r_r = o.intersect(org, d, 0)
             i_h, r_h = h.intersect(org, d)
             assert np.array_equal(i_h, i_r) and np.array_equal(bits(r_h), bits(r_r)), name
+
+
+def _quad_room(flip_every=2, jitter=0.0, seed=0):
+    """a closed room of axis-aligned and rotated quads, each split into two triangles -- every other quad with its second
+    triangle wound the other way (opposite normal, same plane), optionally with one vertex pushed off the plane"""
+    rng = np.random.RandomState(seed)
+    quads = []
+    L = 1.0
+    for ax in range(3):
+        for side in (-L, L):
+            a, b = [(1, 2), (0, 2), (0, 1)][ax]
+            q = np.zeros((4, 3))
+            q[:, ax] = side
+            q[:, a] = [-L, L, L, -L]
+            q[:, b] = [-L, -L, L, L]
+            quads.append(q)
+    for _ in range(10):  # free-standing rotated rectangles inside
+        c = rng.uniform(-0.6, 0.6, 3)
+        e1 = rng.normal(size=3)
+        e1 /= np.linalg.norm(e1)
+        e2 = np.cross(e1, rng.normal(size=3))
+        e2 /= np.linalg.norm(e2)
+        w, h = rng.uniform(0.1, 0.35, 2)
+        quads.append(np.array([c - w * e1 - h * e2, c + w * e1 - h * e2, c + w * e1 + h * e2, c - w * e1 + h * e2]))
+    tris = []
+    for i, q in enumerate(quads):
+        q = q.copy()
+        if jitter and i % 3 == 0:
+            q[2] += jitter * rng.normal(size=3)
+        tris.append([q[0], q[1], q[2]])
+        tris.append([q[0], q[3], q[2]] if i % flip_every == 0 else [q[0], q[2], q[3]])
+    V = np.asarray(tris, np.float32)
+    g = np.cross(V[:, 1] - V[:, 0], V[:, 2] - V[:, 0])
+    g /= np.maximum(np.linalg.norm(g, axis=-1, keepdims=True), 1e-20)
+    n = V.shape[0]
+    return {"name": "quad_room_%d_%g" % (flip_every, jitter), "vertices": V.reshape(-1, 9),
+            "normals": np.repeat(g[:, None, :], 3, 1).astype(np.float32).reshape(-1, 9),
+            "diffuse": np.full((n, 4), 0.6, np.float32), "camera": None, "light": {"pos": [0.0, 0.9, 0.0], "color": [1, 1, 1, 1]}}
+
+
+def test_one_leaf_scenes_brute_force_kernel(api, ob, scenes, monkeypatch):
+    # The brute-force kernel of one-leaf trees (traverse_flat.cuh): scan groups (coplanar pairs and single triangles), both
+    # candidate-mask words (33..64 triangles), pairs with opposite windings, nearly-coplanar pairs that must NOT be merged,
+    # rays that graze planes (box test not trusted), start on a surface, start far away, or have zero direction components.
+    cases = [scenes.random_soup(n, seed=s, extent=e, size=z) for n, s, e, z in
+             ((33, 3, 1.0, 2.0), (40, 4, 1.0, 2.0), (50, 5, 1.0, 3.0), (64, 6, 0.5, 2.0), (7, 7, 1.0, 2.0), (1, 8, 1.0, 2.0))]
+    cases += [_quad_room(2, 0.0), _quad_room(1, 0.0), _quad_room(2, 1e-6, seed=1), _quad_room(3, 1e-3, seed=2), scenes.fixture("cornell_box")]
+    total = 0
+    for sc in cases:
+        p = api.Scene.from_dict(sc)
+        assert p.height == 0, sc["name"]
+        o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
+        V = sc["vertices"].reshape(-1, 3, 3)
+        size = float(np.abs(V).max())
+        rng = np.random.RandomState(12)
+        sets = [scenes.random_rays(sc, 60000, seed=21, inside=True), scenes.random_rays(sc, 40000, seed=22, inside=False),
+                _secondary_shaped_rays(sc, 60000, 23)]
+        # grazing: rays inside a triangle's plane (up to rounding) and nearly so
+        t = rng.randint(0, V.shape[0], 30000)
+        b = rng.dirichlet((1, 1, 1), 30000)
+        pt = (V[t] * b[:, :, None]).sum(1)
+        e1 = V[t, 1] - V[t, 0]
+        e2 = V[t, 2] - V[t, 0]
+        nrm = np.cross(e1, e2)
+        nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
+        d = e1 * rng.normal(size=(30000, 1)) + e2 * rng.normal(size=(30000, 1)) + nrm * (rng.normal(size=(30000, 1)) * 10.0 ** rng.uniform(-9, -2, (30000, 1)))
+        og = pt - d * rng.uniform(0.1, 2.0, (30000, 1))
+        sets.append((np.ascontiguousarray(og, np.float32), np.ascontiguousarray(d, np.float32)))
+        # far away: origins 10 .. 1e5 scene sizes out, aimed at the scene
+        tgt = rng.uniform(-1, 1, (20000, 3)) * size
+        u = rng.normal(size=(20000, 3))
+        u /= np.linalg.norm(u, axis=1, keepdims=True)
+        of = tgt + u * size * 10.0 ** rng.uniform(1, 5, (20000, 1))
+        sets.append((np.ascontiguousarray(of, np.float32), np.ascontiguousarray(tgt - of, np.float32)))
+        for ro, rd in sets:
+            rd = rd.copy()
+            rd[::23, 1] = 0
+            rd[::29, 0] = 0
+            i_o, r_o = o.intersect(ro, rd, 0)
+            for pairs in ("1", "0"):
+                monkeypatch.setenv("TRN_FLAT_PAIRS", pairs)
+                q = api.Scene.from_dict(sc) if pairs == "0" else p
+                i_g, r_g = q.intersect(ro, rd)
+                assert np.array_equal(i_g, i_o), (sc["name"], pairs, int((i_g != i_o).sum()))
+                assert np.array_equal(bits(r_g), bits(r_o)), (sc["name"], pairs)
+                hit = i_o != ob.MISS
+                tmax = np.where(hit, r_o[:, 0], np.float32(size)).astype(np.float32)
+                tmax[::3] = np.nextafter(tmax[::3], np.float32(-1))
+                tmax[1::3] = tmax[1::3] * np.float32(1.5)
+                assert np.array_equal(q.occluded(ro, rd, tmax), hit & (r_o[:, 0] <= tmax)), (sc["name"], pairs)
+            monkeypatch.delenv("TRN_FLAT_PAIRS")
+            total += ro.shape[0]
+        assert (i_o != ob.MISS).any()
+    assert total > 1_500_000

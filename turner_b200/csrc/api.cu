@@ -127,6 +127,7 @@ struct DeviceScene {
     bool pooled = true;   // pooled kernel for both kinds of wave (a real tree: many leaves of moderate size)
     bool flat = false;    // the tree is ONE leaf of <= kFlatMaxTris triangles (cornell_box): brute-force kernel, no walk
     uint32_t flat_first = 0, flat_count = 0; // that leaf's references
+    uint32_t flat_groups = 0;                // scan records of the brute-force kernel (a triangle or a coplanar pair each)
     FlatParams flat_params{};                // its pre-filter records (plane + grown box, visiting order): kernel parameters
     int grid_flat[3] = {0, 0, 0};
     int grid_closest = 0, grid_shadow = 0, grid_plain = 0; // persistent grids: resident CTAs per SM x SMs
@@ -268,6 +269,8 @@ static void ensure_reference_shape(trn_scene* sc) {
     sc->reference_shape = true;
 }
 
+static uint64_t env_u64(const char* name, uint64_t dflt);
+
 static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -369,23 +372,76 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
                     ds->flat = true;
                     ds->flat_first = static_cast<uint32_t>(nd);
                     ds->flat_count = y >> 2;
-                    for (uint32_t k = 0; k < ds->flat_count; ++k) {
-                        const uint32_t id = sc->tree.pair_leaf_refs[ds->flat_first + k];
-                        FlatTri& t = ds->flat_params.t[k];
-                        t.nx = flat_planes[id * 4];
-                        t.ny = flat_planes[id * 4 + 1];
-                        t.nz = flat_planes[id * 4 + 2];
-                        t.dp = flat_planes[id * 4 + 3];
-                        // the scan's own box: grown by kFlatBoxGrow x scene scale, 50x the exact path's tri_box, so that the
-                        // approximate hit point is trusted for all but grazing rays (traverse_flat.cuh)
-                        float scale = 0.f;
-                        for (int c = 0; c < 6; ++c) scale = std::max(scale, std::fabs(sc->tree.box[c]));
+                    // Scan groups (traverse_flat.cuh): one record per triangle, or per PAIR of coplanar triangles with nearly the
+                    // same box (the two halves of a quad -- every face of cornell_box). A pair shares the leader's plane: its
+                    // partner's normal / plane offset may differ by at most 8 u / 8 u x scale (u = 2^-24), which the kernel's
+                    // error bounds E, F include.
+                    float scale = 0.f;
+                    for (int c = 0; c < 6; ++c) scale = std::max(scale, std::fabs(sc->tree.box[c]));
+                    const float u8 = 8.f * 5.9604645e-8f;
+                    auto leaf_id = [&](uint32_t k) { return sc->tree.pair_leaf_refs[ds->flat_first + k]; };
+                    auto tri_box = [&](uint32_t id, float* lo, float* hi) {
                         const float* v = &sc->tris.verts[static_cast<size_t>(id) * 9];
                         for (int c = 0; c < 3; ++c) {
-                            t.blo[c] = std::min(v[c], std::min(v[3 + c], v[6 + c])) - kFlatBoxGrow * scale;
-                            t.bhi[c] = std::max(v[c], std::max(v[3 + c], v[6 + c])) + kFlatBoxGrow * scale;
+                            lo[c] = std::min(v[c], std::min(v[3 + c], v[6 + c]));
+                            hi[c] = std::max(v[c], std::max(v[3 + c], v[6 + c]));
                         }
+                    };
+                    std::vector<char> grouped(ds->flat_count, 0);
+                    uint32_t ng = 0;
+                    for (uint32_t k = 0; k < ds->flat_count; ++k) {
+                        if (grouped[k]) continue;
+                        grouped[k] = 1;
+                        const uint32_t id = leaf_id(k);
+                        const float* pk = &flat_planes[static_cast<size_t>(id) * 4];
+                        float lo[3], hi[3];
+                        tri_box(id, lo, hi);
+                        uint32_t members = k + 1u;
+                        if (env_u64("TRN_FLAT_PAIRS", 1) != 0) {
+                            for (uint32_t j = k + 1; j < ds->flat_count; ++j) {
+                                if (grouped[j]) continue;
+                                const uint32_t idj = leaf_id(j);
+                                const float* pj = &flat_planes[static_cast<size_t>(idj) * 4];
+                                bool match = false;
+                                for (float sgn : {1.f, -1.f}) {
+                                    bool m = std::fabs(pk[3] - sgn * pj[3]) <= u8 * scale;
+                                    for (int c = 0; c < 3; ++c) m = m && std::fabs(pk[c] - sgn * pj[c]) <= u8;
+                                    match = match || m;
+                                }
+                                if (!match) continue;
+                                // the union box must not be much larger than either box (else the shared box filters poorly)
+                                float lj[3], hj[3];
+                                tri_box(idj, lj, hj);
+                                bool close = true;
+                                for (int c = 0; c < 3; ++c) {
+                                    const float eu = std::max(hi[c], hj[c]) - std::min(lo[c], lj[c]);
+                                    close = close && eu <= 1.5f * std::min(hi[c] - lo[c], hj[c] - lj[c]) + 1e-3f * scale;
+                                }
+                                if (!close) continue;
+                                for (int c = 0; c < 3; ++c) {
+                                    lo[c] = std::min(lo[c], lj[c]);
+                                    hi[c] = std::max(hi[c], hj[c]);
+                                }
+                                grouped[j] = 1;
+                                members |= (j + 1u) << 8;
+                                break;
+                            }
+                        }
+                        FlatTri& t = ds->flat_params.t[ng];
+                        t.nx = pk[0];
+                        t.ny = pk[1];
+                        t.nz = pk[2];
+                        t.dp = pk[3];
+                        // the scan's own box: grown by kFlatBoxGrow x scene scale, 50x the exact path's tri_box, so that the
+                        // approximate hit point is trusted for all but grazing rays (traverse_flat.cuh)
+                        for (int c = 0; c < 3; ++c) {
+                            t.blo[c] = lo[c] - kFlatBoxGrow * scale;
+                            t.bhi[c] = hi[c] + kFlatBoxGrow * scale;
+                        }
+                        ds->flat_params.members[ng] = static_cast<uint16_t>(members);
+                        ++ng;
                     }
+                    ds->flat_groups = ng;
                 }
             }
         }
@@ -510,18 +566,18 @@ static int persistent_mode(const DeviceScene* ds, bool shadow) {
     return shadow ? 0 : 2;
 }
 
-// brute-force kernel of a one-leaf scene: the instantiation whose unrolled scan covers the leaf (multiples of 4 triangles)
+// brute-force kernel of a one-leaf scene: the instantiation whose unrolled scan covers the leaf's scan groups (multiples of 4)
 template <int MODE, int NT>
 static void launch_flat_nt(DeviceScene* ds, unsigned grid, cudaStream_t stream, const float4* ra, const float4* rb, const float4* rc,
                            const float* po, const float* pd, uint32_t n, const uint32_t* count_ptr, uint4* hits, float4* acc) {
     if constexpr (NT > kFlatMaxTris) {
         (void)ds; (void)grid; (void)stream; (void)ra; (void)rb; (void)rc; (void)po; (void)pd; (void)n; (void)count_ptr; (void)hits; (void)acc;
     } else {
-        if (ds->flat_count > static_cast<uint32_t>(NT))
+        if (ds->flat_groups > static_cast<uint32_t>(NT))
             launch_flat_nt<MODE, NT + 4>(ds, grid, stream, ra, rb, rc, po, pd, n, count_ptr, hits, acc);
         else
-            trace_flat_kernel<MODE, NT><<<grid, 128, 0, stream>>>(ds->dev, ds->flat_params, ds->flat_first, ds->flat_count, ra, rb, rc, po, pd, n,
-                                                                  count_ptr, hits, acc);
+            trace_flat_kernel<MODE, NT><<<grid, 128, 0, stream>>>(ds->dev, ds->flat_params, ds->flat_first, ds->flat_count, ds->flat_groups, ra, rb,
+                                                                  rc, po, pd, n, count_ptr, hits, acc);
     }
 }
 template <int MODE>

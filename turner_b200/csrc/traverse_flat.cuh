@@ -32,22 +32,26 @@ constexpr int kFlatMaxTris = 64; // triangles of the single leaf this kernel acc
 // exact path's 1e-4 (DevScene::tri_box) every pair with A < 0.18 stayed a candidate (10 per ray); 5e-3 leaves A < 0.004.
 constexpr float kFlatBoxGrow = 5e-3f;
 
-// pre-filter record of one triangle, in leaf (= visiting) order
+// Pre-filter record of one SCAN GROUP: a triangle, or two coplanar triangles with (nearly) the same box -- the halves of a
+// quad, which is every face of cornell_box. A pair is scanned once, with the leader's plane and the union box; the host only
+// pairs triangles whose unit normals / plane offsets agree to 8 u / 8 u x scale, and E, F below carry that difference.
 struct FlatTri {
     float nx, ny, nz, dp;    // plane: n, n.v0 (the pooled kernel's record)
     float blo[3], bhi[3];    // bounding box grown by kFlatBoxGrow x scene scale
 };
 struct FlatParams {
-    FlatTri t[kFlatMaxTris]; // 2560 bytes of the 4 KB parameter space
+    FlatTri t[kFlatMaxTris];        // one per scan group; 2560 bytes of the 4 KB parameter space
+    uint16_t members[kFlatMaxTris]; // the group's triangles as leaf slots + 1: k0 + 1 | (k1 + 1) << 8 (0 = no second triangle)
 };
 
 // MODE 0: closest hit, rays from a RayWave (a,b) -> hits[idx];  MODE 1: any-hit shadow rays -> acc[pixel] += c when
 // unoccluded;  MODE 2: closest hit, plain (o,d) arrays -> hits[idx]
-// NT: the leaf's triangle count rounded up to a multiple of 4 -- the SCAN loop is fully unrolled so that every triangle
-// constant is an immediate constant-bank operand (a runtime loop costs ~12 more instructions per triangle: indexed
-// LDC/LDCU, moves, the shifted mask bit); the padding triangles' bits are masked off
+// NT: the number of scan groups rounded up to a multiple of 4 -- the SCAN loop is fully unrolled so that every constant is an
+// immediate constant-bank operand (a runtime loop costs ~12 more instructions per record: indexed LDC/LDCU, moves, the
+// shifted mask bit); the padding records' bits are masked off
 template <int MODE, int NT>
 __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const __grid_constant__ FlatParams P, uint32_t first_ref, uint32_t ntris,
+                                                         uint32_t ngroups,
                                                          const float4* __restrict__ ra, const float4* __restrict__ rb,
                                                          const float4* __restrict__ rc, const float* __restrict__ po,
                                                          const float* __restrict__ pd, uint32_t count_arg,
@@ -57,6 +61,8 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const __gr
     // exact-test records, one array per 16-byte word so that lanes with different triangles spread over the banks
     __shared__ float4 s_rec[4][kFlatMaxTris];
     __shared__ uint32_t s_id[kFlatMaxTris];
+    __shared__ uint32_t s_members[kFlatMaxTris];
+    if (threadIdx.x < static_cast<uint32_t>(kFlatMaxTris)) s_members[threadIdx.x] = threadIdx.x < ngroups ? P.members[threadIdx.x] : 0u;
     for (uint32_t k = threadIdx.x; k < ntris; k += blockDim.x) {
         const uint32_t id = __ldg(&sc.prefs[first_ref + k]);
         s_id[k] = id;
@@ -70,9 +76,9 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const __gr
     float scale = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) scale = fmaxf(scale, fmaxf(fabsf(sc.lo[c]), fabsf(sc.hi[c])));
-    // candidate bits that belong to real triangles
-    const uint32_t real0 = ntris >= 32u ? 0xffffffffu : (1u << ntris) - 1u;
-    const uint32_t real1 = ntris >= 64u ? 0xffffffffu : (ntris > 32u ? (1u << (ntris - 32u)) - 1u : 0u);
+    // candidate bits that belong to real scan groups
+    const uint32_t real0 = ngroups >= 32u ? 0xffffffffu : (1u << ngroups) - 1u;
+    const uint32_t real1 = ngroups >= 64u ? 0xffffffffu : (ngroups > 32u ? (1u << (ngroups - 32u)) - 1u : 0u);
 
     // every ray costs the same (all triangles are scanned): a static grid-stride split needs no work cursor
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
@@ -102,10 +108,11 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const __gr
             t1 = fminf(t1, fmaxf(tz1, tz2));
             valid = !(t1 < t0);
         }
-        // Error bounds of the pre-filter, as in traverse_pooled.cuh (u = 2^-24): |b - nom| <= E, |a - denom| <= F for the
-        // reference's nom = n.(v0 - o), denom = n.d.
-        const float E = 1.9073486e-6f * (3.f * scale + (fabsf(ox) + fabsf(oy) + fabsf(oz)));
-        const float F = 9.5367432e-7f * (fabsf(dx) + fabsf(dy) + fabsf(dz));
+        // Error bounds of the pre-filter (u = 2^-24): |b - nom| <= E, |a - denom| <= F for the reference's nom = n.(v0 - o),
+        // denom = n.d of EVERY triangle of the group. traverse_pooled.cuh derives 11 u (3 S + |o|_1) and 6 u |d|_1 for a
+        // triangle's own plane; a pair's partner adds 8 u (S + |o|_1) and 8 u |d|_1: E = 48 u (...), F = 24 u |d|_1.
+        const float E = 2.8610229e-6f * (3.f * scale + (fabsf(ox) + fabsf(oy) + fabsf(oz)));
+        const float F = 1.4305115e-6f * (fabsf(dx) + fabsf(dy) + fabsf(dz));
         // Approximate hit point h = o + (B / A) d. Against the reference's r = nom / denom:
         //   |B / A - r| <= (E + |B / A| F) / (A - F)            (A > F)
         // so every coordinate of h is within (E + |B / A| F) / (A - F) * max|d_i| of the reference's hit point, plus the
@@ -174,49 +181,56 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const __gr
             m1 &= real1;
         }
 
-        // EXACT: the lane's own candidates in visiting order
-        uint32_t best_id = kMiss;
+        // EXACT: the lane's own candidate groups; an exact tie in r goes to the triangle visited first (the lower leaf slot)
+        uint32_t best_id = kMiss, best_k = 0;
         float best_r = kFltMax, best_s = 0.f, best_t = 0.f;
         bool occluded = false;
         while ((m0 | m1) != 0u) {
-            uint32_t k;
+            uint32_t g;
             if (m0 != 0u) {
-                k = __ffs(m0) - 1;
+                g = __ffs(m0) - 1;
                 m0 &= m0 - 1u;
             } else {
-                k = 32u + (__ffs(m1) - 1);
+                g = 32u + (__ffs(m1) - 1);
                 m1 &= m1 - 1u;
             }
-            const float4 q0 = s_rec[0][k], q1 = s_rec[1][k];
-            const float nx = q0.w, ny = q1.x, nz = q1.y;
-            const float denom = nx * dx + ny * dy + nz * dz; // intersect_ray_plane, lib/intersection.h:40-49
-            const float nom = nx * (q0.x - ox) + ny * (q0.y - oy) + nz * (q0.z - oz);
-            const float r = nom / denom;
-            // r < 0 rejects (intersection.h:66); a hit only matters if it beats the running minimum (lib/kdtree.cpp:591;
-            // strict: the first-visited triangle keeps an exact tie), resp. lies within the light distance
-            if (denom != 0.f && r >= 0.f && (ANY ? r <= tmax_any : r < best_r)) {
-                const float4 q2 = s_rec[2][k], q3 = s_rec[3][k];
-                const float wx = (ox + r * dx) - q0.x, wy = (oy + r * dy) - q0.y, wz = (oz + r * dz) - q0.z; // :70-71
-                const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
-                const float wv = wx * vx + wy * vy + wz * vz;
-                const float wu = wx * ux + wy * uy + wz * uz;
-                const float s = (q3.x * wv - q3.y * wu) / q3.w; // :78-86
-                if (!(s < 0.f)) {
-                    const float t = (q3.x * wu - q3.z * wv) / q3.w;
-                    if (!(t < 0.f || 1.f < s + t)) {
-                        if (ANY) {
-                            occluded = true;
-                            m0 = 0u;
-                            m1 = 0u;
-                        } else {
-                            best_r = r;
-                            best_s = s;
-                            best_t = t;
-                            best_id = s_id[k];
+            uint32_t kk = s_members[g];
+            do {
+                const uint32_t k = (kk & 0xffu) - 1u;
+                kk >>= 8;
+                const float4 q0 = s_rec[0][k], q1 = s_rec[1][k];
+                const float nx = q0.w, ny = q1.x, nz = q1.y;
+                const float denom = nx * dx + ny * dy + nz * dz; // intersect_ray_plane, lib/intersection.h:40-49
+                const float nom = nx * (q0.x - ox) + ny * (q0.y - oy) + nz * (q0.z - oz);
+                const float r = nom / denom;
+                // r < 0 rejects (intersection.h:66); a hit only matters if it can beat the running minimum (lib/kdtree.cpp:591),
+                // resp. lies within the light distance
+                if (denom != 0.f && r >= 0.f && r <= (ANY ? tmax_any : best_r)) {
+                    const float4 q2 = s_rec[2][k], q3 = s_rec[3][k];
+                    const float wx = (ox + r * dx) - q0.x, wy = (oy + r * dy) - q0.y, wz = (oz + r * dz) - q0.z; // :70-71
+                    const float ux = q1.z, uy = q1.w, uz = q2.x, vx = q2.y, vy = q2.z, vz = q2.w;
+                    const float wv = wx * vx + wy * vy + wz * vz;
+                    const float wu = wx * ux + wy * uy + wz * uz;
+                    const float s = (q3.x * wv - q3.y * wu) / q3.w; // :78-86
+                    if (!(s < 0.f)) {
+                        const float t = (q3.x * wu - q3.z * wv) / q3.w;
+                        if (!(t < 0.f || 1.f < s + t)) {
+                            if (ANY) {
+                                occluded = true;
+                                m0 = 0u;
+                                m1 = 0u;
+                                kk = 0u;
+                            } else if (r < best_r || k < best_k) { // (r == best_r here unless r < best_r)
+                                best_r = r;
+                                best_s = s;
+                                best_t = t;
+                                best_k = k;
+                                best_id = s_id[k];
+                            }
                         }
                     }
                 }
-            }
+            } while (kk != 0u);
         }
         if (ANY) {
             if (!occluded) accumulate(acc, __float_as_uint(__ldcs(&rb[idx]).w), __ldcs(&rc[idx]));
