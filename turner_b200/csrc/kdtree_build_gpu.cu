@@ -44,10 +44,13 @@ namespace gpubuild {
 constexpr int kBins = 32;
 constexpr int kMaxLevels = 56;          // tree height bound (the traversal stack holds 64 entries)
 // lib/kdtree.cpp:178 has 15: on the pooled GPU traversal an inner-node step costs more against a triangle pre-test than on
-// the CPU; 30 renders the 1M mesh 3 % faster than 15 (8: -6 %, 60: +2.5 %; profiles/README.md), the tree is as correct
-constexpr float kCostTraversal = 30.f;
+// the CPU; 30 renders the 1M mesh 3 % faster than 15 (8: -6 %, 60: +2.5 %), 40 together with the weaker empty-space bonus
+// below another 3 % (profiles/README.md); the tree is as correct
+constexpr float kCostTraversal = 40.f;
 constexpr float kCostIntersection = 20.f; // lib/kdtree.cpp:179
-constexpr float kLambdaEmpty = 0.8f;    // lib/kdtree.cpp:183-188
+// lib/kdtree.cpp:183-188 has 0.8. 39 % of the walk steps of the 1M mesh were at empty-space cuts; a cut has to save more than a
+// step per ray through the node to pay: 0.8 / 0.85 / 0.9 / 0.95 / 1.0 render at 1691 / 1718 / 1738 / 1728 / 1641 Mrays/s
+constexpr float kLambdaEmpty = 0.9f;
 constexpr uint32_t kLeafMax = 3;        // lib/kdtree.cpp:133-136
 
 struct SahParams { // the reference's constants; TRN_KD_* override them for experiments (profiles/README.md)
