@@ -113,21 +113,22 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const __gr
         // triangle's own plane; a pair's partner adds 8 u (S + |o|_1) and 8 u |d|_1: E = 48 u (...), F = 24 u |d|_1.
         const float E = 2.8610229e-6f * (3.f * scale + (fabsf(ox) + fabsf(oy) + fabsf(oz)));
         const float F = 1.4305115e-6f * (fabsf(dx) + fabsf(dy) + fabsf(dz));
-        // Approximate hit point h = o + (B / A) d. Against the reference's r = nom / denom:
-        //   |B / A - r| <= (E + |B / A| F) / (A - F)            (A > F)
-        // so every coordinate of h is within (E + |B / A| F) / (A - F) * max|d_i| of the reference's hit point, plus the
-        // rounding of the reciprocal, the product and the three FMAs (a few ulp of |o| + scale when the point is anywhere
-        // near the box). The triangle's box is grown by kFlatBoxGrow x scale; the box test is TRUSTED only where the first term
-        // stays below `tol` = half of that growth minus the rounding allowance -- a grazing ray keeps the triangle instead.
+        // Approximate hit point h = o + (B / A) d. Against the reference's r = nom / denom (both bounds above hold, signs aligned):
+        //   |B / A - r| = |(nom - B) denom - nom (denom - A)| / (|denom| A) <= (E + |r| F) / A
+        // and a hit the reference accepts lies in the triangle, so |r| max|d_i| <= max|o_i| + scale: every coordinate of h is
+        // within  (E max|d_i| + (max|o_i| + scale) F) / A  of the accepted hit point, plus the rounding of the reciprocal, the
+        // product and the three FMAs (a few ulp of |o| + scale). The group's box is grown by kFlatBoxGrow x scale; the box test
+        // is TRUSTED only where that bound stays below `tol` = half of the growth minus the rounding allowance, i.e. for
+        // A >= Amin -- a per-ray constant. A grazing ray (and a ray so far away that tol <= 0) keeps the group instead.
         const float dmax = fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz)));
         const float omax = fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz)));
-        const float tol = 0.5f * kFlatBoxGrow * scale - 1e-6f * (omax + 2.f * scale); // <= 0 for an origin > 2000 scene sizes away: nothing is trusted
-        const float Ed = E * dmax, Fd = F * dmax, tolF = tol * F;
+        const float tol = 0.5f * kFlatBoxGrow * scale - 1e-6f * (omax + 2.f * scale);
+        const float Amin = tol > 0.f ? (E * dmax + (omax + scale) * F) / tol : kFltMax; // > F
         const float limE = ANY ? fmaf(tmax_any, F, E) : 0.f; // B <= lim (A + F) + E  <=>  B <= fma(lim, A, limE)
 
         uint32_t m0 = 0, m1 = 0; // candidate bits of triangles 0..31 / 32..63
         const float negE = -E;
-        // one triangle of the scan: sets `bit` in `m` iff  ((A <= F) | in_range) & (!trust | inside).  The predicate logic is
+        // one group of the scan: sets `bit` in `m` iff  ((A <= F) | in_range) & (A < Amin | inside).  The predicate logic is
         // written as PTX so that every compare folds its AND / OR into the FSETP (the C++ form compiles to a SEL per term).
         auto scan = [&](int k, uint32_t& m, uint32_t bit) {
             const FlatTri& T = P.t[k];
@@ -140,8 +141,6 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const __gr
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(A));
             const float rr = B * rcp; // A == 0 -> inf or NaN: untrusted below
             const float hx = fmaf(rr, dx, ox), hy = fmaf(rr, dy, oy), hz = fmaf(rr, dz, oz);
-            // trust <=> tl <= tr; false for A <= F (right side <= 0 < Ed) and for NaN
-            const float tl = fmaf(fabsf(rr), Fd, Ed), tr = fmaf(tol, A, -tolF);
             // 0 <= nom/denom <= lim  ==>  A <= F  or  (B + E >= 0  and  B - E <= lim (A + F))   (traverse_pooled.cuh)
 #define TRN_FLAT_BOX_PRED                                                                                                  \
     "setp.ge.f32 p, %1, %4;\n\t"        /* inside the grown box */                                                          \
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const __gr
     "setp.le.and.f32 p, %1, %7, p;\n\t"                                                                                     \
     "setp.le.and.f32 p, %2, %8, p;\n\t"                                                                                     \
     "setp.le.and.f32 p, %3, %9, p;\n\t"                                                                                     \
-    "setp.gtu.or.f32 p, %10, %11, p;\n\t" /* ... or the box test is not trusted */                                          \
+    "setp.ltu.or.f32 p, %10, %11, p;\n\t" /* ... or the box test is not trusted: A < Amin (or NaN) */                                          \
     "setp.ge.f32 q, %12, %13;\n\t"        /* B >= -E */
             if constexpr (ANY) {
                 const float blim = fmaf(tmax_any, A, limE); // B <= lim A + (lim F + E)
@@ -161,7 +160,7 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const __gr
                     "@p or.b32 %0, %0, %16;\n\t}"
                     : "+r"(m)
                     : "f"(hx), "f"(hy), "f"(hz), "f"(T.blo[0]), "f"(T.blo[1]), "f"(T.blo[2]), "f"(T.bhi[0]), "f"(T.bhi[1]), "f"(T.bhi[2]),
-                      "f"(tl), "f"(tr), "f"(B), "f"(negE), "f"(A), "f"(F), "r"(bit), "f"(blim));
+                      "f"(A), "f"(Amin), "f"(B), "f"(negE), "f"(A), "f"(F), "r"(bit), "f"(blim));
             } else {
                 asm("{\n\t.reg .pred p, q;\n\t" TRN_FLAT_BOX_PRED
                     "setp.le.or.f32 q, %14, %15, q;\n\t" // ... or A <= F
@@ -169,7 +168,7 @@ __global__ void __launch_bounds__(128) trace_flat_kernel(DevScene sc, const __gr
                     "@p or.b32 %0, %0, %16;\n\t}"
                     : "+r"(m)
                     : "f"(hx), "f"(hy), "f"(hz), "f"(T.blo[0]), "f"(T.blo[1]), "f"(T.blo[2]), "f"(T.bhi[0]), "f"(T.bhi[1]), "f"(T.bhi[2]),
-                      "f"(tl), "f"(tr), "f"(B), "f"(negE), "f"(A), "f"(F), "r"(bit));
+                      "f"(A), "f"(Amin), "f"(B), "f"(negE), "f"(A), "f"(F), "r"(bit));
             }
         };
         if (valid) {
