@@ -368,6 +368,22 @@ __device__ __forceinline__ bool traverse_pairs(const DevScene& sc, float ox, flo
 
 // ---------------------------------------------------------------------- kernels
 
+__device__ __forceinline__ uint32_t pixel_of(const FrameParams& fp, uint64_t first_local_index, uint32_t rel,
+                                             uint32_t& sample_i) {
+    const uint64_t gl = first_local_index + rel;
+    uint32_t pixel, j;
+    if ((gl >> 32) == 0) { // (a 64-bit division costs ~100 instructions: 9 % of the last wave's shading)
+        const uint32_t g = static_cast<uint32_t>(gl), nl = static_cast<uint32_t>(fp.n_local);
+        pixel = g / nl;
+        j = g - pixel * nl;
+    } else {
+        pixel = static_cast<uint32_t>(gl / static_cast<uint32_t>(fp.n_local));
+        j = static_cast<uint32_t>(gl % static_cast<uint32_t>(fp.n_local));
+    }
+    sample_i = fp.sample_begin + j * fp.sample_stride;
+    return pixel;
+}
+
 // raygen: one thread per primary sample of the batch. Batch-relative index rel -> (pixel, local sample j) ->
 // jittered raster position -> Camera::raster2cam (lib/types.h:119-123). Jitter = the reference's per-row
 // xorshift64star<float>(42) stream (main.cpp:201-206), precomputed on the host as a [width][pps][2] table
@@ -376,10 +392,8 @@ __global__ void __launch_bounds__(256) raygen_kernel(FrameParams fp, const float
                                                      uint64_t first_local_index, uint32_t count, RayWave out) {
     const uint32_t rel = blockIdx.x * blockDim.x + threadIdx.x;
     if (rel >= count) return;
-    const uint64_t gl = first_local_index + rel;
-    const uint32_t pixel = static_cast<uint32_t>(gl / static_cast<uint32_t>(fp.n_local));
-    const uint32_t j = static_cast<uint32_t>(gl % static_cast<uint32_t>(fp.n_local));
-    const uint32_t i = fp.sample_begin + j * fp.sample_stride;
+    uint32_t i;
+    const uint32_t pixel = pixel_of(fp, first_local_index, rel, i);
     const int x = static_cast<int>(pixel % static_cast<uint32_t>(fp.width));
     const int y = static_cast<int>(pixel / static_cast<uint32_t>(fp.width));
     const float2 jit = __ldg(&jitter[static_cast<size_t>(x) * fp.pps + i]);
@@ -479,15 +493,6 @@ struct WaveCounters {
 __device__ __forceinline__ void accumulate(float4* acc, uint32_t pixel, float4 v) {
     if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) return;
     atomicAdd(acc + pixel, v); // red.global.add.v4.f32 (sm_90+)
-}
-
-__device__ __forceinline__ uint32_t pixel_of(const FrameParams& fp, uint64_t first_local_index, uint32_t rel,
-                                             uint32_t& sample_i) {
-    const uint64_t gl = first_local_index + rel;
-    const uint32_t pixel = static_cast<uint32_t>(gl / static_cast<uint32_t>(fp.n_local));
-    const uint32_t j = static_cast<uint32_t>(gl % static_cast<uint32_t>(fp.n_local));
-    sample_i = fp.sample_begin + j * fp.sample_stride;
-    return pixel;
 }
 
 // shade/bounce (pathtracer.cpp:26-101 in throughput form): per ray of the wave
@@ -637,6 +642,9 @@ __global__ void __launch_bounds__(256) shade_bounce_kernel(DevScene sc, FramePar
 
     const uint64_t sample_index = static_cast<uint64_t>(pixel) * static_cast<uint64_t>(fp.pps) + sample_i;
     const float fm = static_cast<float>(m);
+    // x / m == x * (1 / m) bit for bit when m is a power of two (-m 4 of every BASELINE config); an IEEE division is ~12 instructions
+    const bool m_pow2 = (m & (m - 1)) == 0;
+    const float inv_m = 1.f / fm;
     for (int k = 0; k < m; ++k) {
         const uint32_t child = node * static_cast<uint32_t>(m) + static_cast<uint32_t>(k) + 1u;
         uint64_t st = node_state(fp.seed, sample_index, child);
@@ -652,7 +660,7 @@ __global__ void __launch_bounds__(256) shade_bounce_kernel(DevScene sc, FramePar
         const float dx = m00 * lx + m01 * ly + m02 * lz;
         const float dy = m10 * lx + m11 * ly + m12 * lz;
         const float dz = m20 * lx + m21 * ly + m22 * lz;
-        const float wgt = (2.f * u1) / fm; // pathtracer.cpp:84,88,100-101: rho * 2 * (cos / m)
+        const float wgt = m_pow2 ? (2.f * u1) * inv_m : (2.f * u1) / fm; // pathtracer.cpp:84,88,100-101: rho * 2 * (cos / m)
         // k-major: every store of the loop is one contiguous run; child-major: the m rays that share an origin sit in
         // adjacent lanes of the next wave, so their walks down the tree touch the same lines (profiles/README.md)
         const uint32_t slot = fp.child_major ? cbase + rank * static_cast<uint32_t>(m) + static_cast<uint32_t>(k)
