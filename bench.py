@@ -561,6 +561,29 @@ def main():
             achieved = b_alg * pst.trace_queries / ms_trace / 1e6
             peak, bound, unit_note = peak_hbm, "hbm", "algorithmic bytes / kernel time"
         traffic, kernel_name, ncu_fig = None, ("trace_pooled_kernel<0>" if pooled else "trace_persistent_ww_kernel<0,false>"), None
+        unit = "GB/s"
+        flat_records = int(getattr(pst, "flat_records", 0))
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        flat = None
+        if flat_records > 0:
+            # One-leaf scene: the brute-force kernel (traverse_flat.cuh). Its triangle records are kernel parameters (constant
+            # bank) and its rays stream through once, so no memory level binds it: it is bound by the FP32 pipes. Algorithmic
+            # work of a query = its scan: every record costs 3 FMUL + 7 FFMA + 1 FADD + 1 MUFU (18 flop on the FMA pipe; the 9
+            # compares run on the ALU pipe beside it) -- the exact tests of the ~2 candidates per ray are not counted.
+            nt = (flat_records + 3) // 4 * 4
+            kernel_name = "trace_flat_kernel<0,%d>" % nt
+            flop_q = 18.0 * flat_records
+            achieved = flop_q * pst.trace_queries / ms_trace / 1e9
+            peak = 148 * 128 * 2 * sm_mhz / 1e6
+            bound, unit = "fp32", "TFLOP/s"
+            unit_note = ("scan flops (18 per record x %d records per query) / kernel time against the FFMA peak 148 SMs x 128 lanes x 2 x "
+                         "SM clock under load (MEASURED_PEAKS.json holds no fp32 figure)" % flat_records)
+            flat = {"records_per_query": flat_records, "flop_per_query": flop_q,
+                    # the FMA pipe issues one warp instruction per 2 cycles per SM sub-partition (B300_MICROARCH.md); the scan
+                    # alone needs 11 FMA-pipe instructions per record
+                    "fma_pipe_busy_frac_scan_only": 11.0 * flat_records / 32.0 * 2.0 * pst.trace_queries / (ms_trace * 1e-3)
+                                                    / (148 * 4 * sm_mhz * 1e6),
+                    "queries_per_s": pst.trace_queries / (ms_trace * 1e-3)}
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
             try:
@@ -569,11 +592,10 @@ def main():
                 ncu_fig = ent.get("ncu")
             except Exception:
                 traffic = None
-        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         fp32_rate = 37.0 * (rst.trace_tri_tests / rq) * pst.trace_queries / ms_trace / 1e6
         roofline = {
-            "bound": bound, "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "how": unit_note,
+            "bound": bound, "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": unit,
+            "frac": achieved / peak, "traffic": traffic, "how": unit_note, "brute_force": flat,
             "peaks_measured": peaks,
             "requested_bytes_per_query": b_req,
             "requested_per_query": ({k: v / q for k, v in zip(("walk_steps", "chunks", "tri_pretests", "exact_tests", "cold_records",

@@ -114,6 +114,9 @@ typedef struct trn_stats {
      * empty-space cuts (a subset of [0]), [9] unused */
     uint64_t trace_pooled[10];
     uint64_t shadow_pooled[10];
+    /* one-leaf scenes (the brute-force kernel, traverse_flat.cuh): scan records every query of this call was tested against
+     * -- a record is one triangle or one coplanar pair; 0 when another traversal kernel ran */
+    uint64_t flat_records;
 } trn_stats;
 
 typedef struct trn_scene_info {

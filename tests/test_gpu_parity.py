@@ -799,7 +799,15 @@ def test_device_built_tree_reference_view_and_render(api, ob, scenes):
         ro, rd = scenes.random_rays(sc, 40000, seed=12, inside=True)
         i1, r1 = o.intersect(ro, rd, 0)
         i2, r2 = o2.intersect(ro, rd, 0)
-        assert np.array_equal(i1, i2) and np.array_equal(bits(r1), bits(r2)), sc["name"]
+        # Same hit distance everywhere; the triangle may differ only on an EXACT tie in r (cornell_box: the boxes' bottom faces
+        # lie in the floor's plane). The reference's traversal has no per-cell hit range: in a deeper tree it can meet the
+        # floor triangle in a cell before the one that holds the hit point and keeps it (strict '<'), where its own one-leaf
+        # tree -- and the GPU on either tree, see the assertion below -- reports the lower id.
+        assert np.array_equal(bits(r1[:, 0]), bits(r2[:, 0])), sc["name"]
+        tie = i1 != i2
+        assert tie.mean() < 0.005 and np.array_equal(bits(r1[~tie]), bits(r2[~tie])), (sc["name"], int(tie.sum()))
+        ig, rg = p.intersect(ro, rd)
+        assert np.array_equal(ig, i1) and np.array_equal(bits(rg), bits(r1)), sc["name"]
         assert np.array_equal(np.array(p.info.box, np.float32).view(np.uint32), o.box.view(np.uint32))
         # and the renderer on the device-built tree gives the counter-seeded oracle's image
         _compare_counter_mode(api, ob, sc, p, o, 96, 3, 3, 2, bg=(0.2, 0.3, 0.4, 1))

@@ -61,7 +61,7 @@ class Stats(C.Structure):
                 ("trace_actual_tri_tests", C.c_uint64), ("shadow_actual_inner", C.c_uint64),
                 ("shadow_actual_leaf_nodes", C.c_uint64), ("shadow_actual_tri_tests", C.c_uint64),
                 ("ms_reduce", C.c_double), ("ms_d2h", C.c_double),
-                ("trace_pooled", C.c_uint64 * 10), ("shadow_pooled", C.c_uint64 * 10)]
+                ("trace_pooled", C.c_uint64 * 10), ("shadow_pooled", C.c_uint64 * 10), ("flat_records", C.c_uint64)]
 
 
 class SceneInfo(C.Structure):

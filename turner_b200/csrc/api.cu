@@ -1081,6 +1081,7 @@ static int render_on_device(trn_scene* scene, int device, const trn_camera* cam,
         stats->trace_launches = r.trace_launches;
         stats->trace_queries = r.trace_queries;
         stats->shadow_launches = r.shadow_launches;
+        stats->flat_records = (r.mode_closest == 4 && !r.counting) ? ds->flat_groups : 0;
         if (r.counting) {
             unsigned long long v[kVisitSlots];
             cudaMemcpy(v, ds->d_visits, sizeof v, cudaMemcpyDeviceToHost);
