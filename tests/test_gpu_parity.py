@@ -896,6 +896,7 @@ def test_device_builder_degenerate_and_awkward_inputs(api, ob, scenes):
 def _quad_room(flip_every=2, jitter=0.0, seed=0):
     """a closed room of axis-aligned and rotated quads, each split into two triangles -- every other quad with its second
     triangle wound the other way (opposite normal, same plane), optionally with one vertex pushed off the plane"""
+    from turner_b200.scenes import look_at_camera
     rng = np.random.RandomState(seed)
     quads = []
     L = 1.0
@@ -928,7 +929,8 @@ def _quad_room(flip_every=2, jitter=0.0, seed=0):
     n = V.shape[0]
     return {"name": "quad_room_%d_%g" % (flip_every, jitter), "vertices": V.reshape(-1, 9),
             "normals": np.repeat(g[:, None, :], 3, 1).astype(np.float32).reshape(-1, 9),
-            "diffuse": np.full((n, 4), 0.6, np.float32), "camera": None, "light": {"pos": [0.0, 0.9, 0.0], "color": [1, 1, 1, 1]}}
+            "diffuse": np.full((n, 4), 0.6, np.float32), "camera": look_at_camera((0.0, 0.0, 0.9), (0.0, 0.0, 0.0)),
+            "light": {"pos": [0.0, 0.9, 0.0], "color": [1, 1, 1, 1]}}
 
 
 def test_one_leaf_scenes_brute_force_kernel(api, ob, scenes, monkeypatch):
@@ -939,9 +941,18 @@ def test_one_leaf_scenes_brute_force_kernel(api, ob, scenes, monkeypatch):
              ((33, 3, 1.0, 2.0), (40, 4, 1.0, 2.0), (50, 5, 1.0, 3.0), (64, 6, 0.5, 2.0), (7, 7, 1.0, 2.0), (1, 8, 1.0, 2.0))]
     cases += [_quad_room(2, 0.0), _quad_room(1, 0.0), _quad_room(2, 1e-6, seed=1), _quad_room(3, 1e-3, seed=2), scenes.fixture("cornell_box")]
     total = 0
+    # scan records (trn_stats.flat_records): a soup pairs nothing; the axis-aligned walls of the quad rooms pair whatever their
+    # winding (the free-standing rectangles only where fp32 rounding left the two normals within 8 ulp); cornell_box has 16
+    # planar quads + one folded quad (two records)
+    want_records = {"soup_33_3": (33, 33), "soup_64_6": (64, 64), "soup_1_8": (1, 1), "quad_room_2_0": (16, 26), "quad_room_1_0": (16, 26),
+                    "cornell_box.blend": (20, 20)}
     for sc in cases:
         p = api.Scene.from_dict(sc)
         assert p.height == 0, sc["name"]
+        if sc["name"] in want_records and sc.get("camera") is not None:
+            cam, cfg = api.make_config(sc, 32, max_depth=1, mc_samples=1, pixel_samples=1, seed=1)
+            got = p.render(cam, cfg)[1].flat_records
+            assert want_records[sc["name"]][0] <= got <= want_records[sc["name"]][1], (sc["name"], got)
         o = ob.OracleScene(sc["vertices"], sc["normals"], sc["diffuse"])
         V = sc["vertices"].reshape(-1, 3, 3)
         size = float(np.abs(V).max())

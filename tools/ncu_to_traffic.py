@@ -3,7 +3,7 @@
 
     python tools/ncu_to_traffic.py gpurun_out/r2_prof_pooled_mesh1m.ncu-rep mesh1m [summary.txt]
 
-Takes the longest launch of the dominant kernel (trace_pooled_kernel<0,...> on the mesh, trace_persistent_ww_kernel<0,...> on
+Takes the longest launch of the dominant kernel (trace_pooled_kernel<0,...> on the mesh, trace_flat_kernel<0,...> on
 cornell_box) out of an `ncu --set full --clock-control none` capture and writes the per-launch figures bench.py copies into
 its JSON line (a bench never runs under the profiler): DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum), duration,
 instructions, lanes per instruction, issue-slot / l1tex / LSU-data-pipe / lts utilisation, L1 and L2 hit rates."""
@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, workload = sys.argv[1], sys.argv[2]
-kernel_key = {"mesh1m": "trace_pooled_kernel<0", "cornell": "trace_persistent_ww_kernel<0"}[workload]
+kernel_key = {"mesh1m": "trace_pooled_kernel<0", "cornell": "trace_flat_kernel<0"}[workload]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
