@@ -942,10 +942,10 @@ def test_one_leaf_scenes_brute_force_kernel(api, ob, scenes, monkeypatch):
     cases += [_quad_room(2, 0.0), _quad_room(1, 0.0), _quad_room(2, 1e-6, seed=1), _quad_room(3, 1e-3, seed=2), scenes.fixture("cornell_box")]
     total = 0
     # scan records (trn_stats.flat_records): a soup pairs nothing; the axis-aligned walls of the quad rooms pair whatever their
-    # winding (the free-standing rectangles only where fp32 rounding left the two normals within 8 ulp); cornell_box has 16
-    # planar quads + one folded quad (two records)
+    # winding (the free-standing rectangles only where fp32 rounding left the two normals within 8 ulp); cornell_box's 36 triangles
+    # make 17 pairs + 2 single triangles
     want_records = {"soup_33_3": (33, 33), "soup_64_6": (64, 64), "soup_1_8": (1, 1), "quad_room_2_0": (16, 26), "quad_room_1_0": (16, 26),
-                    "cornell_box.blend": (20, 20)}
+                    "cornell_box.blend": (19, 19)}
     for sc in cases:
         p = api.Scene.from_dict(sc)
         assert p.height == 0, sc["name"]
