@@ -57,3 +57,27 @@ def test_pooled_cycle_matches_per_ray_traversal(emulator, tmp_path, n):
     for depth, rays, occluded, completed, diff in shadows:
         assert completed == "1" and diff == "0" and int(rays) > 0, out
     assert sum(int(s[2]) for s in shadows) > 0  # some rays are occluded
+
+
+def test_pooled_cycle_on_a_device_built_tree(emulator, tmp_path):
+    """The production tree of the benchmark is DEVICE-built (kdtree_build_gpu.cu): other shape, empty-space cuts everywhere.
+    tests/golden/kd_gpu_cubesphere32.bin.gz is such a tree, written on a B200 by tools/jobs/dump_small.sh (TRN_KD_DUMP) for
+    scenes.cubesphere(32). On the CPU this pins (a) that it is a correct tree -- the per-ray traversal finds what the
+    exhaustive search over all 12 288 triangles finds, ties included -- and (b) the pooled cycle on it (closest hit and
+    any-hit), void leaves and cut chains included."""
+    import gzip
+    from turner_b200 import scenes
+    mesh, tree = str(tmp_path / "mesh.bin"), str(tmp_path / "tree.bin")
+    _write_mesh(mesh, scenes.cubesphere(32))
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "kd_gpu_cubesphere32.bin.gz")) as f, open(tree, "wb") as g:
+        g.write(f.read())
+    out = subprocess.run([emulator, mesh, "12", tree, "1"], check=True, capture_output=True, text=True, timeout=600).stdout
+    brute = re.findall(r"brute (\d): (\d+) rays, differences (\d+), exact ties resolved differently (\d+)", out)
+    assert len(brute) == 3 and all(b[2] == "0" and b[3] == "0" for b in brute), out
+    lines = re.findall(r"depth (\d): (\d+) rays, (\d+) hits, completed (\d), id differences (\d+), \(r,s,t\) bit differences (\d+)", out)
+    assert len(lines) == 3 and all(l[3] == "1" and l[4] == "0" and l[5] == "0" and int(l[2]) > 0 for l in lines), out
+    shadows = re.findall(r"shadow (\d): (\d+) rays, (\d+) occluded, completed (\d), differences (\d+)", out)
+    assert len(shadows) == 3 and all(s[3] == "1" and s[4] == "0" for s in shadows), out
+    # the walk really met cut-off voids (the host-built tree of this mesh has hardly any)
+    voids = [float(v) for v in re.findall(r"waiting at a void ([0-9.]+)", out)]
+    assert max(voids) > 0.5, out

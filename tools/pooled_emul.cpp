@@ -4,7 +4,9 @@
 // traversal on the benchmark mesh without spending GPU time.
 //
 //   g++ -O2 -std=c++17 -ffp-contract=off -fopenmp tools/pooled_emul.cpp turner_b200/csrc/kdtree_build.o -o /tmp/sim/pooled_emul
-//   /tmp/sim/pooled_emul /tmp/sim/mesh1m.bin [rows]
+//   /tmp/sim/pooled_emul /tmp/sim/mesh1m.bin [rows] [device-built tree | -] [1 = also compare with the exhaustive search]
+// The optional third argument is a pair-layout tree written by the device builder under TRN_KD_DUMP=<file>
+// (kdtree_build_gpu.cu): the emulated warp then walks the production tree of the benchmark instead of the host-built one.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -199,6 +201,33 @@ struct F4 {
     float x, y, z, w;
 };
 
+// exhaustive closest hit over ALL triangles with the exact sequence (no tree): what any correct tree must return, up to which
+// of several triangles reports an exact tie in r
+static void trace_brute(const Scene& sc, const Ray& ray, Hit& out) {
+    const float ox = ray.o[0], oy = ray.o[1], oz = ray.o[2], dx = ray.d[0], dy = ray.d[1], dz = ray.d[2];
+    out = Hit();
+    for (uint32_t id = 0; id < sc.tris.count; ++id) {
+        const float* q = &sc.tris.isect[size_t(id) * 16];
+        const float nx = q[3], ny = q[4], nz = q[5];
+        const float denom = nx * dx + ny * dy + nz * dz;
+        if (denom == 0.f) continue;
+        const float nom = nx * (q[0] - ox) + ny * (q[1] - oy) + nz * (q[2] - oz);
+        const float r = nom / denom;
+        if (!(r >= 0.f) || !(r < out.r)) continue;
+        const float wx = (ox + r * dx) - q[0], wy = (oy + r * dy) - q[1], wz = (oz + r * dz) - q[2];
+        const float wv = wx * q[9] + wy * q[10] + wz * q[11];
+        const float wu = wx * q[6] + wy * q[7] + wz * q[8];
+        const float s = (q[12] * wv - q[13] * wu) / q[15];
+        if (s < 0.f) continue;
+        const float t = (q[12] * wu - q[14] * wv) / q[15];
+        if (t < 0.f || 1.f < s + t) continue;
+        out.id = id;
+        out.r = r;
+        out.s = s;
+        out.t = t;
+    }
+}
+
 // one emulated warp over rays[begin, end); returns false on a detected hang
 // any: MODE 1 of the kernel (shadow rays: occluded <=> an accepted triangle with 0 <= r <= tmax); hits[i].id is then 0 for
 // occluded, kMiss for unoccluded
@@ -334,6 +363,12 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
             if (last) break;
             ++it;
             stat[0]++;
+            for (int lane = 0; lane < 32; ++lane) { // what the 32 lanes do in this iteration (after the leaf block)
+                const LaneS& l = L[lane];
+                const bool leaf = (l.ny & 3u) == 3u;
+                const int k = !l.busy ? 0 : (!l.walking ? 1 : (blocked[lane] ? 2 : (leaf ? ((l.ny >> 2) == 0u ? 3 : 4) : 5)));
+                stat[8 + k]++;
+            }
             for (int lane = 0; lane < 32; ++lane) {
                 if (!(can[lane] && !at_leaf[lane])) continue;
                 LaneS& l = L[lane];
@@ -491,6 +526,7 @@ static bool warp_run(const Scene& sc, const std::vector<Ray>& rays, size_t begin
 int main(int argc, char** argv) {
     const char* path = argc > 1 ? argv[1] : "/tmp/sim/mesh1m.bin";
     const int rows = argc > 2 ? std::atoi(argv[2]) : 16;
+    const bool brute = argc > 4 && std::atoi(argv[4]) != 0; // also check the per-ray traversal against the exhaustive search
     FILE* f = std::fopen(path, "rb");
     if (!f) return 1;
     uint32_t n = 0;
@@ -500,7 +536,27 @@ int main(int argc, char** argv) {
     std::fclose(f);
     Scene sc;
     precompute_triangles(V.data(), N.data(), D.data(), n, sc.tris);
-    build_kdtree(sc.tris, sc.tree, 0);
+    if (argc > 3 && std::strcmp(argv[3], "-") != 0) {
+        // the production tree of a device build (TRN_KD_DUMP): u64 pair-node count, u64 reference count, nodes, references
+        FILE* g = std::fopen(argv[3], "rb");
+        uint64_t hdr[2] = {0, 0};
+        if (!g || std::fread(hdr, 8, 2, g) != 2 || hdr[0] < 2 || hdr[0] > (1ull << 31) || hdr[1] > (1ull << 32)) return 2;
+        sc.tree.pair_nodes.resize(hdr[0]);
+        sc.tree.pair_leaf_refs.resize(hdr[1]);
+        if (std::fread(sc.tree.pair_nodes.data(), 8, hdr[0], g) != hdr[0] || std::fread(sc.tree.pair_leaf_refs.data(), 4, hdr[1], g) != hdr[1]) return 2;
+        std::fclose(g);
+        for (int c = 0; c < 3; ++c) { // scene box as KDTree::KDTree makes it: min / max over the vertices
+            float lo = V[c], hi = V[c];
+            for (size_t i = 0; i < size_t(n) * 3; ++i) {
+                lo = std::fmin(lo, V[i * 3 + c]);
+                hi = std::fmax(hi, V[i * 3 + c]);
+            }
+            sc.tree.box[c] = lo;
+            sc.tree.box[3 + c] = hi;
+        }
+    } else {
+        build_kdtree(sc.tris, sc.tree, 0);
+    }
     sc.planes.resize(size_t(n) * 4);
     for (size_t i = 0; i < n; ++i) {
         const float* q = &sc.tris.isect[i * 16];
@@ -537,16 +593,16 @@ int main(int argc, char** argv) {
         for (long i = 0; i < long(wave.size()); ++i) trace_plain(sc, wave[i], ref[i]);
         const size_t per = 4096;
         const long nw = long((wave.size() + per - 1) / per);
-        uint64_t stat[8] = {0};
+        uint64_t stat[16] = {0};
         bool ok = true;
 #pragma omp parallel for schedule(dynamic, 1)
         for (long w = 0; w < nw; ++w) {
-            uint64_t st[8] = {0};
+            uint64_t st[16] = {0};
             const bool r = warp_run(sc, wave, size_t(w) * per, std::min(wave.size(), size_t(w + 1) * per), got, 28, 12, 10, st);
 #pragma omp critical
             {
                 ok &= r;
-                for (int k = 0; k < 8; ++k) stat[k] += st[k];
+                for (int k = 0; k < 16; ++k) stat[k] += st[k];
             }
         }
         size_t id_diff = 0, bit_diff = 0, hits = 0;
@@ -555,6 +611,19 @@ int main(int argc, char** argv) {
             if (ref[i].id != got[i].id) ++id_diff;
             else if (ref[i].id != kMiss && (fbits(ref[i].r) != fbits(got[i].r) || fbits(ref[i].s) != fbits(got[i].s) || fbits(ref[i].t) != fbits(got[i].t))) ++bit_diff;
         }
+        if (brute) {
+            // the tree itself (a device-built one comes from outside): the per-ray traversal against the exhaustive search
+            size_t bd = 0, ties = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : bd, ties)
+            for (long i = 0; i < long(wave.size()); ++i) {
+                Hit b;
+                trace_brute(sc, wave[i], b);
+                if (b.id == ref[i].id) continue;
+                if (b.id != kMiss && ref[i].id != kMiss && fbits(b.r) == fbits(ref[i].r)) ++ties;
+                else ++bd;
+            }
+            std::printf("brute %d: %zu rays, differences %zu, exact ties resolved differently %zu\n", depth, wave.size(), bd, ties);
+        }
         const double nr = double(wave.size());
         std::printf("depth %d: %zu rays, %zu hits, completed %d, id differences %zu, (r,s,t) bit differences %zu\n", depth, wave.size(), hits,
                     int(ok), id_diff, bit_diff);
@@ -562,6 +631,12 @@ int main(int argc, char** argv) {
                     "tests %.1f survivors %.2f\n",
                     stat[0] / nr, double(stat[1]) / std::max<uint64_t>(1, stat[0]), stat[2] / nr, double(stat[3]) / std::max<uint64_t>(1, stat[2]),
                     stat[4] / nr, double(stat[5]) / std::max<uint64_t>(1, stat[4]), stat[6] / nr, stat[5] / nr);
+        {
+            const double its = double(std::max<uint64_t>(1, stat[0]));
+            std::printf("   lanes per walk iteration: idle %.1f, walk over %.1f, leaf continues next cycle %.1f, waiting at a void %.1f, "
+                        "waiting at a leaf %.1f, stepping %.1f\n",
+                        stat[8] / its, stat[9] / its, stat[10] / its, stat[11] / its, stat[12] / its, stat[13] / its);
+        }
         {
             // shadow wave of this depth (pathtracer.cpp:44-58): from the offset hit point towards the light of
             // scenes.cubesphere(), inclusive tmax = distance to the light; any-hit mode of the kernel vs the plain traversal
@@ -592,7 +667,7 @@ int main(int argc, char** argv) {
             bool sok = true;
 #pragma omp parallel for schedule(dynamic, 1)
             for (long w = 0; w < snw; ++w) {
-                uint64_t st[8] = {0};
+                uint64_t st[16] = {0};
                 const bool r = warp_run(sc, sh, size_t(w) * per, std::min(sh.size(), size_t(w + 1) * per), sgot, 28, 12, 10, st, true);
 #pragma omp critical
                 sok &= r;

@@ -869,6 +869,19 @@ int build_kdtree_gpu(const HostTriangles& tris, KdTree& out, int device, std::st
         rc = build_impl(tris, out, device, err, budget, t0);
         if (rc != -5) break;
     }
+    // development aid (tools/pooled_emul.cpp replays the production tree on the CPU): TRN_KD_DUMP=<file> writes the pair
+    // layout -- u64 pair-node count, u64 reference count, the nodes, the references
+    if (rc == 0) {
+        if (const char* path = std::getenv("TRN_KD_DUMP")) {
+            if (FILE* f = std::fopen(path, "wb")) {
+                const uint64_t hdr[2] = {out.pair_nodes.size(), out.pair_leaf_refs.size()};
+                std::fwrite(hdr, 8, 2, f);
+                std::fwrite(out.pair_nodes.data(), 8, out.pair_nodes.size(), f);
+                std::fwrite(out.pair_leaf_refs.data(), 4, out.pair_leaf_refs.size(), f);
+                std::fclose(f);
+            }
+        }
+    }
     return rc;
 }
 
