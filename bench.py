@@ -165,10 +165,11 @@ def alg_bytes(inner, leaf_nodes, tri_tests, queries):
 
 def requested_bytes(pc, queries):
     """bytes the pooled schedule itself requests through L1 (trn_stats.trace_pooled, include/turner_b200.h): 16 per walk
-    step (node pair), 16 + 4*16 per chunk (id vector + four plane records), 32 per exact test (+32 with the cold record),
+    step (node pair), 4*16 per chunk (the four plane records behind the leaf's references, one 64-byte block) + 16 for the id
+    vector of a chunk with a pre-filter survivor (at most one per exact test), 32 per exact test (+32 with the cold record),
     16 per stack push / pop (local memory), 32 ray in + 16 hit out per query"""
     steps, chunks, tris, exact, cold, push, pop = [int(x) for x in list(pc)[:7]]
-    return 16 * steps + 80 * chunks + 32 * exact + 32 * cold + 16 * (push + pop) + 48 * queries
+    return 16 * steps + 64 * chunks + 16 * min(chunks, exact) + 32 * exact + 32 * cold + 16 * (push + pop) + 48 * queries
 
 
 def cpu_reference_run(name, sc, nodes, box, steps=1, warmup=0, budget_s=100.0):

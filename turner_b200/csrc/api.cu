@@ -100,7 +100,7 @@ struct DeviceScene {
     void* d_isect_hot = nullptr;
     void* d_isect_cold = nullptr;
     void* d_tri_box = nullptr;
-    void* d_planes = nullptr; // float4 per triangle: unit normal, n.v0 -- the pre-filter record of the pooled kernels
+    void* d_planes = nullptr; // float4 per leaf REFERENCE: unit normal, n.v0 of its triangle -- the pre-filter record of the pooled kernels
     void* d_shade = nullptr;
     void* d_mirror = nullptr;
     uint32_t* d_child_slot = nullptr; // raytracer: child-ray slot of every shadow query
@@ -329,7 +329,18 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
             pl[i * 4 + 2] = q[5];
             pl[i * 4 + 3] = static_cast<float>(static_cast<double>(q[3]) * q[0] + static_cast<double>(q[4]) * q[1] + static_cast<double>(q[5]) * q[2]);
         }
+#if TRN_PQ_REFPLANES
+        { // one plane record per leaf REFERENCE, in the order of the (padded) reference array: the pooled kernel reads a chunk's
+          // four planes as one 64-byte block and the ids only for pre-filter survivors (16 B x 3.06 M references = 49 MB on the
+          // benchmark's device-built tree; +4 % whole-job throughput over the per-triangle array, profiles/README.md)
+            const auto& refs = sc->tree.pair_leaf_refs;
+            std::vector<float> pr(refs.size() * 4);
+            for (size_t j = 0; j < refs.size(); ++j) std::memcpy(&pr[j * 4], &pl[static_cast<size_t>(refs[j]) * 4], 16);
+            CUDA_TRY(up(&ds->d_planes, pr.data(), pr.size() * sizeof(float)));
+        }
+#else
         CUDA_TRY(up(&ds->d_planes, pl.data(), pl.size() * sizeof(float)));
+#endif
         if (nt <= static_cast<size_t>(kFlatMaxTris)) flat_planes = pl;
     }
     CUDA_TRY(up(&ds->d_shade, sc->tris.shade.data(), sc->tris.shade.size() * sizeof(float)));

@@ -67,6 +67,9 @@ struct PooledWarpSmem {
 #ifndef TRN_PQ_TRI_HINT
 #define TRN_PQ_TRI_HINT 0 // 1: id vectors and plane records are loaded L1::evict_first
 #endif
+#ifndef TRN_PQ_REFPLANES
+#define TRN_PQ_REFPLANES 1 // plane records per leaf REFERENCE: a chunk's four planes are one 64-byte block behind the leaf's first
+#endif                     // reference (two 32-byte loads, no id -> plane gather); 0 = per triangle, through the ids (A/B, profiles/README.md)
 #ifndef TRN_PQ_TREELET
 #define TRN_PQ_TREELET 0 // node pairs of the top treelet staged in shared memory per CTA (0 = off; A/B in profiles/README.md)
 #endif
@@ -455,8 +458,17 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                     const float c1 = fmaf(-lo, F, -E), c2 = fmaf(hi, F, E);
                     // leaf runs start at multiples of 4 references and the array is padded (kdtree_build.cpp): one 16-byte
                     // load brings the chunk's ids; ids beyond cnt are valid triangles whose result is masked
+#if TRN_PQ_REFPLANES
+                    // one plane record per reference, in the order of the reference array (leaf runs start at multiples of 4 and
+                    // the array is padded): the chunk's planes are one aligned 64-byte block, fetched as two LDG.E.256
+                    struct alignas(32) F8 { float4 a, b; };
+                    const float4* pr = planes + first + off0;
+                    const F8 v0 = *reinterpret_cast<const F8*>(pr), v1 = *reinterpret_cast<const F8*>(pr + 2);
+                    const float4 p0 = v0.a, p1 = v0.b, p2 = v1.a, p3 = v1.b;
+#else
                     ids = ld_tri(reinterpret_cast<const uint4*>(sc.prefs + first + off0));
                     const float4 p0 = ld_tri(&planes[ids.x]), p1 = ld_tri(&planes[ids.y]), p2 = ld_tri(&planes[ids.z]), p3 = ld_tri(&planes[ids.w]);
+#endif
                     if (COUNT) {
                         pc.chunks += 1;
                         pc.tris += cnt;
@@ -472,6 +484,9 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                         const bool keep = (static_cast<uint32_t>(k) < cnt) & ((A <= F) | ((B >= fmaf(lo, A, c1)) & (B <= fmaf(hi, A, c2))));
                         km |= keep ? (1u << k) : 0u;
                     }
+#if TRN_PQ_REFPLANES
+                    if (km != 0u) ids = ld_tri(reinterpret_cast<const uint4*>(sc.prefs + first + off0)); // ids only for survivors
+#endif
                 }
                 // append the survivors of the round, k-major (the order inside the queue is irrelevant: seq carries the
                 // visiting order): four ballots, no scan, no atomics
