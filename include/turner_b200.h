@@ -108,7 +108,7 @@ typedef struct trn_stats {
     double ms_reduce;
     double ms_d2h;
     /* counting mode, pooled traversal kernel (trees with >= 1024 leaves): what the production schedule itself issues --
-     * [0] walk steps (one 16-byte node-pair load each), [1] chunks (one 16-byte id vector + four 16-byte plane records),
+     * [0] walk steps (one 16-byte node-pair load each), [1] chunks (four 16-byte plane records = one 64-byte block; + one 16-byte id vector if a triangle survives the pre-filter),
      * [2] triangle pre-tests (valid ids of the chunks), [3] exact tests (32-byte hot record), [4] of those with the
      * 32-byte cold record, [5] stack pushes, [6] pops (16 bytes of local memory each), [7] leaves, [8] walk steps at
      * empty-space cuts (a subset of [0]), [9] unused */
