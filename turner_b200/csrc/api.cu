@@ -97,8 +97,6 @@ struct DeviceScene {
     void* d_refs = nullptr;
     void* d_pnodes = nullptr;
     void* d_prefs = nullptr;
-    void* d_arena = nullptr; // TRN_L2_PERSIST: one allocation behind d_pnodes / d_prefs / d_planes
-    size_t arena_bytes = 0;
     void* d_isect_hot = nullptr;
     void* d_isect_cold = nullptr;
     void* d_tri_box = nullptr;
@@ -163,10 +161,6 @@ struct DeviceScene {
         cudaSetDevice(device);
         cudaFree(d_nodes);
         cudaFree(d_refs);
-        if (d_arena) { // pnodes / prefs / planes are slices of it
-            cudaFree(d_arena);
-            d_arena = d_pnodes = d_prefs = d_planes = nullptr;
-        }
         cudaFree(d_pnodes);
         cudaFree(d_prefs);
         cudaFree(d_isect_hot);
@@ -294,24 +288,10 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     std::unique_ptr<DeviceScene> ds(new DeviceScene);
     ds->device = device;
     auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
-        if (!*dst) { // (already set: a slice of the arena below)
-            cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
-            if (e != cudaSuccess) return e;
-        }
+        cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) return e;
         return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
     };
-    // TRN_L2_PERSIST=1 (A/B): node pairs, references and plane records -- what the walk and the pre-filter gather from -- in ONE
-    // allocation, so that one access-policy window can keep them resident in L2 while the ray waves stream through it
-    if (env_u64("TRN_L2_PERSIST", 0) != 0) {
-        auto r256 = [](size_t b) { return (std::max<size_t>(b, 16) + 255) & ~static_cast<size_t>(255); };
-        const size_t b0 = r256(sc->tree.pair_nodes.size() * sizeof(uint64_t)), b1 = r256(sc->tree.pair_leaf_refs.size() * sizeof(uint32_t)),
-                     b2 = r256(sc->tree.pair_leaf_refs.size() * 16);
-        CUDA_TRY(cudaMalloc(&ds->d_arena, b0 + b1 + b2));
-        ds->arena_bytes = b0 + b1 + b2;
-        ds->d_pnodes = ds->d_arena;
-        ds->d_prefs = static_cast<char*>(ds->d_arena) + b0;
-        ds->d_planes = static_cast<char*>(ds->d_arena) + b0 + b1;
-    }
     if (sc->reference_shape) { // only the instrumented reference-schedule twins read these (upload_reference_shape otherwise)
         CUDA_TRY(up(&ds->d_nodes, sc->gpu_nodes.data(), sc->gpu_nodes.size() * sizeof(uint2)));
         CUDA_TRY(up(&ds->d_refs, sc->leaf_refs.data(), sc->leaf_refs.size() * sizeof(uint32_t)));
@@ -480,24 +460,6 @@ static int get_device_scene(trn_scene* sc, int device, DeviceScene** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream_b, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&ds->stream_copy, cudaStreamNonBlocking));
-    if (ds->d_arena) {
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
-        const size_t carve = std::min<size_t>(static_cast<size_t>(max_persist), ds->arena_bytes);
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
-        cudaStreamAttrValue av{};
-        av.accessPolicyWindow.base_ptr = ds->d_arena;
-        av.accessPolicyWindow.num_bytes = std::min<size_t>(ds->arena_bytes, static_cast<size_t>(max_window));
-        av.accessPolicyWindow.hitRatio = std::min(1.0f, static_cast<float>(carve) / static_cast<float>(std::max<size_t>(1, av.accessPolicyWindow.num_bytes)));
-        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaStreamSetAttribute(ds->stream, cudaStreamAttributeAccessPolicyWindow, &av);
-        cudaStreamSetAttribute(ds->stream_b, cudaStreamAttributeAccessPolicyWindow, &av);
-        if (std::getenv("TRN_KD_DEBUG"))
-            std::fprintf(stderr, "[l2] arena %.1f MB, persisting carve-out %.1f MB (max %.1f), window max %.1f MB, hit ratio %.2f\n", ds->arena_bytes / 1e6,
-                         carve / 1e6, max_persist / 1e6, max_window / 1e6, av.accessPolicyWindow.hitRatio);
-    }
     CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_shaded, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_shadow_done[0], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&ds->ev_shadow_done[1], cudaEventDisableTiming));

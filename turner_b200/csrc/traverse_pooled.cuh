@@ -70,9 +70,6 @@ struct PooledWarpSmem {
 #ifndef TRN_PQ_REFPLANES
 #define TRN_PQ_REFPLANES 1 // plane records per leaf REFERENCE: a chunk's four planes are one 64-byte block behind the leaf's first
 #endif                     // reference (two 32-byte loads, no id -> plane gather); 0 = per triangle, through the ids (A/B, profiles/README.md)
-#ifndef TRN_PQ_IDEARLY
-#define TRN_PQ_IDEARLY 0
-#endif
 #ifndef TRN_PQ_TREELET
 #define TRN_PQ_TREELET 0 // node pairs of the top treelet staged in shared memory per CTA (0 = off; A/B in profiles/README.md)
 #endif
@@ -466,9 +463,6 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                     // the array is padded): the chunk's planes are one aligned 64-byte block, fetched as two LDG.E.256
                     struct alignas(32) F8 { float4 a, b; };
                     const float4* pr = planes + first + off0;
-#if TRN_PQ_IDEARLY
-                    ids = ld_tri(reinterpret_cast<const uint4*>(sc.prefs + first + off0)); // A/B: in flight next to the planes
-#endif
                     const F8 v0 = *reinterpret_cast<const F8*>(pr), v1 = *reinterpret_cast<const F8*>(pr + 2);
                     const float4 p0 = v0.a, p1 = v0.b, p2 = v1.a, p3 = v1.b;
 #else
@@ -490,7 +484,7 @@ __global__ void __launch_bounds__(128, TRN_PQ_MINBLOCKS) trace_pooled_kernel(
                         const bool keep = (static_cast<uint32_t>(k) < cnt) & ((A <= F) | ((B >= fmaf(lo, A, c1)) & (B <= fmaf(hi, A, c2))));
                         km |= keep ? (1u << k) : 0u;
                     }
-#if TRN_PQ_REFPLANES && !TRN_PQ_IDEARLY
+#if TRN_PQ_REFPLANES
                     if (km != 0u) ids = ld_tri(reinterpret_cast<const uint4*>(sc.prefs + first + off0)); // ids only for survivors
 #endif
                 }
